@@ -1,0 +1,184 @@
+/*
+ * mxf_b200.h -- C ABI of libmxf_b200.so: the sm_100a kernels behind the
+ * MXFusion variational-inference / Gaussian-process hot path.
+ *
+ * The reference (amzn/MXFusion) has no native code: every entry point below
+ * replaces an MXNet operator call that the reference issues through its `F`
+ * namespace.  The reference-side binding is a ctypes stub
+ * (INTEGRATION.md); the in-tree binding is mxfusion_b200/_lib.py.
+ *
+ * Conventions
+ *   - row-major, innermost dimension contiguous, batch-major over the
+ *     reference's leading sample axis S (components/variables/
+ *     runtime_variable.py:20-50).  Batch strides are given in ELEMENTS; a batch
+ *     stride of 0 broadcasts one matrix over all S samples
+ *     (runtime_variable.py:102-118 `arrays_as_samples`, without the copy).
+ *   - dtype: MXF_F32 (reference default, common/config.py:18) or MXF_F64
+ *     (what the reference's tests use).
+ *   - ownership: the caller owns every buffer, including workspaces.  The
+ *     library never allocates, frees or synchronises; all work is enqueued on
+ *     the cudaStream_t passed as `stream` (NULL = legacy default stream).
+ *   - errors: 0 = ok; negative = invalid argument (MXF_EINVAL...); positive =
+ *     the cudaError_t of the failed launch.  No exception or abort crosses the
+ *     ABI.  A non-positive-definite potrf input is reported through the
+ *     device-side `info` array (1-based index of the first bad pivot, 0 = ok).
+ *   - re-entrant: no global mutable state.
+ */
+#ifndef MXF_B200_H
+#define MXF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXF_F32 0
+#define MXF_F64 1
+
+#define MXF_OK 0
+#define MXF_EINVAL (-1)
+#define MXF_EDTYPE (-2)
+#define MXF_ENOTIMPL (-3)
+#define MXF_EWORKSPACE (-4)
+
+/* stationary kernel kinds: gp/kernels/rbf.py:71-72, matern.py:84-88,116-120,148-151 */
+#define MXF_KERN_RBF 0
+#define MXF_KERN_MATERN12 1
+#define MXF_KERN_MATERN32 2
+#define MXF_KERN_MATERN52 3
+
+int mxf_version(void);
+/* number of kernel launches enqueued by this library in this process so far */
+uint64_t mxf_launch_count(void);
+
+/* ---- covariance build ---------------------------------------------------
+ * Replaces StationaryKernel._compute_R2 + RBF/Matern._compute_K
+ * (gp/kernels/stationary.py:74-107, rbf.py:54-72, matern.py:67-151): the
+ * scale -> squared distance (|a|^2+|b|^2-2a.b) -> kernel -> store chain in ONE
+ * pass over the (S,N,N2) output.
+ *   X (S,N,D), X2 (S,N2,D) or NULL (then X2 := X, N2 := N),
+ *   ls (S,ls_len) with ls_len in {1, D}, var (S,1)  ->  out (S,N,N2), ldo = row stride of out.
+ *   diag_add (S,1) or NULL, diag_add_const: out[i][i] += diag_add[s] + diag_add_const
+ *   when X2 == NULL (the `+ eye*noise_var`, `+ eye*jitter` of gp_regression.py:55-60,
+ *   svgp_regression.py:70-72 folded into the store). */
+int mxf_kbuild_fwd(int kind, int dtype,
+                   const void* X, const void* X2, const void* ls, int ls_len, const void* var,
+                   const void* diag_add, double diag_add_const,
+                   void* out, int64_t ldo,
+                   int S, int N, int N2, int D,
+                   int64_t sX, int64_t sX2, int64_t sLs, int64_t sVar, int64_t sDiag, int64_t sOut,
+                   void* stream);
+
+/* Adjoint of mxf_kbuild_fwd (replaces MXNet autograd through the same ops).
+ *   G (S,N,N2) with row stride ldg -> dX (S,N,D) or NULL, dX2 (S,N2,D) or NULL,
+ *   dls (S,ls_len), dvar (S,1); every output is OVERWRITTEN (write, not add).
+ *   When X2 == NULL the symmetric contribution of both arguments goes to dX.
+ *   ws: workspace of mxf_kbuild_bwd_workspace_bytes() bytes. */
+size_t mxf_kbuild_bwd_workspace_bytes(int dtype, int S, int N, int N2, int D);
+int mxf_kbuild_bwd(int kind, int dtype,
+                   const void* X, const void* X2, const void* ls, int ls_len, const void* var,
+                   const void* G, int64_t ldg,
+                   void* dX, void* dX2, void* dls, void* dvar,
+                   int S, int N, int N2, int D,
+                   int64_t sX, int64_t sX2, int64_t sLs, int64_t sVar, int64_t sG,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---- dense linear algebra (replaces mx.nd.linalg.*) -----------------------
+ * gemm2 / syrk / trmm: C = alpha * op(A) op(B) + beta * C   (svgp_regression.py:76,82,89,90)
+ *   op(A) is m x k, op(B) is k x n, C is m x n; lda/ldb/ldc row strides; sA/sB/sC batch strides.
+ *   tri: 0 = full C; 1 = only tiles touching the lower triangle of C are computed
+ *   (syrk-type trailing update).  Elements strictly above those tiles are left untouched. */
+int mxf_gemm(int dtype, int transA, int transB, int m, int n, int k,
+             double alpha, const void* A, int64_t lda, int64_t sA,
+             const void* B, int64_t ldb, int64_t sB,
+             double beta, void* C, int64_t ldc, int64_t sC,
+             int S, int tri, void* stream);
+
+/* linalg.potrf (svgp_regression.py:83-84, gp_regression.py:61): in-place lower
+ * Cholesky of the S n x n matrices at A (row stride lda, batch stride sA); the
+ * strict upper triangle is zeroed (MXNet convention).  info: int32[S] on device. */
+int mxf_potrf(int dtype, void* A, int64_t lda, int64_t sA, int S, int n, int* info, void* stream);
+
+/* linalg.trsm, left side, lower triangular A (svgp_regression.py:85-87,92; gp_regression.py:66):
+ *   B := alpha * A^-1 B (transpose=0) or alpha * A^-T B (transpose=1); B is n x nrhs. */
+int mxf_trsm(int dtype, int transpose, int n, int nrhs, double alpha,
+             const void* A, int64_t lda, int64_t sA,
+             void* B, int64_t ldb, int64_t sB, int S, void* stream);
+
+/* Cholesky adjoint helper: out = phi(P) + phi(P)^T with phi = lower triangle, i.e. the
+ * symmetric matrix whose lower triangle (diagonal included) is copied from P. */
+int mxf_copy_ltu(int dtype, const void* P, int64_t ldp, int64_t sP,
+                 void* out, int64_t ldo, int64_t sO, int S, int n, void* stream);
+/* out = alpha * (A + A^T)  (symmetrise; in-place allowed only if out != A is false -> use distinct buffers) */
+int mxf_symmetrize(int dtype, double alpha, const void* A, int64_t lda, int64_t sA,
+                   void* out, int64_t ldo, int64_t sO, int S, int n, void* stream);
+/* out = tril(A) (mode 0, diagonal kept) / strictly-lower (mode 1); upper part zero-filled. */
+int mxf_tril(int dtype, int mode, const void* A, int64_t lda, int64_t sA,
+             void* out, int64_t ldo, int64_t sO, int S, int n, void* stream);
+/* out (n x m) = A^T, A is m x n. */
+int mxf_transpose(int dtype, const void* A, int64_t lda, int64_t sA,
+                  void* out, int64_t ldo, int64_t sO, int S, int m, int n, void* stream);
+
+/* ---- reductions (linalg.sumlogdiag, F.sum(F.square(.)), ...) ---------------
+ * svgp_regression.py:94-107, gp_regression.py:67-70.  One output scalar per sample. */
+#define MXF_RED_SUM 0      /* sum a                 */
+#define MXF_RED_SUMSQ 1    /* sum a*a               */
+#define MXF_RED_DOT 2      /* sum a*b               */
+#define MXF_RED_SUMLOG 3   /* sum log(a)            */
+/* a, b: (S, rows, cols) with row strides lda/ldb; out[s] = scale * reduce.  b may be NULL. */
+int mxf_reduce(int op, int dtype, const void* a, int64_t lda, int64_t sA,
+               const void* b, int64_t ldb, int64_t sB,
+               int S, int64_t rows, int64_t cols, double scale, void* out, void* stream);
+/* linalg.sumlogdiag(|A|) for n x n matrices: out[s] = sum_i log|A[s][i][i]|. */
+int mxf_sumlogdiag(int dtype, const void* A, int64_t lda, int64_t sA, int S, int n,
+                   void* out, void* stream);
+/* make_diagonal (util/customop.py:22-81) fused into its only consumer:
+ * A[s][i][i] += d[s][i] (+ c).  Used for S = syrk(W) + make_diagonal(diag). */
+int mxf_add_diag(int dtype, void* A, int64_t lda, int64_t sA, const void* d, int64_t sD,
+                 double c, int S, int n, void* stream);
+/* out[s][i] = A[s][i][i]  (backward of make_diagonal, customop.py:45-57). */
+int mxf_get_diag(int dtype, const void* A, int64_t lda, int64_t sA, void* out, int64_t sO,
+                 int S, int n, void* stream);
+
+/* ---- Normal distribution: MC-ELBO pieces (normal.py:52-92, factor_graph.py:223) ----
+ * Fused log-density + sample-mean + sum:
+ *   out[0] = scale * (1/S) * sum_{s,i} [ -0.5 log 2pi - 0.5 log v - (x-m)^2 / (2 v) ]
+ * x (Sx,n), m (Sm,n), v (Sv,n) with S = max(Sx,Sm,Sv); an operand with batch
+ * stride 0 is broadcast over samples.  out must be zero-initialised by the caller
+ * (accumulated with one atomic per CTA). */
+int mxf_normal_logpdf_sum(int dtype, const void* x, int64_t sX, const void* m, int64_t sM,
+                          const void* v, int64_t sV, int S, int64_t n, double scale,
+                          void* out, void* stream);
+/* Adjoint: gx/gm/gv (any may be NULL) receive d out / d x,m,v times gout[0];
+ * an operand broadcast over S gets the sum over samples.  Outputs are overwritten. */
+int mxf_normal_logpdf_sum_bwd(int dtype, const void* x, int64_t sX, const void* m, int64_t sM,
+                              const void* v, int64_t sV, int S, int64_t n, double scale,
+                              const void* gout, void* gx, void* gm, void* gv, void* stream);
+/* Reparameterised draw (normal.py:89-92): w[s][i] = eps[s][i]*sqrt(v[i]) + m[i].
+ * If eps == NULL a counter-based Philox4x32-10 standard-normal stream keyed by
+ * (seed, offset) is generated in-kernel and, if eps_out != NULL, stored for the adjoint. */
+int mxf_normal_reparam(int dtype, const void* eps, const void* m, int64_t sM, const void* v, int64_t sV,
+                       int S, int64_t n, uint64_t seed, uint64_t offset,
+                       void* w, void* eps_out, void* stream);
+
+/* ---- optimiser (mx.gluon.Trainer('adam').step(batch_size), minibatch_loop.py:71-91) ----
+ * One fused update over a flat parameter bucket:
+ *   g *= rescale; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *   w -= lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)
+ * step_count: device int32[1], incremented by the kernel (so the update can live in a CUDA graph). */
+int mxf_adam_step(int dtype, void* w, const void* g, void* m, void* v, int64_t n,
+                  double lr, double beta1, double beta2, double eps, double rescale,
+                  int* step_count, void* stream);
+
+/* ---- minibatch gather (gluon DataLoader batchify, minibatch_loop.py:68-70,78) ----
+ * out[r][:] = src[idx[off + r]][:] for r < rows; idx is int64 on device; bit-exact copy.
+ * `off` is read from device memory (int64[1]) so the gather can be replayed inside a CUDA graph. */
+int mxf_gather_rows(int dtype, const void* src, int64_t cols, const int64_t* idx, const int64_t* off,
+                    int64_t rows, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MXF_B200_H */

@@ -1,0 +1,443 @@
+// Reductions, small matrix utilities, the Normal-distribution MC-ELBO pieces, the fused Adam update and
+// the minibatch row gather.  Each replaces a run of elementwise/reduce MXNet operators on the reference's
+// hot path; the reference line ranges are given at each entry point in include/mxf_b200.h.
+#include <algorithm>
+#include "common.cuh"
+
+namespace mxf {
+
+// ------------------------------------------------------------------------------------------
+// reductions: out[s] = scale * sum_{r,c} f(a[s][r][c], b[s][r][c])
+// ------------------------------------------------------------------------------------------
+template <typename T, int OP>
+__device__ __forceinline__ T red_term(T a, T b) {
+    if (OP == MXF_RED_SUM) return a;
+    if (OP == MXF_RED_SUMSQ) return a * a;
+    if (OP == MXF_RED_DOT) return a * b;
+    return Num<T>::log_(a);
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256)
+reduce_kernel(const T* __restrict__ a, int64_t lda, int64_t sA, const T* __restrict__ b, int64_t ldb,
+              int64_t sB, int64_t rows, int64_t cols, int64_t rows_per_block, T scale, T* __restrict__ out,
+              int use_atomic) {
+    __shared__ T red[32];
+    const int s = blockIdx.y;
+    const T* as = a + (int64_t)s * sA;
+    const T* bs = (OP == MXF_RED_DOT) ? b + (int64_t)s * sB : nullptr;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    T acc = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const T* ar = as + r * lda;
+        const T* br = (OP == MXF_RED_DOT) ? bs + r * ldb : nullptr;
+        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x)
+            acc += red_term<T, OP>(ar[c], (OP == MXF_RED_DOT) ? br[c] : T(0));
+    }
+    T tot = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        if (use_atomic) atomicAdd(&out[s], scale * tot);
+        else out[s] = scale * tot;
+    }
+}
+
+template <typename T>
+__global__ void fill_kernel(T* p, int64_t n, T v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+template <typename T>
+static int reduce_impl(int op, const T* a, int64_t lda, int64_t sA, const T* b, int64_t ldb, int64_t sB, int S,
+                       int64_t rows, int64_t cols, double scale, T* out, cudaStream_t st) {
+    if (S == 0) return MXF_OK;
+    // collapse contiguous matrices into long rows so that a block streams a contiguous range
+    if (lda == cols && (op != MXF_RED_DOT || ldb == cols) && rows > 1) {
+        const int64_t total = rows * cols;
+        int64_t chunk = 8192;
+        while (total % chunk != 0 && chunk > 1) chunk >>= 1;
+        if (chunk >= 256) { rows = total / chunk; cols = chunk; lda = chunk; ldb = chunk; }
+    }
+    int64_t nblk = std::min<int64_t>(std::max<int64_t>(1, rows), (int64_t)2 * kNumSMs);
+    int64_t rpb = (rows + nblk - 1) / nblk;
+    if (rpb < 1) rpb = 1;
+    nblk = std::max<int64_t>(1, (rows + rpb - 1) / rpb);
+    const int use_atomic = nblk > 1;
+    int launches = 1;
+    if (use_atomic) { fill_kernel<T><<<cdiv(S, 128), 128, 0, st>>>(out, S, T(0)); ++launches; }
+    dim3 grid((unsigned)nblk, S);
+#define MXF_RED_CASE(OP)                                                                                      \
+    case OP:                                                                                                  \
+        reduce_kernel<T, OP><<<grid, 256, 0, st>>>(a, lda, sA, b, ldb, sB, rows, cols, rpb, (T)scale, out, use_atomic); \
+        break;
+    switch (op) {
+        MXF_RED_CASE(MXF_RED_SUM)
+        MXF_RED_CASE(MXF_RED_SUMSQ)
+        MXF_RED_CASE(MXF_RED_DOT)
+        MXF_RED_CASE(MXF_RED_SUMLOG)
+        default: return MXF_EINVAL;
+    }
+#undef MXF_RED_CASE
+    return after_launch(launches);
+}
+
+template <typename T>
+__global__ void sumlogdiag_kernel(const T* __restrict__ A, int64_t lda, int64_t sA, int n, T* __restrict__ out) {
+    __shared__ T red[32];
+    const int s = blockIdx.x;
+    T acc = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        T d = A[(int64_t)s * sA + (int64_t)i * lda + i];
+        acc += Num<T>::log_(d < T(0) ? -d : d);
+    }
+    T tot = block_sum(acc, red);
+    if (threadIdx.x == 0) out[s] = tot;
+}
+
+template <typename T>
+__global__ void add_diag_kernel(T* __restrict__ A, int64_t lda, int64_t sA, const T* __restrict__ d, int64_t sD,
+                                T c, int n) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(int64_t)s * sA + (int64_t)i * lda + i] += (d ? d[(int64_t)s * sD + i] : T(0)) + c;
+}
+
+template <typename T>
+__global__ void get_diag_kernel(const T* __restrict__ A, int64_t lda, int64_t sA, T* __restrict__ out, int64_t sO,
+                                int n) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[(int64_t)s * sO + i] = A[(int64_t)s * sA + (int64_t)i * lda + i];
+}
+
+// MODE 0: copy_ltu (symmetric from lower), 1: alpha*(A + A^T), 2: tril keep diag, 3: strictly lower, 4: transpose
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+square_tile_kernel(const T* __restrict__ A, int64_t lda, int64_t sA, T* __restrict__ out, int64_t ldo, int64_t sO,
+                   int m, int n, T alpha) {
+    // out is (n x m) for MODE 4, else (m x n) with m == n.  32x32 tiles, 32x8 threads.
+    __shared__ T tile[32][33];
+    const int s = blockIdx.z;
+    const T* As = A + (int64_t)s * sA;
+    T* Os = out + (int64_t)s * sO;
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // output tile origin: rows by.., cols bx..
+    // stage the transposed source tile: tile[c][r] = A[bx + c][by + r]  (A^T restricted to the out tile)
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int ai = bx + r, aj = by + threadIdx.x;       // read A[ai][aj] coalesced along aj
+        const int rows_a = (MODE == 4) ? m : m, cols_a = (MODE == 4) ? n : n;
+        tile[r][threadIdx.x] = (ai < rows_a && aj < cols_a) ? As[(int64_t)ai * lda + aj] : T(0);
+    }
+    __syncthreads();
+    const int orow_lim = (MODE == 4) ? n : m, ocol_lim = (MODE == 4) ? m : n;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = by + r, j = bx + threadIdx.x;          // output element (i, j)
+        if (i >= orow_lim || j >= ocol_lim) continue;
+        const T at = tile[threadIdx.x][r];                   // A[j][i]
+        T v;
+        if (MODE == 4) {
+            v = at;
+        } else {
+            const T aa = As[(int64_t)i * lda + j];           // A[i][j]
+            if (MODE == 0) v = (j <= i) ? aa : at;
+            else if (MODE == 1) v = alpha * (aa + at);
+            else if (MODE == 2) v = (j <= i) ? aa : T(0);
+            else v = (j < i) ? aa : T(0);
+        }
+        Os[(int64_t)i * ldo + j] = v;
+    }
+}
+
+template <typename T, int MODE>
+static int square_tile_launch(const T* A, int64_t lda, int64_t sA, T* out, int64_t ldo, int64_t sO, int S, int m,
+                              int n, double alpha, cudaStream_t st) {
+    if (S == 0 || m == 0 || n == 0) return MXF_OK;
+    const int orows = (MODE == 4) ? n : m, ocols = (MODE == 4) ? m : n;
+    dim3 grid(cdiv(ocols, 32), cdiv(orows, 32), S);
+    square_tile_kernel<T, MODE><<<grid, dim3(32, 8), 0, st>>>(A, lda, sA, out, ldo, sO, m, n, (T)alpha);
+    return after_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// Normal distribution
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+normal_logpdf_sum_kernel(const T* __restrict__ x, int64_t sX, const T* __restrict__ m, int64_t sM,
+                         const T* __restrict__ v, int64_t sV, int S, int64_t n, T scale, T* __restrict__ out) {
+    __shared__ T red[32];
+    const T c0 = T(-0.91893853320467274178);   // -0.5 log(2 pi)
+    T acc = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        for (int s = 0; s < S; ++s) {
+            const T xv = x[s * sX + i], mv = m[s * sM + i], vv = v[s * sV + i];
+            const T d = xv - mv;
+            acc += c0 - T(0.5) * Num<T>::log_(vv) - d * d / (T(2) * vv);
+        }
+    }
+    T tot = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, tot * scale / T(S));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+normal_logpdf_sum_bwd_kernel(const T* __restrict__ x, int64_t sX, const T* __restrict__ m, int64_t sM,
+                             const T* __restrict__ v, int64_t sV, int S, int64_t n, T scale,
+                             const T* __restrict__ gout, T* __restrict__ gx, T* __restrict__ gm,
+                             T* __restrict__ gv) {
+    const T g = gout[0] * scale / T(S);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T ax = 0, am = 0, av = 0;
+        for (int s = 0; s < S; ++s) {
+            const T xv = x[s * sX + i], mv = m[s * sM + i], vv = v[s * sV + i];
+            const T d = xv - mv;
+            const T dx = -d / vv * g;                                         // d/dx
+            const T dv = (T(-0.5) / vv + T(0.5) * d * d / (vv * vv)) * g;     // d/dv
+            if (gx) { if (sX) gx[s * n + i] = dx; else ax += dx; }
+            if (gm) { if (sM) gm[s * n + i] = -dx; else am -= dx; }
+            if (gv) { if (sV) gv[s * n + i] = dv; else av += dv; }
+        }
+        if (gx && !sX) gx[i] = ax;
+        if (gm && !sM) gm[i] = am;
+        if (gv && !sV) gv[i] = av;
+    }
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (idx_lo, idx_hi, offset_lo, offset_hi), key = seed.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint64_t idx, uint64_t offset, uint64_t seed, uint32_t (&out)[4]) {
+    uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+normal_reparam_kernel(const T* __restrict__ eps, const T* __restrict__ m, int64_t sM, const T* __restrict__ v,
+                      int64_t sV, int S, int64_t n, uint64_t seed, uint64_t offset, T* __restrict__ w,
+                      T* __restrict__ eps_out) {
+    const int64_t total = (int64_t)S * n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (eps) {
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+            const int64_t s = e / n, i = e - s * n;
+            w[e] = fma(eps[e], Num<T>::sqrt_(v[s * sV + i]), m[s * sM + i]);
+        }
+        return;
+    }
+    // four normals per Philox call: thread handles elements 4q .. 4q+3
+    const int64_t quads = (total + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+        uint32_t r[4];
+        philox4x32_10((uint64_t)q, offset, seed, r);
+        float z[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float u1 = ((float)r[2 * h] + 1.0f) * 2.3283064365386963e-10f;       // (0,1]
+            const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;            // [0,1)
+            const float rad = sqrtf(-2.0f * logf(u1));
+            float sn, cs;
+            sincospif(2.0f * u2, &sn, &cs);
+            z[2 * h] = rad * cs;
+            z[2 * h + 1] = rad * sn;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int64_t e = 4 * q + t;
+            if (e < total) {
+                const int64_t s = e / n, i = e - s * n;
+                const T ev = (T)z[t];
+                if (eps_out) eps_out[e] = ev;
+                w[e] = fma(ev, Num<T>::sqrt_(v[s * sV + i]), m[s * sM + i]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam, gather
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+adam_kernel(T* __restrict__ w, const T* __restrict__ g, T* __restrict__ m, T* __restrict__ v, int64_t n,
+            double lr, double b1, double b2, double eps, double rescale, const int* __restrict__ step_count) {
+    const int t = step_count[0] + 1;
+    const double lr_t = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
+    const T lrt = (T)lr_t, B1 = (T)b1, B2 = (T)b2, E = (T)eps, R = (T)rescale;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T gi = g[i] * R;
+        const T mi = B1 * m[i] + (T(1) - B1) * gi;
+        const T vi = B2 * v[i] + (T(1) - B2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        w[i] -= lrt * mi / (Num<T>::sqrt_(vi) + E);
+    }
+}
+
+__global__ void incr_kernel(int* c) { c[0] += 1; }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const T* __restrict__ src, int64_t cols, const int64_t* __restrict__ idx,
+                   const int64_t* __restrict__ off, int64_t rows, T* __restrict__ out) {
+    const int64_t o = off ? off[0] : 0;
+    const int64_t total = rows * cols;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t r = e / cols, c = e - r * cols;
+        out[e] = src[idx[o + r] * cols + c];
+    }
+}
+
+static inline int grid_for(int64_t n, int threads = 256) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)8 * kNumSMs));
+}
+
+}  // namespace mxf
+
+using namespace mxf;
+
+std::atomic<uint64_t> mxf::g_launches{0};
+
+extern "C" int mxf_version(void) { return 100; }
+extern "C" uint64_t mxf_launch_count(void) { return g_launches.load(); }
+
+extern "C" int mxf_reduce(int op, int dtype, const void* a, int64_t lda, int64_t sA, const void* b, int64_t ldb,
+                          int64_t sB, int S, int64_t rows, int64_t cols, double scale, void* out, void* stream) {
+    if (!a || !out || rows < 0 || cols < 0 || S < 0 || (op == MXF_RED_DOT && !b)) return MXF_EINVAL;
+    if (S > 65535) return MXF_ENOTIMPL;
+    MXF_DISPATCH_DTYPE(dtype, return reduce_impl<T>(op, (const T*)a, lda, sA, (const T*)b, ldb, sB, S, rows, cols,
+                                                    scale, (T*)out, (cudaStream_t)stream));
+}
+
+extern "C" int mxf_sumlogdiag(int dtype, const void* A, int64_t lda, int64_t sA, int S, int n, void* out,
+                              void* stream) {
+    if (!A || !out || n < 0 || S < 0) return MXF_EINVAL;
+    if (S == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, sumlogdiag_kernel<T><<<S, 256, 0, (cudaStream_t)stream>>>((const T*)A, lda, sA, n,
+                                                                                       (T*)out));
+    return after_launch();
+}
+
+extern "C" int mxf_add_diag(int dtype, void* A, int64_t lda, int64_t sA, const void* d, int64_t sD, double c,
+                            int S, int n, void* stream) {
+    if (!A || n < 0 || S < 0) return MXF_EINVAL;
+    if (S == 0 || n == 0) return MXF_OK;
+    if (S > 65535) return MXF_ENOTIMPL;
+    dim3 grid(cdiv(n, 256), S);
+    MXF_DISPATCH_DTYPE(dtype, add_diag_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((T*)A, lda, sA,
+                                                                                        (const T*)d, sD, (T)c, n));
+    return after_launch();
+}
+
+extern "C" int mxf_get_diag(int dtype, const void* A, int64_t lda, int64_t sA, void* out, int64_t sO, int S, int n,
+                            void* stream) {
+    if (!A || !out || n < 0 || S < 0) return MXF_EINVAL;
+    if (S == 0 || n == 0) return MXF_OK;
+    if (S > 65535) return MXF_ENOTIMPL;
+    dim3 grid(cdiv(n, 256), S);
+    MXF_DISPATCH_DTYPE(dtype, get_diag_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)A, lda, sA,
+                                                                                        (T*)out, sO, n));
+    return after_launch();
+}
+
+extern "C" int mxf_copy_ltu(int dtype, const void* P, int64_t ldp, int64_t sP, void* out, int64_t ldo, int64_t sO,
+                            int S, int n, void* stream) {
+    if (!P || !out || P == out) return MXF_EINVAL;
+    if (S > 65535) return MXF_ENOTIMPL;
+    MXF_DISPATCH_DTYPE(dtype, return (square_tile_launch<T, 0>((const T*)P, ldp, sP, (T*)out, ldo, sO, S, n, n, 1.0,
+                                                               (cudaStream_t)stream)));
+}
+
+extern "C" int mxf_symmetrize(int dtype, double alpha, const void* A, int64_t lda, int64_t sA, void* out,
+                              int64_t ldo, int64_t sO, int S, int n, void* stream) {
+    if (!A || !out || A == out) return MXF_EINVAL;
+    if (S > 65535) return MXF_ENOTIMPL;
+    MXF_DISPATCH_DTYPE(dtype, return (square_tile_launch<T, 1>((const T*)A, lda, sA, (T*)out, ldo, sO, S, n, n,
+                                                               alpha, (cudaStream_t)stream)));
+}
+
+extern "C" int mxf_tril(int dtype, int mode, const void* A, int64_t lda, int64_t sA, void* out, int64_t ldo,
+                        int64_t sO, int S, int n, void* stream) {
+    if (!A || !out || A == out || (mode != 0 && mode != 1)) return MXF_EINVAL;
+    if (S > 65535) return MXF_ENOTIMPL;
+    if (mode == 0)
+        MXF_DISPATCH_DTYPE(dtype, return (square_tile_launch<T, 2>((const T*)A, lda, sA, (T*)out, ldo, sO, S, n, n,
+                                                                   1.0, (cudaStream_t)stream)));
+    MXF_DISPATCH_DTYPE(dtype, return (square_tile_launch<T, 3>((const T*)A, lda, sA, (T*)out, ldo, sO, S, n, n, 1.0,
+                                                               (cudaStream_t)stream)));
+}
+
+extern "C" int mxf_transpose(int dtype, const void* A, int64_t lda, int64_t sA, void* out, int64_t ldo, int64_t sO,
+                             int S, int m, int n, void* stream) {
+    if (!A || !out || A == out) return MXF_EINVAL;
+    if (S > 65535) return MXF_ENOTIMPL;
+    MXF_DISPATCH_DTYPE(dtype, return (square_tile_launch<T, 4>((const T*)A, lda, sA, (T*)out, ldo, sO, S, m, n, 1.0,
+                                                               (cudaStream_t)stream)));
+}
+
+extern "C" int mxf_normal_logpdf_sum(int dtype, const void* x, int64_t sX, const void* m, int64_t sM,
+                                     const void* v, int64_t sV, int S, int64_t n, double scale, void* out,
+                                     void* stream) {
+    if (!x || !m || !v || !out || S <= 0 || n < 0) return MXF_EINVAL;
+    if (n == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, normal_logpdf_sum_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)x, sX, (const T*)m, sM, (const T*)v, sV, S, n, (T)scale, (T*)out));
+    return after_launch();
+}
+
+extern "C" int mxf_normal_logpdf_sum_bwd(int dtype, const void* x, int64_t sX, const void* m, int64_t sM,
+                                         const void* v, int64_t sV, int S, int64_t n, double scale,
+                                         const void* gout, void* gx, void* gm, void* gv, void* stream) {
+    if (!x || !m || !v || !gout || S <= 0 || n < 0) return MXF_EINVAL;
+    if (n == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, normal_logpdf_sum_bwd_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)x, sX, (const T*)m, sM, (const T*)v, sV, S, n, (T)scale,
+                                  (const T*)gout, (T*)gx, (T*)gm, (T*)gv));
+    return after_launch();
+}
+
+extern "C" int mxf_normal_reparam(int dtype, const void* eps, const void* m, int64_t sM, const void* v, int64_t sV,
+                                  int S, int64_t n, uint64_t seed, uint64_t offset, void* w, void* eps_out,
+                                  void* stream) {
+    if (!m || !v || !w || S <= 0 || n < 0) return MXF_EINVAL;
+    if (n == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, normal_reparam_kernel<T><<<grid_for((int64_t)S * n), 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)eps, (const T*)m, sM, (const T*)v, sV, S, n, seed, offset, (T*)w,
+                                  (T*)eps_out));
+    return after_launch();
+}
+
+extern "C" int mxf_adam_step(int dtype, void* w, const void* g, void* m, void* v, int64_t n, double lr,
+                             double beta1, double beta2, double eps, double rescale, int* step_count,
+                             void* stream) {
+    if (!w || !g || !m || !v || !step_count || n < 0) return MXF_EINVAL;
+    if (n > 0)
+        MXF_DISPATCH_DTYPE(dtype, adam_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
+                                      (T*)w, (const T*)g, (T*)m, (T*)v, n, lr, beta1, beta2, eps, rescale,
+                                      step_count));
+    incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_count);
+    return after_launch(2);
+}
+
+extern "C" int mxf_gather_rows(int dtype, const void* src, int64_t cols, const int64_t* idx, const int64_t* off,
+                               int64_t rows, void* out, void* stream) {
+    if (!src || !idx || !out || rows < 0 || cols <= 0) return MXF_EINVAL;
+    if (rows == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, gather_rows_kernel<T><<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)src, cols, idx, off, rows, (T*)out));
+    return after_launch();
+}

@@ -1,0 +1,187 @@
+// Batched row-major GEMM on the FP32/FP64 FMA pipes:  C = alpha * op(A) op(B) + beta * C.
+//
+// Replaces mx.nd.linalg.gemm2 / syrk / trmm call sites of the reference
+// (modules/gp_modules/svgp_regression.py:76,82,89,90; gp/kernels/stationary.py:94,102 are folded into
+// kbuild.cu instead) and is the update engine of the blocked potrf / trsm in potrf.cu / trsm.cu.
+// This is the exact-precision path (f32 FMA, f64 FMA); the f32 tensor-core path (3xTF32 on tcgen05)
+// lives in gemm_tc.cu and is selected by mxf_gemm for large f32 problems when enabled.
+//
+// Tiling: CTA tile BM x BN, K-step BK, 256 threads, each thread a (2*H) x (2*H) micro-tile split
+// into four H x H quadrants (rows ty*H and BM/2+ty*H; columns tx*H and BN/2+tx*H) so that the
+// shared-memory reads are 16-byte and bank-conflict free.  Global tiles are prefetched into
+// registers while the current tile is multiplied (software double buffering).
+#include <algorithm>
+#include "common.cuh"
+
+namespace mxf {
+
+template <typename T, int BM, int BN, int BK>
+struct GemmCfg {
+    static constexpr int THREADS = 256;
+    static constexpr int H = BM / 32;              // quadrant edge: 4 (f32, 128) or 2 (f64, 64)
+    static constexpr int PAD = 4;
+    static constexpr int LDS_A = BM + PAD;
+    static constexpr int LDS_B = BN + PAD;
+    static constexpr int EA = BM * BK / THREADS;   // elements of the A tile per thread
+    static constexpr int EB = BN * BK / THREADS;
+};
+
+// Load this thread's slice of a (MN x BK) operand tile into registers.
+// kcontig: the operand is stored with K contiguous (A not transposed / B transposed).
+template <typename T, int BMN, int BK, int E>
+__device__ __forceinline__ void load_tile(T (&reg)[E], const T* __restrict__ P, int64_t ld, bool kcontig,
+                                          int mn0, int k0, int mn_lim, int k_lim) {
+    const int t = threadIdx.x;
+    if (kcontig) {
+        // thread -> (row = t / (BK/E), kk = (t % (BK/E)) * E .. +E)
+        constexpr int TPR = BK / E;
+        const int r = t / TPR, kk = (t % TPR) * E;
+        const int mn = mn0 + r;
+        const T* src = P + (int64_t)mn * ld + k0 + kk;
+#pragma unroll
+        for (int e = 0; e < E; ++e) reg[e] = (mn < mn_lim && k0 + kk + e < k_lim) ? src[e] : T(0);
+    } else {
+        // thread -> (kk = t / (BMN/E), mn = (t % (BMN/E)) * E .. +E)
+        constexpr int TPK = BMN / E;
+        const int kk = t / TPK, c = (t % TPK) * E;
+        const T* src = P + (int64_t)(k0 + kk) * ld + mn0 + c;
+#pragma unroll
+        for (int e = 0; e < E; ++e) reg[e] = (k0 + kk < k_lim && mn0 + c + e < mn_lim) ? src[e] : T(0);
+    }
+}
+
+template <typename T, int BMN, int BK, int E, int LDS>
+__device__ __forceinline__ void store_tile(const T (&reg)[E], T* __restrict__ sm, bool kcontig) {
+    const int t = threadIdx.x;
+    if (kcontig) {
+        constexpr int TPR = BK / E;
+        const int r = t / TPR, kk = (t % TPR) * E;
+#pragma unroll
+        for (int e = 0; e < E; ++e) sm[(kk + e) * LDS + r] = reg[e];
+    } else {
+        constexpr int TPK = BMN / E;
+        const int kk = t / TPK, c = (t % TPK) * E;
+#pragma unroll
+        for (int e = 0; e < E; ++e) sm[kk * LDS + c + e] = reg[e];
+    }
+}
+
+template <typename T, int BM, int BN, int BK>
+__global__ void __launch_bounds__(256)
+gemm_kernel(int transA, int transB, int m, int n, int k, T alpha, const T* __restrict__ A, int64_t lda,
+            int64_t sA, const T* __restrict__ B, int64_t ldb, int64_t sB, T beta, T* __restrict__ C,
+            int64_t ldc, int64_t sC, int tri) {
+    using Cfg = GemmCfg<T, BM, BN, BK>;
+    constexpr int H = Cfg::H;
+    __shared__ __align__(16) T As[2][BK * Cfg::LDS_A];
+    __shared__ __align__(16) T Bs[2][BK * Cfg::LDS_B];
+
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    if (tri && j0 > i0 + BM - 1) return;
+    const int s = blockIdx.z;
+    A += (int64_t)s * sA;
+    B += (int64_t)s * sB;
+    C += (int64_t)s * sC;
+
+    const bool a_kc = (transA == 0), b_kc = (transB != 0);
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+
+    T acc[2 * H][2 * H];
+#pragma unroll
+    for (int r = 0; r < 2 * H; ++r)
+#pragma unroll
+        for (int c = 0; c < 2 * H; ++c) acc[r][c] = T(0);
+
+    T ra[Cfg::EA], rb[Cfg::EB];
+    load_tile<T, BM, BK, Cfg::EA>(ra, A, lda, a_kc, i0, 0, m, k);
+    load_tile<T, BN, BK, Cfg::EB>(rb, B, ldb, b_kc, j0, 0, n, k);
+    store_tile<T, BM, BK, Cfg::EA, Cfg::LDS_A>(ra, As[0], a_kc);
+    store_tile<T, BN, BK, Cfg::EB, Cfg::LDS_B>(rb, Bs[0], b_kc);
+    __syncthreads();
+
+    int buf = 0;
+    for (int k0 = 0; k0 < k; k0 += BK) {
+        const bool more = k0 + BK < k;
+        if (more) {
+            load_tile<T, BM, BK, Cfg::EA>(ra, A, lda, a_kc, i0, k0 + BK, m, k);
+            load_tile<T, BN, BK, Cfg::EB>(rb, B, ldb, b_kc, j0, k0 + BK, n, k);
+        }
+        const T* as = As[buf];
+        const T* bs = Bs[buf];
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            T a[2 * H], b[2 * H];
+#pragma unroll
+            for (int e = 0; e < H; ++e) {
+                a[e] = as[kk * Cfg::LDS_A + ty * H + e];
+                a[H + e] = as[kk * Cfg::LDS_A + BM / 2 + ty * H + e];
+                b[e] = bs[kk * Cfg::LDS_B + tx * H + e];
+                b[H + e] = bs[kk * Cfg::LDS_B + BN / 2 + tx * H + e];
+            }
+#pragma unroll
+            for (int r = 0; r < 2 * H; ++r)
+#pragma unroll
+                for (int c = 0; c < 2 * H; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+        }
+        if (more) {
+            store_tile<T, BM, BK, Cfg::EA, Cfg::LDS_A>(ra, As[buf ^ 1], a_kc);
+            store_tile<T, BN, BK, Cfg::EB, Cfg::LDS_B>(rb, Bs[buf ^ 1], b_kc);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2 * H; ++r) {
+        const int i = i0 + (r < H ? ty * H + r : BM / 2 + ty * H + (r - H));
+        if (i >= m) continue;
+#pragma unroll
+        for (int c = 0; c < 2 * H; ++c) {
+            const int j = j0 + (c < H ? tx * H + c : BN / 2 + tx * H + (c - H));
+            if (j >= n) continue;
+            T* dst = C + (int64_t)i * ldc + j;
+            T v = alpha * acc[r][c];
+            if (beta != T(0)) v = fma(beta, *dst, v);
+            *dst = v;
+        }
+    }
+}
+
+template <typename T>
+int gemm_simt(int transA, int transB, int m, int n, int k, double alpha, const T* A, int64_t lda, int64_t sA,
+              const T* B, int64_t ldb, int64_t sB, double beta, T* C, int64_t ldc, int64_t sC, int S, int tri,
+              cudaStream_t st) {
+    if (m == 0 || n == 0 || S == 0) return MXF_OK;
+    if constexpr (sizeof(T) == 4) {
+        constexpr int BM = 128, BN = 128, BK = 16;
+        dim3 grid(cdiv(n, BN), cdiv(m, BM), S);
+        gemm_kernel<T, BM, BN, BK><<<grid, 256, 0, st>>>(transA, transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB,
+                                                        (T)beta, C, ldc, sC, tri);
+    } else {
+        constexpr int BM = 64, BN = 64, BK = 16;
+        dim3 grid(cdiv(n, BN), cdiv(m, BM), S);
+        gemm_kernel<T, BM, BN, BK><<<grid, 256, 0, st>>>(transA, transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB,
+                                                        (T)beta, C, ldc, sC, tri);
+    }
+    return after_launch();
+}
+
+template int gemm_simt<float>(int, int, int, int, int, double, const float*, int64_t, int64_t, const float*,
+                              int64_t, int64_t, double, float*, int64_t, int64_t, int, int, cudaStream_t);
+template int gemm_simt<double>(int, int, int, int, int, double, const double*, int64_t, int64_t, const double*,
+                               int64_t, int64_t, double, double*, int64_t, int64_t, int, int, cudaStream_t);
+
+}  // namespace mxf
+
+using namespace mxf;
+
+extern "C" int mxf_gemm(int dtype, int transA, int transB, int m, int n, int k, double alpha, const void* A,
+                        int64_t lda, int64_t sA, const void* B, int64_t ldb, int64_t sB, double beta, void* C,
+                        int64_t ldc, int64_t sC, int S, int tri, void* stream) {
+    if (m < 0 || n < 0 || k < 0 || S < 0 || !C) return MXF_EINVAL;
+    if (k > 0 && (!A || !B)) return MXF_EINVAL;
+    if (S > 65535) return MXF_ENOTIMPL;
+    MXF_DISPATCH_DTYPE(dtype, return gemm_simt<T>(transA, transB, m, n, k, alpha, (const T*)A, lda, sA,
+                                                  (const T*)B, ldb, sB, beta, (T*)C, ldc, sC, S, tri,
+                                                  (cudaStream_t)stream));
+}
