@@ -127,6 +127,7 @@ int mxf_transpose(int dtype, const void* A, int64_t lda, int64_t sA,
 #define MXF_RED_SUMSQ 1    /* sum a*a               */
 #define MXF_RED_DOT 2      /* sum a*b               */
 #define MXF_RED_SUMLOG 3   /* sum log(a)            */
+#define MXF_RED_SUMSQDIFF 4 /* sum (a-b)^2          */
 /* a, b: (S, rows, cols) with row strides lda/ldb; out[s] = scale * reduce.  b may be NULL. */
 int mxf_reduce(int op, int dtype, const void* a, int64_t lda, int64_t sA,
                const void* b, int64_t ldb, int64_t sB,
@@ -141,6 +142,30 @@ int mxf_add_diag(int dtype, void* A, int64_t lda, int64_t sA, const void* d, int
 /* out[s][i] = A[s][i][i]  (backward of make_diagonal, customop.py:45-57). */
 int mxf_get_diag(int dtype, const void* A, int64_t lda, int64_t sA, void* out, int64_t sO,
                  int S, int n, void* stream);
+
+/* out[s] = a[s] * X[s] + b[s] * Y[s] elementwise over n elements per sample; a, b are DEVICE scalars
+ * (one per sample; NULL = 1 for a, 0 for b and then Y may be NULL) so that coefficients that depend on
+ * learnable parameters or on the upstream gradient never visit the host.  sX/sY/sO batch strides. */
+int mxf_axpby_dev(int dtype, const void* a, const void* X, int64_t sX, const void* b, const void* Y, int64_t sY,
+                  void* out, int64_t sO, int S, int64_t n, void* stream);
+
+/* Softplus parameter transform (components/variables/var_trans.py:63-91, applied to every constrained
+ * parameter on every forward, inference_alg.py:79-80): y = log(1 + exp(x)) + offset, overflow-safe;
+ * adjoint gx = gy * sigmoid(x). */
+int mxf_softplus_fwd(int dtype, const void* x, double offset, void* y, int64_t n, void* stream);
+int mxf_softplus_bwd(int dtype, const void* x, const void* gy, void* gx, int64_t n, void* stream);
+
+/* ---- SVGP bound, adjoint assembly (analytic gradient of svgp_regression.py:43-109) ----
+ * With Phi = A A^T (A = L^-1 Kuf), T = C C^T (C = L^-1 Ls), U = Phi T, mt = L^-1 mu (M x P),
+ * v = A (Y - A^T mt) (M x P) and per-sample device coefficients coef[s][0..5] =
+ * {gP/2, c1 = g*scale*P*beta/2, g/2, g*scale*beta/2, g*scale*P*beta, g*scale*beta} this writes the three
+ * symmetric M x M matrices whose two-/one-sided solves with L give the gradients wrt Kuu, S and Kuf:
+ *   E   = coef2 mt mt^T + coef0 (T - I) - c1 Phi + c1 (U + U^T) - coef3 (v mt^T + mt v^T)
+ *   E_S = coef0 I + c1 Phi
+ *   E_R = -coef4 (T - I) - coef5 mt mt^T
+ * into out (S, M, 3M) as [E | E_S | E_R] (row stride 3M). */
+int mxf_svgp_bwd_assemble(int dtype, const void* Phi, const void* T, const void* U, const void* mt, const void* v,
+                          const void* coef, void* out, int S, int M, int P, void* stream);
 
 /* ---- Normal distribution: MC-ELBO pieces (normal.py:52-92, factor_graph.py:223) ----
  * Fused log-density + sample-mean + sum:

@@ -42,6 +42,10 @@ def _declare(lib):
         'mxf_sumlogdiag': (i, [i, p, l, l, i, i, p, p]),
         'mxf_add_diag': (i, [i, p, l, l, p, l, d, i, i, p]),
         'mxf_get_diag': (i, [i, p, l, l, p, l, i, i, p]),
+        'mxf_axpby_dev': (i, [i, p, p, l, p, p, l, p, l, i, l, p]),
+        'mxf_softplus_fwd': (i, [i, p, d, p, l, p]),
+        'mxf_softplus_bwd': (i, [i, p, p, p, l, p]),
+        'mxf_svgp_bwd_assemble': (i, [i, p, p, p, p, p, p, p, i, i, i, p]),
         'mxf_normal_logpdf_sum': (i, [i, p, l, p, l, p, l, i, l, d, p, p]),
         'mxf_normal_logpdf_sum_bwd': (i, [i, p, l, p, l, p, l, i, l, d, p, p, p, p, p]),
         'mxf_normal_reparam': (i, [i, p, p, l, p, l, i, l, u, u, p, p, p]),

@@ -1,0 +1,326 @@
+"""Thin tensor-level wrappers over the C ABI (include/mxf_b200.h).
+
+Every function takes CUDA tensors that carry the reference's leading sample
+axis S (components/variables/runtime_variable.py:20-50), enqueues kernels on
+the current torch stream and returns torch tensors.  No autograd here (see
+ops.py) and no fallback: a CPU tensor or a missing library raises.
+"""
+import torch
+
+from . import _lib
+from ._lib import lib, ptr, stream_ptr, check, dtype_code, require_cuda
+
+RBF, MATERN12, MATERN32, MATERN52 = 0, 1, 2, 3
+RED_SUM, RED_SUMSQ, RED_DOT, RED_SUMLOG, RED_SUMSQDIFF = 0, 1, 2, 3, 4
+
+
+def _bstride(t, S):
+    """Batch stride in elements; 0 broadcasts a single sample over S."""
+    return 0 if t.shape[0] == 1 and S > 1 else (t.stride(0) if t.shape[0] > 1 else 0)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def kbuild_fwd(kind, X, X2, ls, var, diag_add=None, diag_const=0.0, out=None):
+    """K (S,N,N2) for X (Sx,N,D), X2 (Sx2,N2,D) or None, ls (Sl,1|D), var (Sv,1)."""
+    require_cuda(X, X2, ls, var, diag_add)
+    X, ls, var = _c(X), _c(ls), _c(var)
+    X2 = None if X2 is None else _c(X2)
+    diag_add = None if diag_add is None else _c(diag_add)
+    S = max(X.shape[0], ls.shape[0], var.shape[0], 1 if X2 is None else X2.shape[0],
+            1 if diag_add is None else diag_add.shape[0])
+    N, D = X.shape[1], X.shape[2]
+    N2 = N if X2 is None else X2.shape[1]
+    if out is None:
+        out = torch.empty((S, N, N2), dtype=X.dtype, device=X.device)
+    check(lib().mxf_kbuild_fwd(kind, dtype_code(X), ptr(X), ptr(X2), ptr(ls), ls.shape[-1], ptr(var),
+                               ptr(diag_add), float(diag_const), ptr(out), out.stride(1),
+                               S, N, N2, D, _bstride(X, S), 0 if X2 is None else _bstride(X2, S),
+                               _bstride(ls, S), _bstride(var, S),
+                               0 if diag_add is None else _bstride(diag_add, S), out.stride(0),
+                               stream_ptr()), 'mxf_kbuild_fwd')
+    return out
+
+
+def kbuild_bwd(kind, X, X2, ls, var, G, need_dX=True, need_dX2=True):
+    """Adjoint of kbuild_fwd.  Returns (dX, dX2, dls, dvar), each with S leading."""
+    require_cuda(X, X2, ls, var, G)
+    X, ls, var = _c(X), _c(ls), _c(var)
+    X2 = None if X2 is None else _c(X2)
+    if G.stride(2) != 1:
+        G = G.contiguous()
+    S, N, N2 = G.shape
+    D = X.shape[2]
+    # operands broadcast over S are expanded: the adjoint then sums over S on the host side
+    def ex(t):
+        return t if t.shape[0] == S else t.expand((S,) + t.shape[1:]).contiguous()
+    Xe, lse, vare = ex(X), ex(ls), ex(var)
+    X2e = None if X2 is None else ex(X2)
+    dX = torch.empty_like(Xe) if need_dX else None
+    dX2 = torch.empty_like(X2e) if (need_dX2 and X2e is not None) else None
+    dls = torch.empty_like(lse)
+    dvar = torch.empty_like(vare)
+    nbytes = lib().mxf_kbuild_bwd_workspace_bytes(dtype_code(X), S, N, N2, D)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=X.device)
+    check(lib().mxf_kbuild_bwd(kind, dtype_code(X), ptr(Xe), ptr(X2e), ptr(lse), lse.shape[-1], ptr(vare),
+                               ptr(G), G.stride(1), ptr(dX), ptr(dX2), ptr(dls), ptr(dvar),
+                               S, N, N2, D, Xe.stride(0), 0 if X2e is None else X2e.stride(0),
+                               lse.stride(0), vare.stride(0), G.stride(0), ptr(ws), nbytes, stream_ptr()),
+          'mxf_kbuild_bwd')
+
+    def red(g, t):
+        if g is None:
+            return None
+        return g if t.shape[0] == S else g.sum(dim=0, keepdim=True)
+    return red(dX, X), (None if X2 is None else red(dX2, X2)), red(dls, ls), red(dvar, var)
+
+
+def gemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None, tri=False):
+    """C = alpha op(A) op(B) + beta C, batched over the leading axis (stride-0 broadcast allowed)."""
+    require_cuda(A, B, C)
+    if A.stride(2) != 1:
+        A = A.contiguous()
+    if B.stride(2) != 1:
+        B = B.contiguous()
+    S = max(A.shape[0], B.shape[0], 1 if C is None else C.shape[0])
+    m = A.shape[2] if transA else A.shape[1]
+    k = A.shape[1] if transA else A.shape[2]
+    n = B.shape[1] if transB else B.shape[2]
+    kb = B.shape[2] if transB else B.shape[1]
+    if k != kb:
+        raise _lib.MXFusionB200Error("gemm: inner dimensions differ (%d vs %d)" % (k, kb))
+    if C is None:
+        C = torch.empty((S, m, n), dtype=A.dtype, device=A.device)
+        if tri:
+            C.zero_()
+        beta = 0.0
+    check(lib().mxf_gemm(dtype_code(A), int(transA), int(transB), m, n, k, float(alpha),
+                         ptr(A), A.stride(1), _bstride(A, S), ptr(B), B.stride(1), _bstride(B, S),
+                         float(beta), ptr(C), C.stride(1), C.stride(0) if C.shape[0] > 1 else 0,
+                         S, int(tri), stream_ptr()), 'mxf_gemm')
+    return C
+
+
+def potrf_(A, info=None):
+    """In-place lower Cholesky of A (S,n,n).  Returns (A, info int32[S])."""
+    require_cuda(A)
+    S, n, _ = A.shape
+    if info is None:
+        info = torch.empty((S,), dtype=torch.int32, device=A.device)
+    check(lib().mxf_potrf(dtype_code(A), ptr(A), A.stride(1), A.stride(0), S, n, ptr(info), stream_ptr()),
+          'mxf_potrf')
+    return A, info
+
+
+def trsm_(L, B, transpose=False, alpha=1.0):
+    """In-place B := alpha op(L)^-1 B; L (Sl,n,n) lower, B (S,n,nrhs)."""
+    require_cuda(L, B)
+    S, n, nrhs = B.shape
+    check(lib().mxf_trsm(dtype_code(B), int(transpose), n, nrhs, float(alpha), ptr(L), L.stride(1),
+                         _bstride(L, S), ptr(B), B.stride(1), B.stride(0), S, stream_ptr()), 'mxf_trsm')
+    return B
+
+
+def _sq(fn, name, A, *extra):
+    require_cuda(A)
+    S, n, _ = A.shape
+    out = torch.empty((S, n, n), dtype=A.dtype, device=A.device)
+    check(fn(dtype_code(A), *extra, ptr(A), A.stride(1), A.stride(0), ptr(out), out.stride(1), out.stride(0),
+             S, n, stream_ptr()), name)
+    return out
+
+
+def copy_ltu(P):
+    return _sq(lib().mxf_copy_ltu, 'mxf_copy_ltu', P)
+
+
+def symmetrize(A, alpha=1.0):
+    return _sq(lib().mxf_symmetrize, 'mxf_symmetrize', A, float(alpha))
+
+
+def tril(A, strict=False):
+    return _sq(lib().mxf_tril, 'mxf_tril', A, 1 if strict else 0)
+
+
+def transpose(A, out=None):
+    require_cuda(A, out)
+    if A.stride(2) != 1:
+        A = A.contiguous()
+    S, m, n = A.shape
+    if out is None:
+        out = torch.empty((S, n, m), dtype=A.dtype, device=A.device)
+    check(lib().mxf_transpose(dtype_code(A), ptr(A), A.stride(1), A.stride(0), ptr(out), out.stride(1),
+                              out.stride(0), S, m, n, stream_ptr()), 'mxf_transpose')
+    return out
+
+
+def reduce(op, a, b=None, scale=1.0):
+    """out[s] = scale * sum over the trailing two axes of f(a, b); a (S,rows,cols)."""
+    require_cuda(a, b)
+    if a.stride(2) != 1:
+        a = a.contiguous()
+    if b is not None and b.stride(2) != 1:
+        b = b.contiguous()
+    S = a.shape[0] if b is None else max(a.shape[0], b.shape[0])
+    rows, cols = a.shape[1], a.shape[2]
+    out = torch.empty((S,), dtype=a.dtype, device=a.device)
+    check(lib().mxf_reduce(op, dtype_code(a), ptr(a), a.stride(1), _bstride(a, S),
+                           ptr(b), 0 if b is None else b.stride(1), 0 if b is None else _bstride(b, S),
+                           S, rows, cols, float(scale), ptr(out), stream_ptr()), 'mxf_reduce')
+    return out
+
+
+def sumlogdiag(A):
+    require_cuda(A)
+    S, n, _ = A.shape
+    out = torch.empty((S,), dtype=A.dtype, device=A.device)
+    check(lib().mxf_sumlogdiag(dtype_code(A), ptr(A), A.stride(1), A.stride(0), S, n, ptr(out), stream_ptr()),
+          'mxf_sumlogdiag')
+    return out
+
+
+def add_diag_(A, d=None, c=0.0):
+    require_cuda(A, d)
+    S, n, _ = A.shape
+    d = None if d is None else _c(d)
+    check(lib().mxf_add_diag(dtype_code(A), ptr(A), A.stride(1), A.stride(0), ptr(d),
+                             0 if d is None else _bstride(d, S), float(c), S, n, stream_ptr()), 'mxf_add_diag')
+    return A
+
+
+def get_diag(A):
+    require_cuda(A)
+    S, n, _ = A.shape
+    out = torch.empty((S, n), dtype=A.dtype, device=A.device)
+    check(lib().mxf_get_diag(dtype_code(A), ptr(A), A.stride(1), A.stride(0), ptr(out), out.stride(0), S, n,
+                             stream_ptr()), 'mxf_get_diag')
+    return out
+
+
+def _flat(t):
+    """(S', ...) -> contiguous (S', n) view."""
+    t = _c(t)
+    return t.reshape(t.shape[0], -1)
+
+
+def normal_logpdf_sum(x, m, v, scale=1.0):
+    """scale * sum(mean_S(log N(x | m, v))) -> tensor of shape (1,)."""
+    require_cuda(x, m, v)
+    x, m, v = _flat(x), _flat(m), _flat(v)
+    S = max(x.shape[0], m.shape[0], v.shape[0])
+    n = x.shape[1]
+    out = torch.zeros((1,), dtype=x.dtype, device=x.device)
+    check(lib().mxf_normal_logpdf_sum(dtype_code(x), ptr(x), _bstride(x, S), ptr(m), _bstride(m, S),
+                                      ptr(v), _bstride(v, S), S, n, float(scale), ptr(out), stream_ptr()),
+          'mxf_normal_logpdf_sum')
+    return out
+
+
+def normal_logpdf_sum_bwd(x, m, v, gout, scale=1.0, need=(True, True, True)):
+    require_cuda(x, m, v, gout)
+    xs, ms, vs = x.shape, m.shape, v.shape
+    x, m, v = _flat(x), _flat(m), _flat(v)
+    S = max(x.shape[0], m.shape[0], v.shape[0])
+    n = x.shape[1]
+    gx = torch.empty_like(x) if need[0] else None
+    gm = torch.empty_like(m) if need[1] else None
+    gv = torch.empty_like(v) if need[2] else None
+    gout = _c(gout).reshape(-1)
+    check(lib().mxf_normal_logpdf_sum_bwd(dtype_code(x), ptr(x), _bstride(x, S), ptr(m), _bstride(m, S),
+                                          ptr(v), _bstride(v, S), S, n, float(scale), ptr(gout),
+                                          ptr(gx), ptr(gm), ptr(gv), stream_ptr()), 'mxf_normal_logpdf_sum_bwd')
+    return (None if gx is None else gx.reshape(xs), None if gm is None else gm.reshape(ms),
+            None if gv is None else gv.reshape(vs))
+
+
+def normal_reparam(m, v, S, eps=None, seed=0, offset=0, return_eps=False):
+    """w (S, *shape) = eps*sqrt(v)+m; m, v carry a leading axis of 1 or S."""
+    require_cuda(m, v, eps)
+    shape = m.shape[1:]
+    mf, vf = _flat(m), _flat(v)
+    n = mf.shape[1]
+    w = torch.empty((S, n), dtype=m.dtype, device=m.device)
+    eps_out = None
+    if eps is not None:
+        eps = _c(eps).reshape(S, n)
+    elif return_eps:
+        eps_out = torch.empty_like(w)
+    check(lib().mxf_normal_reparam(dtype_code(m), ptr(eps), ptr(mf), _bstride(mf, S), ptr(vf), _bstride(vf, S),
+                                   S, n, int(seed), int(offset), ptr(w), ptr(eps_out), stream_ptr()),
+          'mxf_normal_reparam')
+    w = w.reshape((S,) + tuple(shape))
+    if return_eps:
+        e = eps if eps is not None else eps_out
+        return w, e.reshape((S,) + tuple(shape))
+    return w
+
+
+def adam_step_(w, g, m, v, step_count, lr, beta1=0.9, beta2=0.999, eps=1e-8, rescale=1.0):
+    require_cuda(w, g, m, v, step_count)
+    check(lib().mxf_adam_step(dtype_code(w), ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), float(lr), float(beta1),
+                              float(beta2), float(eps), float(rescale), ptr(step_count), stream_ptr()),
+          'mxf_adam_step')
+
+
+def gather_rows(src, idx, off, rows, out=None):
+    require_cuda(src, idx, off)
+    src = _c(src)
+    cols = src.shape[1]
+    if out is None:
+        out = torch.empty((rows, cols), dtype=src.dtype, device=src.device)
+    check(lib().mxf_gather_rows(dtype_code(src), ptr(src), cols, ptr(idx), ptr(off), rows, ptr(out), stream_ptr()),
+          'mxf_gather_rows')
+    return out
+
+
+def axpby_dev(a, X, b=None, Y=None, out=None):
+    """out[s] = a[s]*X[s] + b[s]*Y[s]; a, b device tensors (S,) or None; X, Y (S|1, ...)."""
+    require_cuda(a, X, b, Y)
+    X = _c(X)
+    Y = None if Y is None else _c(Y)
+    S = max(X.shape[0], 1 if Y is None else Y.shape[0], 1 if a is None else a.numel(),
+            1 if b is None else b.numel())
+    n = X[0].numel()
+    if out is None:
+        out = torch.empty((S,) + tuple(X.shape[1:]), dtype=X.dtype, device=X.device)
+
+    def coef(c):
+        if c is None:
+            return None
+        c = _c(c).reshape(-1)
+        return c if c.numel() == S else c.expand(S).contiguous()
+    a, b = coef(a), coef(b)
+    check(lib().mxf_axpby_dev(dtype_code(X), ptr(a), ptr(X), _bstride(X, S) if X.shape[0] > 1 else 0,
+                              ptr(b), ptr(Y), 0 if Y is None else (n if Y.shape[0] > 1 else 0),
+                              ptr(out), n, S, n, stream_ptr()), 'mxf_axpby_dev')
+    return out
+
+
+def softplus_fwd(x, offset=0.0):
+    require_cuda(x)
+    x = _c(x)
+    y = torch.empty_like(x)
+    check(lib().mxf_softplus_fwd(dtype_code(x), ptr(x), float(offset), ptr(y), x.numel(), stream_ptr()),
+          'mxf_softplus_fwd')
+    return y
+
+
+def softplus_bwd(x, gy):
+    require_cuda(x, gy)
+    x, gy = _c(x), _c(gy)
+    gx = torch.empty_like(x)
+    check(lib().mxf_softplus_bwd(dtype_code(x), ptr(x), ptr(gy), ptr(gx), x.numel(), stream_ptr()),
+          'mxf_softplus_bwd')
+    return gx
+
+
+def svgp_bwd_assemble(Phi, T, U, mt, v, coef):
+    require_cuda(Phi, T, U, mt, v, coef)
+    S, M, _ = Phi.shape
+    P = mt.shape[2]
+    out = torch.empty((S, M, 3 * M), dtype=Phi.dtype, device=Phi.device)
+    check(lib().mxf_svgp_bwd_assemble(dtype_code(Phi), ptr(_c(Phi)), ptr(_c(T)), ptr(_c(U)), ptr(_c(mt)), ptr(_c(v)),
+                                      ptr(_c(coef)), ptr(out), S, M, P, stream_ptr()), 'mxf_svgp_bwd_assemble')
+    return out

@@ -14,6 +14,7 @@ __device__ __forceinline__ T red_term(T a, T b) {
     if (OP == MXF_RED_SUM) return a;
     if (OP == MXF_RED_SUMSQ) return a * a;
     if (OP == MXF_RED_DOT) return a * b;
+    if (OP == MXF_RED_SUMSQDIFF) return (a - b) * (a - b);
     return Num<T>::log_(a);
 }
 
@@ -25,15 +26,16 @@ reduce_kernel(const T* __restrict__ a, int64_t lda, int64_t sA, const T* __restr
     __shared__ T red[32];
     const int s = blockIdx.y;
     const T* as = a + (int64_t)s * sA;
-    const T* bs = (OP == MXF_RED_DOT) ? b + (int64_t)s * sB : nullptr;
+    constexpr bool TWO = (OP == MXF_RED_DOT || OP == MXF_RED_SUMSQDIFF);
+    const T* bs = TWO ? b + (int64_t)s * sB : nullptr;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(rows, r0 + rows_per_block);
     T acc = 0;
     for (int64_t r = r0; r < r1; ++r) {
         const T* ar = as + r * lda;
-        const T* br = (OP == MXF_RED_DOT) ? bs + r * ldb : nullptr;
+        const T* br = TWO ? bs + r * ldb : nullptr;
         for (int64_t c = threadIdx.x; c < cols; c += blockDim.x)
-            acc += red_term<T, OP>(ar[c], (OP == MXF_RED_DOT) ? br[c] : T(0));
+            acc += red_term<T, OP>(ar[c], TWO ? br[c] : T(0));
     }
     T tot = block_sum(acc, red);
     if (threadIdx.x == 0) {
@@ -53,7 +55,8 @@ static int reduce_impl(int op, const T* a, int64_t lda, int64_t sA, const T* b, 
                        int64_t rows, int64_t cols, double scale, T* out, cudaStream_t st) {
     if (S == 0) return MXF_OK;
     // collapse contiguous matrices into long rows so that a block streams a contiguous range
-    if (lda == cols && (op != MXF_RED_DOT || ldb == cols) && rows > 1) {
+    const bool two = (op == MXF_RED_DOT || op == MXF_RED_SUMSQDIFF);
+    if (lda == cols && (!two || ldb == cols) && rows > 1) {
         const int64_t total = rows * cols;
         int64_t chunk = 8192;
         while (total % chunk != 0 && chunk > 1) chunk >>= 1;
@@ -76,6 +79,7 @@ static int reduce_impl(int op, const T* a, int64_t lda, int64_t sA, const T* b, 
         MXF_RED_CASE(MXF_RED_SUMSQ)
         MXF_RED_CASE(MXF_RED_DOT)
         MXF_RED_CASE(MXF_RED_SUMLOG)
+        MXF_RED_CASE(MXF_RED_SUMSQDIFF)
         default: return MXF_EINVAL;
     }
 #undef MXF_RED_CASE
@@ -317,7 +321,8 @@ extern "C" uint64_t mxf_launch_count(void) { return g_launches.load(); }
 
 extern "C" int mxf_reduce(int op, int dtype, const void* a, int64_t lda, int64_t sA, const void* b, int64_t ldb,
                           int64_t sB, int S, int64_t rows, int64_t cols, double scale, void* out, void* stream) {
-    if (!a || !out || rows < 0 || cols < 0 || S < 0 || (op == MXF_RED_DOT && !b)) return MXF_EINVAL;
+    if (!a || !out || rows < 0 || cols < 0 || S < 0 || ((op == MXF_RED_DOT || op == MXF_RED_SUMSQDIFF) && !b))
+        return MXF_EINVAL;
     if (S > 65535) return MXF_ENOTIMPL;
     MXF_DISPATCH_DTYPE(dtype, return reduce_impl<T>(op, (const T*)a, lda, sA, (const T*)b, ldb, sB, S, rows, cols,
                                                     scale, (T*)out, (cudaStream_t)stream));

@@ -1,0 +1,138 @@
+// Pieces of the analytic SVGP-bound gradient (modules/gp_modules/svgp_regression.py:43-109 differentiated by
+// hand; the reference leaves this to MXNet autograd), the device-scalar axpby used to combine them, and the
+// softplus parameter transform (components/variables/var_trans.py:63-91).
+#include <algorithm>
+#include "common.cuh"
+
+namespace mxf {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+axpby_dev_kernel(const T* __restrict__ a, const T* __restrict__ X, int64_t sX, const T* __restrict__ b,
+                 const T* __restrict__ Y, int64_t sY, T* __restrict__ out, int64_t sO, int64_t n) {
+    const int s = blockIdx.y;
+    const T av = a ? a[s] : T(1);
+    const T bv = b ? b[s] : T(0);
+    const T* xs = X + (int64_t)s * sX;
+    const T* ys = Y ? Y + (int64_t)s * sY : nullptr;
+    T* os = out + (int64_t)s * sO;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T v = av * xs[i];
+        if (ys) v = fma(bv, ys[i], v);
+        os[i] = v;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) softplus_fwd_kernel(const T* __restrict__ x, T offset, T* __restrict__ y, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T v = x[i];
+        // log(1+e^v) = max(v,0) + log1p(e^{-|v|})
+        const T av = v < T(0) ? -v : v;
+        y[i] = (v > T(0) ? v : T(0)) + log1p(exp(-av)) + offset;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) softplus_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, T* __restrict__ gx, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T v = x[i];
+        const T e = exp(v < T(0) ? v : -v);                 // e^{-|v|}
+        const T sig = v >= T(0) ? T(1) / (T(1) + e) : e / (T(1) + e);
+        gx[i] = gy[i] * sig;
+    }
+}
+
+// 32x32 tiles, 32x8 threads; U^T is staged through shared memory so every global access is coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+svgp_bwd_assemble_kernel(const T* __restrict__ Phi, const T* __restrict__ Tm, const T* __restrict__ U,
+                         const T* __restrict__ mt, const T* __restrict__ v, const T* __restrict__ coef,
+                         T* __restrict__ out, int M, int P) {
+    __shared__ T ut[32][33];
+    const int s = blockIdx.z;
+    const int64_t mo = (int64_t)s * M * M;
+    const T* Phis = Phi + mo;
+    const T* Ts = Tm + mo;
+    const T* Us = U + mo;
+    const T* mts = mt + (int64_t)s * M * P;
+    const T* vs = v + (int64_t)s * M * P;
+    const T* cf = coef + (int64_t)s * 6;
+    T* os = out + (int64_t)s * M * 3 * M;
+    const T c0 = cf[0], c1 = cf[1], c2 = cf[2], c3 = cf[3], c4 = cf[4], c5 = cf[5];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int ui = bx + r, uj = by + threadIdx.x;       // U[ui][uj], coalesced along uj
+        ut[r][threadIdx.x] = (ui < M && uj < M) ? Us[(int64_t)ui * M + uj] : T(0);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = by + r, j = bx + threadIdx.x;
+        if (i >= M || j >= M) continue;
+        const int64_t e = (int64_t)i * M + j;
+        const T ph = Phis[e], t = Ts[e], u = Us[e], uT = ut[threadIdx.x][r];
+        T mm = 0, vm = 0;
+        for (int p = 0; p < P; ++p) {
+            const T mi = mts[i * P + p], mj = mts[j * P + p];
+            mm = fma(mi, mj, mm);
+            vm = fma(vs[i * P + p], mj, vm);
+            vm = fma(mi, vs[j * P + p], vm);
+        }
+        const T dl = (i == j) ? T(1) : T(0);
+        T* orow = os + (int64_t)i * 3 * M;
+        orow[j] = c2 * mm + c0 * (t - dl) - c1 * ph + c1 * (u + uT) - c3 * vm;
+        orow[M + j] = c0 * dl + c1 * ph;
+        orow[2 * M + j] = -c4 * (t - dl) - c5 * mm;
+    }
+}
+
+static inline int grid1d(int64_t n) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)8 * kNumSMs));
+}
+
+}  // namespace mxf
+
+using namespace mxf;
+
+extern "C" int mxf_axpby_dev(int dtype, const void* a, const void* X, int64_t sX, const void* b, const void* Y,
+                             int64_t sY, void* out, int64_t sO, int S, int64_t n, void* stream) {
+    if (!X || !out || S < 0 || n < 0 || (b && !Y)) return MXF_EINVAL;
+    if (S == 0 || n == 0) return MXF_OK;
+    if (S > 65535) return MXF_ENOTIMPL;
+    dim3 grid(grid1d(n), S);
+    MXF_DISPATCH_DTYPE(dtype, axpby_dev_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)a, (const T*)X, sX, (const T*)b, (const T*)Y, sY, (T*)out, sO, n));
+    return after_launch();
+}
+
+extern "C" int mxf_softplus_fwd(int dtype, const void* x, double offset, void* y, int64_t n, void* stream) {
+    if (!x || !y || n < 0) return MXF_EINVAL;
+    if (n == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, softplus_fwd_kernel<T><<<grid1d(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T)offset,
+                                                                                                 (T*)y, n));
+    return after_launch();
+}
+
+extern "C" int mxf_softplus_bwd(int dtype, const void* x, const void* gy, void* gx, int64_t n, void* stream) {
+    if (!x || !gy || !gx || n < 0) return MXF_EINVAL;
+    if (n == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, softplus_bwd_kernel<T><<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)x, (const T*)gy, (T*)gx, n));
+    return after_launch();
+}
+
+extern "C" int mxf_svgp_bwd_assemble(int dtype, const void* Phi, const void* T_, const void* U, const void* mt,
+                                     const void* v, const void* coef, void* out, int S, int M, int P,
+                                     void* stream) {
+    if (!Phi || !T_ || !U || !mt || !v || !coef || !out || S < 0 || M < 0 || P < 0) return MXF_EINVAL;
+    if (S == 0 || M == 0) return MXF_OK;
+    if (S > 65535) return MXF_ENOTIMPL;
+    dim3 grid(cdiv(M, 32), cdiv(M, 32), S);
+    MXF_DISPATCH_DTYPE(dtype, svgp_bwd_assemble_kernel<T><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+                                  (const T*)Phi, (const T*)T_, (const T*)U, (const T*)mt, (const T*)v,
+                                  (const T*)coef, (T*)out, M, P));
+    return after_launch();
+}

@@ -1,0 +1,395 @@
+"""Differentiable operators of the hot path: torch.autograd.Function wrappers whose forward AND
+backward are C-ABI kernel launches (mxfusion_b200._raw -> libmxf_b200.so).
+
+These stand where the reference calls MXNet operators through `F` and leaves the adjoints to MXNet
+autograd.  Two kinds of operator live here:
+
+* primitives that mirror the MXNet operators one for one (`kernel_matrix`, `potrf`, `trsm`, `gemm2`,
+  `syrk`, `sumlogdiag`, `make_diagonal`, `softplus`, the Normal pieces), so that a user-written
+  `InferenceAlgorithm.compute` reads like the reference's;
+* the two fused module bounds, `svgp_log_pdf` (svgp_regression.py:43-109) and `gp_log_pdf`
+  (gp_regression.py:42-76), each one autograd node with an analytic, hand-derived gradient.
+
+Every array carries the reference's leading sample axis (runtime_variable.py:20-50).
+"""
+import math
+
+import torch
+
+from . import _raw as R   # tests may monkeypatch `ops.R` with a stand-in to check the algebra without a GPU
+
+RBF, MATERN12, MATERN32, MATERN52 = 0, 1, 2, 3
+_LOG2PI = math.log(2.0 * math.pi)
+
+
+def _lead(*ts):
+    return max(t.shape[0] for t in ts if t is not None)
+
+
+def _expand(t, S):
+    """Differentiable broadcast of the sample axis (arrays_as_samples, runtime_variable.py:102-118)."""
+    if t is None or t.shape[0] == S:
+        return t
+    return t.expand((S,) + tuple(t.shape[1:]))
+
+
+# --------------------------------------------------------------------------------------------------
+# primitives
+# --------------------------------------------------------------------------------------------------
+class _Softplus(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, offset):
+        ctx.save_for_backward(x)
+        return R.softplus_fwd(x, offset)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return R.softplus_bwd(x, gy), None
+
+
+def softplus(x, offset=0.0):
+    """var_trans.py:75 (Activation softrelu) + offset."""
+    return _Softplus.apply(x, offset)
+
+
+class _KernelMatrix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kind, X, X2, ls, var, diag_add, diag_const):
+        ctx.kind = kind
+        ctx.save_for_backward(X, X2, ls, var)
+        ctx.has_diag = diag_add is not None
+        return R.kbuild_fwd(kind, X, X2, ls, var, diag_add=diag_add, diag_const=diag_const)
+
+    @staticmethod
+    def backward(ctx, G):
+        X, X2, ls, var = ctx.saved_tensors
+        dX, dX2, dls, dvar = R.kbuild_bwd(ctx.kind, X, X2, ls, var, G,
+                                          need_dX=ctx.needs_input_grad[1] or X2 is None,
+                                          need_dX2=ctx.needs_input_grad[2])
+        ddiag = None
+        if ctx.has_diag and ctx.needs_input_grad[5]:
+            ddiag = R.reduce(R.RED_SUM, R.get_diag(G).unsqueeze(1)).unsqueeze(1)
+        return None, dX, dX2, dls, dvar, ddiag, None
+
+
+def kernel_matrix(kind, X, X2, lengthscale, variance, diag_add=None, diag_const=0.0):
+    """Stationary covariance matrix (stationary.py:74-107 + rbf.py:71-72 / matern.py:84-151), with the
+    `+ eye * noise_var` / `+ eye * jitter` of the callers folded into the store."""
+    S = _lead(X, X2, lengthscale, variance, diag_add)
+    return _KernelMatrix.apply(kind, _expand(X, S), _expand(X2, S), _expand(lengthscale, S),
+                               _expand(variance, S), _expand(diag_add, S), diag_const)
+
+
+class _Potrf(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A):
+        L, info = R.potrf_(A.clone())
+        ctx.save_for_backward(L)
+        ctx.mark_non_differentiable(info)
+        return L, info
+
+    @staticmethod
+    def backward(ctx, Lbar, _):
+        # Murray (2016): Abar = 1/2 L^-T (P + P^T) L^-1 with P = Phi(L^T Lbar), Phi = lower triangle with the
+        # diagonal halved, so P + P^T is the symmetric matrix built from the lower triangle of L^T Lbar.
+        (L,) = ctx.saved_tensors
+        G = R.gemm(L, R.tril(Lbar), transA=True)
+        Psym = R.copy_ltu(G)
+        R.trsm_(L, Psym, transpose=True)
+        Y = R.transpose(Psym)
+        R.trsm_(L, Y, transpose=True)
+        return R.symmetrize(Y, 0.25)      # 1/2 * (Y + Y^T)/2: symmetric by construction, cleans rounding
+
+
+def potrf(A, return_info=False):
+    """linalg.potrf: lower Cholesky factor with the strict upper triangle zeroed."""
+    L, info = _Potrf.apply(A)
+    return (L, info) if return_info else L
+
+
+class _Trsm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, L, B, transpose, alpha):
+        X = R.trsm_(L, B.clone(), transpose=transpose, alpha=alpha)
+        ctx.transpose, ctx.alpha = transpose, alpha
+        ctx.save_for_backward(L, X)
+        return X
+
+    @staticmethod
+    def backward(ctx, Xbar):
+        L, X = ctx.saved_tensors
+        Bbar = R.trsm_(L, Xbar.clone(), transpose=not ctx.transpose, alpha=ctx.alpha)
+        Lbar = None
+        if ctx.needs_input_grad[0]:
+            # X = alpha op(L)^-1 B:  Lbar = -(1/alpha) tril(Bbar X^T)  (no transpose),  -(1/alpha) tril(X Bbar^T)
+            if not ctx.transpose:
+                Lbar = R.tril(R.gemm(Bbar, X, transB=True, alpha=-1.0 / ctx.alpha))
+            else:
+                Lbar = R.tril(R.gemm(X, Bbar, transB=True, alpha=-1.0 / ctx.alpha))
+            if L.shape[0] != Lbar.shape[0]:
+                Lbar = Lbar.sum(dim=0, keepdim=True)
+        return Lbar, Bbar, None, None
+
+
+def trsm(L, B, transpose=False, alpha=1.0):
+    """linalg.trsm (left, lower): alpha * op(L)^-1 B."""
+    S = _lead(L, B)
+    return _Trsm.apply(L, _expand(B, S), bool(transpose), float(alpha))
+
+
+class _Gemm2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, B, ta, tb, alpha):
+        ctx.ta, ctx.tb, ctx.alpha = ta, tb, alpha
+        ctx.save_for_backward(A, B)
+        return R.gemm(A, B, ta, tb, alpha=alpha)
+
+    @staticmethod
+    def backward(ctx, G):
+        A, B = ctx.saved_tensors
+        ta, tb, al = ctx.ta, ctx.tb, ctx.alpha
+        dA = dB = None
+        if ctx.needs_input_grad[0]:
+            dA = R.gemm(B, G, tb, True, alpha=al) if ta else R.gemm(G, B, False, not tb, alpha=al)
+        if ctx.needs_input_grad[1]:
+            dB = R.gemm(G, A, True, ta, alpha=al) if tb else R.gemm(A, G, not ta, False, alpha=al)
+        return dA, dB, None, None, None
+
+
+def gemm2(A, B, transpose_a=False, transpose_b=False, alpha=1.0):
+    """linalg.gemm2: alpha * op(A) op(B)."""
+    S = _lead(A, B)
+    return _Gemm2.apply(_expand(A, S), _expand(B, S), bool(transpose_a), bool(transpose_b), float(alpha))
+
+
+def syrk(A, transpose=False, alpha=1.0):
+    """linalg.syrk: alpha * A A^T (A^T A when transpose)."""
+    return gemm2(A, A, transpose, not transpose, alpha)
+
+
+class _SumLogDiag(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A):
+        ctx.save_for_backward(A)
+        return R.sumlogdiag(A)
+
+    @staticmethod
+    def backward(ctx, g):
+        (A,) = ctx.saved_tensors
+        d = R.get_diag(A)
+        out = torch.zeros_like(A)
+        R.add_diag_(out, (g.unsqueeze(1) / d))
+        return out
+
+
+def sumlogdiag(A):
+    """linalg.sumlogdiag."""
+    return _SumLogDiag.apply(A)
+
+
+class _MakeDiagonal(torch.autograd.Function):
+    """util/customop.py:22-81 (`make_diagonal` CustomOp: forward embeds, backward extracts)."""
+
+    @staticmethod
+    def forward(ctx, v):
+        out = torch.zeros(tuple(v.shape) + (v.shape[-1],), dtype=v.dtype, device=v.device)
+        R.add_diag_(out, v)
+        return out
+
+    @staticmethod
+    def backward(ctx, G):
+        return R.get_diag(G)
+
+
+def make_diagonal(v):
+    return _MakeDiagonal.apply(v)
+
+
+class _NormalLogPdfSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, m, v, scale):
+        ctx.scale = scale
+        ctx.save_for_backward(x, m, v)
+        return R.normal_logpdf_sum(x, m, v, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, m, v = ctx.saved_tensors
+        gx, gm, gv = R.normal_logpdf_sum_bwd(x, m, v, g, ctx.scale, need=tuple(ctx.needs_input_grad[:3]))
+        return gx, gm, gv, None
+
+
+def normal_log_pdf_sum(x, mean, variance, scale=1.0):
+    """scale * F.sum(F.mean(Normal.log_pdf, axis=0)) in one pass: normal.py:67-69 + factor_graph.py:223."""
+    return _NormalLogPdfSum.apply(x, mean, variance, float(scale))
+
+
+class _NormalReparam(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, m, v, S, eps, seed, offset):
+        w, e = R.normal_reparam(m, v, S, eps=eps, seed=seed, offset=offset, return_eps=True)
+        ctx.save_for_backward(e, v)
+        ctx.mS, ctx.vS = m.shape[0], v.shape[0]
+        return w
+
+    @staticmethod
+    def backward(ctx, gw):
+        e, v = ctx.saved_tensors
+        gm = gw if ctx.mS == gw.shape[0] else gw.sum(dim=0, keepdim=True)
+        # d/dv [eps sqrt(v)] = eps / (2 sqrt(v))
+        gv = gw * e * (0.5 / torch.sqrt(v))
+        if ctx.vS != gv.shape[0]:
+            gv = gv.sum(dim=0, keepdim=True)
+        return gm, gv, None, None, None, None
+
+
+def normal_draw(mean, variance, num_samples, eps=None, seed=0, offset=0):
+    """Reparameterised draw eps*sqrt(v)+mu (normal.py:89-92); eps injected or Philox-generated in-kernel."""
+    return _NormalReparam.apply(mean, variance, int(num_samples), eps, int(seed), int(offset))
+
+
+# --------------------------------------------------------------------------------------------------
+# fused SVGP bound
+# --------------------------------------------------------------------------------------------------
+class _SVGPLogPdf(torch.autograd.Function):
+    """svgp_regression.py:61-109 (homoscedastic noise).  Forward follows the reference's whitened quantities
+    (A = L^-1 Kuf, C = L^-1 Ls, mt = L^-1 mu); the two B x M products of :89-90 are replaced by
+    Phi = A A^T and T = C C^T, since  sum((A^T C)^2) = tr(Phi T)  and  sum(A^2) = tr(Phi).
+    Backward is the closed-form gradient -- no tape."""
+
+    @staticmethod
+    def forward(ctx, kind, jitter, scale, X, Y, Z, noise, mu, W, dvec, ls, kvar):
+        S, B, P, M = X.shape[0], X.shape[1], Y.shape[2], Z.shape[1]
+        Kuu = R.kbuild_fwd(kind, Z, None, ls, kvar, diag_const=jitter)
+        A = R.kbuild_fwd(kind, Z, X, ls, kvar)                  # Kuf (:73), overwritten below by L^-1 Kuf
+        Sm = R.gemm(W, W, transB=True, tri=True)                # :76 syrk (lower tiles) ...
+        R.add_diag_(Sm, dvec)                                   # ... + make_diagonal
+        L, info = R.potrf_(Kuu)                                 # :83
+        Ls, info_s = R.potrf_(Sm)                               # :84
+        C = R.trsm_(L, Ls.clone())                              # :85
+        mt = R.trsm_(L, mu.clone())                             # :86
+        R.trsm_(L, A)                                           # :87
+        Phi = R.copy_ltu(R.gemm(A, A, transB=True, tri=True))
+        T = R.copy_ltu(R.gemm(C, C, transB=True, tri=True))
+        G1 = R.gemm(A, mt, transA=True)                         # :89  (S,B,P)
+        sumr2 = R.reduce(R.RED_SUMSQDIFF, Y, G1)
+        trPhi = R.reduce(R.RED_SUMSQ, A)
+        trT = R.reduce(R.RED_SUMSQ, C)
+        trPhiT = R.reduce(R.RED_DOT, Phi, T)
+        mm = R.reduce(R.RED_SUMSQ, mt)
+        sldL, sldLs = R.sumlogdiag(L), R.sumlogdiag(Ls)
+        nv, kv = noise[:, 0], kvar[:, 0]
+        beta = 1.0 / nv
+        Q = -0.5 * sumr2 - (0.5 * P * B) * kv - (0.5 * P) * (trPhiT - trPhi)
+        data = beta * Q - (0.5 * B * P) * (_LOG2PI + torch.log(nv))          # :98-107
+        neg_kl = P * (0.5 * M + sldLs - sldL) - (0.5 * P) * trT - 0.5 * mm   # :94-96 (`KL_u` is minus the KL)
+        logL = scale * data + neg_kl                                         # :108
+        ctx.kind, ctx.scale, ctx.dims = kind, scale, (S, B, P, M)
+        ctx.save_for_backward(X, Y, Z, ls, kvar, W, L, Ls, A, Phi, T, mt, G1, beta, Q)
+        ctx.info = (info, info_s)
+        return logL
+
+    @staticmethod
+    def backward(ctx, g):
+        X, Y, Z, ls, kvar, W, L, Ls, A, Phi, T, mt, G1, beta, Q = ctx.saved_tensors
+        S, B, P, M = ctx.dims
+        sc = ctx.scale
+        need = ctx.needs_input_grad      # (kind, jitter, scale, X, Y, Z, noise, mu, W, dvec, ls, kvar)
+        g = g.contiguous()
+        gsb = g * (sc * beta)
+        coef = torch.stack([g * (0.5 * P), gsb * (0.5 * P), 0.5 * g, 0.5 * gsb, gsb * P, gsb], dim=1).contiguous()
+        U = R.gemm(Phi, T)
+        v = R.gemm(A, Y)
+        R.gemm(Phi, mt, alpha=-1.0, beta=1.0, C=v)              # v = A (Y - A^T mt)
+        E3 = R.svgp_bwd_assemble(Phi, T, U, mt, v, coef)        # [E | E_S | E_R]
+        R.trsm_(L, E3, transpose=True)                          # L^-T [.]
+        # Kuf adjoint: (L^-T E_R) A + g s beta (L^-T mt) Y^T
+        dKuf = R.gemm(E3[:, :, 2 * M:], A)
+        w = R.trsm_(L, mt.clone(), transpose=True)
+        R.gemm(R.axpby_dev(gsb, w), Y, transB=True, beta=1.0, C=dKuf)
+        # second side of the two symmetric solves: L^-T E L^-1 = L^-T (L^-T E)^T
+        F2 = torch.empty((S, M, 2 * M), dtype=A.dtype, device=A.device)
+        R.transpose(E3[:, :, :M], out=F2[:, :, :M])
+        R.transpose(E3[:, :, M:2 * M], out=F2[:, :, M:])
+        R.trsm_(L, F2, transpose=True)
+        dKuu = F2[:, :, :M]
+        dZ1, dX, dls1, dvar1 = R.kbuild_bwd(ctx.kind, Z, X, ls, kvar, dKuf, need_dX=True, need_dX2=need[3])
+        dZ2, _, dls2, dvar2 = R.kbuild_bwd(ctx.kind, Z, None, ls, kvar, dKuu)
+        dZ = dZ1 + dZ2
+        dls = dls1 + dls2
+        dkvar = dvar1 + dvar2 - (gsb * (0.5 * P * B)).unsqueeze(1)          # Kff_diag term (:100)
+        # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 ; W adjoint 2 Sbar W ; diag adjoint diag(Sbar)
+        eye = torch.eye(M, dtype=A.dtype, device=A.device).unsqueeze(0).expand(S, M, M).contiguous()
+        Sinv = R.trsm_(Ls, R.trsm_(Ls, eye), transpose=True)
+        minus1 = torch.full((S,), -1.0, dtype=A.dtype, device=A.device)
+        Sbar = R.axpby_dev(coef[:, 0], Sinv, minus1, F2[:, :, M:].contiguous())
+        dW = R.gemm(Sbar, W, alpha=2.0)
+        dd = R.get_diag(Sbar)
+        # mu adjoint: g L^-T (s beta v - mt)
+        dmu = R.trsm_(L, R.axpby_dev(gsb, v, -g, mt), transpose=True)
+        dnoise = (g * sc * (-beta * beta * Q - (0.5 * B * P) * beta)).unsqueeze(1)
+        dY = R.axpby_dev(-gsb, Y, gsb, G1) if need[4] else None             # -g s beta (Y - A^T mt)
+        return None, None, None, dX, dY, dZ, dnoise, dmu, dW, dd, dls, dkvar
+
+
+def svgp_log_pdf(kind, X, Y, Z, noise_var, qU_mean, qU_cov_W, qU_cov_diag, lengthscale, variance,
+                 jitter=0.0, log_pdf_scaling=1.0, mean=None, return_info=False):
+    """SVGPRegressionLogPdf.compute (svgp_regression.py:43-109) as one autograd node -> logL (S,)."""
+    if noise_var.dim() != 2 or noise_var.shape[-1] != 1:
+        raise NotImplementedError("heteroscedastic noise_var of shape (N, P) (svgp_regression.py:61-67) is not "
+                                  "implemented on the fused path")
+    if mean is not None:
+        Y = Y - mean                                            # :78-80
+    S = _lead(X, Y, Z, noise_var, qU_mean, qU_cov_W, qU_cov_diag, lengthscale, variance)
+    args = [_expand(t, S).contiguous() for t in
+            (X, Y, Z, noise_var, qU_mean, qU_cov_W, qU_cov_diag, lengthscale, variance)]
+    return _SVGPLogPdf.apply(kind, float(jitter), float(log_pdf_scaling), *args)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused exact-GP marginal likelihood
+# --------------------------------------------------------------------------------------------------
+class _GPLogPdf(torch.autograd.Function):
+    """gp_regression.py:55-70.  Returns (logL (S,), L, LinvY); L and LinvY are the cached posterior
+    quantities of :72-75 and carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, kind, jitter, X, Y, noise, ls, kvar):
+        S, N, P = X.shape[0], X.shape[1], Y.shape[2]
+        K = R.kbuild_fwd(kind, X, None, ls, kvar, diag_add=noise, diag_const=jitter)   # :55-60
+        L, info = R.potrf_(K)                                                           # :61
+        LinvY = R.trsm_(L, Y.clone())                                                   # :66
+        logdet_l = R.sumlogdiag(L)                                                      # :67 (diag(L) > 0)
+        ss = R.reduce(R.RED_SUMSQ, LinvY)
+        logL = -logdet_l * P - 0.5 * ss - (0.5 * N * P) * _LOG2PI                       # :68-70
+        ctx.kind, ctx.dims = kind, (S, N, P)
+        ctx.save_for_backward(X, ls, kvar, L, LinvY)
+        ctx.mark_non_differentiable(L, LinvY)
+        ctx.info = info
+        return logL, L, LinvY
+
+    @staticmethod
+    def backward(ctx, g, _gL, _gLY):
+        X, ls, kvar, L, LinvY = ctx.saved_tensors
+        S, N, P = ctx.dims
+        g = g.contiguous()
+        # Kbar = g (1/2 a a^T - P/2 K^-1),  a = K^-1 Y = L^-T LinvY ;  Ybar = -g a
+        a = R.trsm_(L, LinvY.clone(), transpose=True)
+        eye = torch.eye(N, dtype=X.dtype, device=X.device).unsqueeze(0).expand(S, N, N).contiguous()
+        Kinv = R.trsm_(L, R.trsm_(L, eye), transpose=True)
+        aaT = R.gemm(a, a, transB=True)
+        Kbar = R.axpby_dev(0.5 * g, aaT, (-0.5 * P) * g, Kinv)
+        dX, _, dls, dvar = R.kbuild_bwd(ctx.kind, X, None, ls, kvar, Kbar)
+        dnoise = R.reduce(R.RED_SUM, R.get_diag(Kbar).unsqueeze(1)).unsqueeze(1)
+        dY = R.axpby_dev(-g, a) if ctx.needs_input_grad[3] else None
+        return None, None, dX, dY, dnoise, dls, dvar
+
+
+def gp_log_pdf(kind, X, Y, noise_var, lengthscale, variance, jitter=0.0, mean=None):
+    """GPRegressionLogPdf.compute (gp_regression.py:42-76) -> (logL (S,), L, LinvY)."""
+    if mean is not None:
+        Y = Y - mean
+    S = _lead(X, Y, noise_var, lengthscale, variance)
+    args = [_expand(t, S).contiguous() for t in (X, Y, noise_var, lengthscale, variance)]
+    return _GPLogPdf.apply(kind, float(jitter), *args)

@@ -1,0 +1,199 @@
+"""CPU stand-in for `mxfusion_b200._raw` -- TEST INFRASTRUCTURE ONLY.
+
+The product's operators (mxfusion_b200/ops.py) call the CUDA library through `mxfusion_b200._raw`
+and raise on CPU tensors.  To check the HOST-SIDE algebra (hand-derived adjoints, module/graph/loop
+logic) in the CPU-only test tier, tests monkeypatch `ops.R` with this module, which offers the same
+function signatures on plain torch CPU tensors.  Nothing under mxfusion_b200/ imports it.
+"""
+import math
+
+import torch
+
+RBF, MATERN12, MATERN32, MATERN52 = 0, 1, 2, 3
+RED_SUM, RED_SUMSQ, RED_DOT, RED_SUMLOG, RED_SUMSQDIFF = 0, 1, 2, 3, 4
+launches = 0
+
+
+def _k(kind, X, X2, ls, var):
+    from oracle import torch_ref
+    return torch_ref.K(kind, X, ls, var, X2)
+
+
+def kbuild_fwd(kind, X, X2, ls, var, diag_add=None, diag_const=0.0, out=None):
+    K = _k(kind, X, X2, ls, var)
+    if X2 is None:
+        n = K.shape[-1]
+        d = torch.full((K.shape[0], 1), float(diag_const), dtype=K.dtype)
+        if diag_add is not None:
+            d = d + diag_add
+        K = K + torch.eye(n, dtype=K.dtype).unsqueeze(0) * d.unsqueeze(-1)
+    if out is not None:
+        out.copy_(K)
+        return out
+    return K.contiguous()
+
+
+def kbuild_bwd(kind, X, X2, ls, var, G, need_dX=True, need_dX2=True):
+    with torch.enable_grad():
+        Xr = X.detach().clone().requires_grad_()
+        X2r = None if X2 is None else X2.detach().clone().requires_grad_()
+        lsr = ls.detach().clone().requires_grad_()
+        vr = var.detach().clone().requires_grad_()
+        K = _k(kind, Xr, X2r, lsr, vr)
+        (K * G).sum().backward()
+    return Xr.grad, (None if X2 is None else X2r.grad), lsr.grad, vr.grad
+
+
+def gemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None, tri=False):
+    a = A.transpose(-1, -2) if transA else A
+    b = B.transpose(-1, -2) if transB else B
+    prod = alpha * torch.matmul(a, b)
+    if C is None:
+        return torch.tril(prod).contiguous() if tri else prod.contiguous()
+    if tri:
+        C.copy_(torch.triu(C, 1) + torch.tril(prod + beta * C))
+    else:
+        C.copy_(prod + beta * C)
+    return C
+
+
+def potrf_(A, info=None):
+    L, inf = torch.linalg.cholesky_ex(torch.tril(A) + torch.tril(A, -1).transpose(-1, -2))
+    A.copy_(L)
+    return A, inf.to(torch.int32)
+
+
+def trsm_(L, B, transpose=False, alpha=1.0):
+    Lt = torch.tril(L)
+    if transpose:
+        X = torch.linalg.solve_triangular(Lt.transpose(-1, -2), B, upper=True)
+    else:
+        X = torch.linalg.solve_triangular(Lt, B, upper=False)
+    B.copy_(alpha * X)
+    return B
+
+
+def copy_ltu(P):
+    return (torch.tril(P) + torch.tril(P, -1).transpose(-1, -2)).contiguous()
+
+
+def symmetrize(A, alpha=1.0):
+    return (alpha * (A + A.transpose(-1, -2))).contiguous()
+
+
+def tril(A, strict=False):
+    return torch.tril(A, -1 if strict else 0).contiguous()
+
+
+def transpose(A, out=None):
+    t = A.transpose(-1, -2)
+    if out is not None:
+        out.copy_(t)
+        return out
+    return t.contiguous()
+
+
+def reduce(op, a, b=None, scale=1.0):
+    if op == RED_SUM:
+        t = a
+    elif op == RED_SUMSQ:
+        t = a * a
+    elif op == RED_DOT:
+        t = a * b
+    elif op == RED_SUMLOG:
+        t = torch.log(a)
+    else:
+        t = (a - b) ** 2
+    return scale * t.sum(dim=(1, 2))
+
+
+def sumlogdiag(A):
+    return torch.log(torch.abs(torch.diagonal(A, dim1=-2, dim2=-1))).sum(-1)
+
+
+def add_diag_(A, d=None, c=0.0):
+    n = A.shape[-1]
+    add = torch.full((A.shape[0], n), float(c), dtype=A.dtype)
+    if d is not None:
+        add = add + d
+    A.diagonal(dim1=-2, dim2=-1).add_(add)
+    return A
+
+
+def get_diag(A):
+    return torch.diagonal(A, dim1=-2, dim2=-1).contiguous()
+
+
+def _lp(x, m, v):
+    return -0.5 * math.log(2 * math.pi) - 0.5 * torch.log(v) - (x - m) ** 2 / (2 * v)
+
+
+def normal_logpdf_sum(x, m, v, scale=1.0):
+    return (scale * torch.sum(torch.mean(_lp(x, m, v), dim=0))).reshape(1)
+
+
+def normal_logpdf_sum_bwd(x, m, v, gout, scale=1.0, need=(True, True, True)):
+    with torch.enable_grad():
+        xr, mr, vr = [t.detach().clone().requires_grad_() for t in (x, m, v)]
+        (normal_logpdf_sum(xr, mr, vr, scale) * gout.reshape(-1)[0]).sum().backward()
+    return (xr.grad if need[0] else None, mr.grad if need[1] else None, vr.grad if need[2] else None)
+
+
+def normal_reparam(m, v, S, eps=None, seed=0, offset=0, return_eps=False):
+    shape = (S,) + tuple(m.shape[1:])
+    if eps is None:
+        g = torch.Generator().manual_seed(int(seed) * 1000003 + int(offset))
+        eps = torch.randn(shape, generator=g, dtype=m.dtype)
+    w = eps * torch.sqrt(v) + m
+    return (w, eps) if return_eps else w
+
+
+def adam_step_(w, g, m, v, step_count, lr, beta1=0.9, beta2=0.999, eps=1e-8, rescale=1.0):
+    t = int(step_count.item()) + 1
+    gg = g * rescale
+    m.mul_(beta1).add_(gg, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+    lr_t = lr * math.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+    w.sub_(lr_t * m / (v.sqrt() + eps))
+    step_count += 1
+
+
+def gather_rows(src, idx, off, rows, out=None):
+    o = int(off.item()) if off is not None else 0
+    r = src[idx[o:o + rows]]
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def axpby_dev(a, X, b=None, Y=None, out=None):
+    def cv(c):
+        return c.reshape((-1,) + (1,) * (X.dim() - 1))
+    r = X if a is None else cv(a) * X
+    if Y is not None:
+        r = r + cv(b) * Y
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r.contiguous()
+
+
+def softplus_fwd(x, offset=0.0):
+    return torch.nn.functional.softplus(x) + offset
+
+
+def softplus_bwd(x, gy):
+    return gy * torch.sigmoid(x)
+
+
+def svgp_bwd_assemble(Phi, T, U, mt, v, coef):
+    M = Phi.shape[-1]
+    I = torch.eye(M, dtype=Phi.dtype).unsqueeze(0)
+    c = [coef[:, i].reshape(-1, 1, 1) for i in range(6)]
+    mm = mt @ mt.transpose(-1, -2)
+    vm = v @ mt.transpose(-1, -2)
+    E = c[2] * mm + c[0] * (T - I) - c[1] * Phi + c[1] * (U + U.transpose(-1, -2)) - c[3] * (vm + vm.transpose(-1, -2))
+    ES = c[0] * I + c[1] * Phi
+    ER = -c[4] * (T - I) - c[5] * mm
+    return torch.cat([E, ES, ER], dim=-1).contiguous()

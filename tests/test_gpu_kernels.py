@@ -1,0 +1,285 @@
+"""Parity of every C-ABI kernel (through mxfusion_b200._raw -> ctypes -> libmxf_b200.so) with the
+NumPy oracle on the same seeded inputs.  Tolerances: float64 follows the reference's own
+`np.allclose` defaults (rtol 1e-5, atol 1e-8; testing/modules/svgpregression_test.py:115) tightened
+to 1e-9 where the arithmetic is benign; float32 uses the only fp32 tolerance the reference states
+(rtol 1e-4, atol 1e-5; testing/components/distributions/normal_test.py:63-67) unless noted."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kernels as ok, linalg as ol, normal as on, loop as oloop
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [ok.RBF, ok.MATERN12, ok.MATERN32, ok.MATERN52]
+DT = {'f64': (torch.float64, np.float64, 1e-9, 1e-11), 'f32': (torch.float32, np.float32, 2e-4, 2e-5)}
+
+
+def T(a, cuda, dt):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=cuda)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('shape', [(1, 10, 7, 3, True), (2, 33, 130, 8, False), (1, 70, 300, 16, True),
+                                   (3, 5, 1, 1, False), (1, 257, 513, 2, False)])
+def test_kbuild_cross(cuda, prec, kind, shape):
+    from mxfusion_b200 import _raw
+    S, N, N2, D, ard = shape
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(1)
+    X = rng.uniform(-2, 2, (S, N, D)).astype(ndt)
+    X2 = rng.uniform(-2, 2, (S, N2, D)).astype(ndt)
+    ls = rng.uniform(0.5, 2.0, (S, D if ard else 1)).astype(ndt)
+    var = rng.uniform(0.5, 2.0, (S, 1)).astype(ndt)
+    want = ok.K(kind, X.astype(np.float64), ls.astype(np.float64), var.astype(np.float64), X2.astype(np.float64))
+    got = _raw.kbuild_fwd(kind, T(X, cuda, tdt), T(X2, cuda, tdt), T(ls, cuda, tdt), T(var, cuda, tdt))
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=rtol, atol=atol * 10 if prec == 'f32' else atol)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('kind', KINDS)
+def test_kbuild_symmetric_with_diag(cuda, prec, kind):
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(2)
+    S, N, D = 2, 67, 3
+    X = rng.uniform(-2, 2, (S, N, D)).astype(ndt)
+    ls = rng.uniform(0.5, 2.0, (S, D)).astype(ndt)
+    var = rng.uniform(0.5, 2.0, (S, 1)).astype(ndt)
+    noise = rng.uniform(0.1, 0.2, (S, 1)).astype(ndt)
+    want = ok.K(kind, X.astype(np.float64), ls.astype(np.float64), var.astype(np.float64)) + \
+        np.eye(N)[None] * (noise.astype(np.float64)[..., None] + 1e-3)
+    got = _raw.kbuild_fwd(kind, T(X, cuda, tdt), None, T(ls, cuda, tdt), T(var, cuda, tdt),
+                          diag_add=T(noise, cuda, tdt), diag_const=1e-3)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=rtol, atol=atol * 10 if prec == 'f32' else atol)
+
+
+def test_kbuild_sample_broadcast(cuda):
+    """X shared over samples (S=1) while the kernel parameters are sampled (S=3)."""
+    from mxfusion_b200 import _raw
+    rng = np.random.RandomState(3)
+    X = rng.rand(1, 20, 4)
+    X2 = rng.rand(1, 9, 4)
+    ls = rng.uniform(0.5, 2.0, (3, 4))
+    var = rng.uniform(0.5, 2.0, (3, 1))
+    want = ok.K(ok.RBF, np.repeat(X, 3, 0), ls, var, np.repeat(X2, 3, 0))
+    got = _raw.kbuild_fwd(ok.RBF, T(X, cuda, torch.float64), T(X2, cuda, torch.float64),
+                          T(ls, cuda, torch.float64), T(var, cuda, torch.float64))
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('sym', [False, True])
+@pytest.mark.parametrize('ard', [False, True])
+def test_kbuild_bwd_matches_autograd_of_restatement(cuda, kind, sym, ard):
+    """The reference never tests gradients; the oracle is autograd through the
+    op-for-op torch restatement (oracle/torch_ref.py) in float64."""
+    from mxfusion_b200 import _raw
+    from oracle import torch_ref
+    rng = np.random.RandomState(4)
+    S, N, N2, D = 2, 37, 37 if sym else 53, 5
+    X = torch.tensor(rng.uniform(-2, 2, (S, N, D)), requires_grad=True)
+    X2 = None if sym else torch.tensor(rng.uniform(-2, 2, (S, N2, D)), requires_grad=True)
+    ls = torch.tensor(rng.uniform(0.5, 2.0, (S, D if ard else 1)), requires_grad=True)
+    var = torch.tensor(rng.uniform(0.5, 2.0, (S, 1)), requires_grad=True)
+    G = torch.tensor(rng.randn(S, N, N2))
+    Kt = torch_ref.K(kind, X, ls, var, X2)
+    (Kt * G).sum().backward()
+    dX, dX2, dls, dvar = _raw.kbuild_bwd(kind, X.detach().to(cuda), None if sym else X2.detach().to(cuda),
+                                         ls.detach().to(cuda), var.detach().to(cuda), G.to(cuda))
+    np.testing.assert_allclose(dX.cpu().numpy(), X.grad.numpy(), rtol=1e-7, atol=1e-9)
+    if not sym:
+        np.testing.assert_allclose(dX2.cpu().numpy(), X2.grad.numpy(), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(dls.cpu().numpy(), ls.grad.numpy(), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(dvar.cpu().numpy(), var.grad.numpy(), rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('ta,tb', [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize('mnk', [(5, 7, 3), (130, 65, 33), (257, 300, 129), (64, 64, 64), (1, 1, 1)])
+def test_gemm(cuda, prec, ta, tb, mnk):
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    m, n, k = mnk
+    rng = np.random.RandomState(5)
+    S = 2
+    A = rng.randn(S, k, m) if ta else rng.randn(S, m, k)
+    B = rng.randn(S, n, k) if tb else rng.randn(S, k, n)
+    C0 = rng.randn(S, m, n)
+    want = 0.7 * ol.gemm2(A, B, ta, tb) + 0.3 * C0
+    C = T(C0, cuda, tdt)
+    _raw.gemm(T(A, cuda, tdt), T(B, cuda, tdt), ta, tb, alpha=0.7, beta=0.3, C=C)
+    np.testing.assert_allclose(C.cpu().numpy(), want, rtol=rtol, atol=atol * 50 if prec == 'f32' else atol)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('n', [1, 3, 64, 65, 130, 300, 513])
+def test_potrf(cuda, prec, n):
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(6)
+    S = 2
+    W = rng.randn(S, n, n)
+    A = W @ np.swapaxes(W, -1, -2) + n * np.eye(n)[None]
+    want = ol.potrf(A)
+    L, info = _raw.potrf_(T(A, cuda, tdt))
+    assert info.cpu().tolist() == [0, 0]
+    got = L.cpu().numpy()
+    assert np.all(np.triu(got, 1) == 0), "strict upper triangle must be zeroed (MXNet potrf convention)"
+    np.testing.assert_allclose(got, want, rtol=rtol * 5, atol=atol * 100 if prec == 'f32' else atol * 100)
+
+
+def test_potrf_reports_first_bad_pivot(cuda):
+    from mxfusion_b200 import _raw
+    A = np.eye(100)[None].repeat(2, 0)
+    A[1, 70, 70] = -1.0
+    L, info = _raw.potrf_(T(A, cuda, torch.float64))
+    assert info.cpu().tolist() == [0, 71]
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('transpose', [False, True])
+@pytest.mark.parametrize('n,nrhs', [(1, 1), (3, 1), (64, 5), (65, 130), (200, 257), (513, 33)])
+def test_trsm(cuda, prec, transpose, n, nrhs):
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(7)
+    S = 2
+    Lm = np.tril(rng.randn(S, n, n)) * 0.1 + 2.0 * np.eye(n)[None]
+    B = rng.randn(S, n, nrhs)
+    want = ol.trsm(Lm, B, transpose=transpose, alpha=0.5)
+    Bt = T(B, cuda, tdt)
+    _raw.trsm_(T(Lm, cuda, tdt), Bt, transpose=transpose, alpha=0.5)
+    np.testing.assert_allclose(Bt.cpu().numpy(), want, rtol=rtol * 5, atol=atol * 100)
+
+
+def test_trsm_broadcast_factor(cuda):
+    from mxfusion_b200 import _raw
+    rng = np.random.RandomState(8)
+    Lm = np.tril(rng.randn(1, 50, 50)) * 0.1 + 2.0 * np.eye(50)[None]
+    B = rng.randn(3, 50, 7)
+    want = ol.trsm(np.repeat(Lm, 3, 0), B)
+    Bt = T(B, cuda, torch.float64)
+    _raw.trsm_(T(Lm, cuda, torch.float64), Bt)
+    np.testing.assert_allclose(Bt.cpu().numpy(), want, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+def test_square_matrix_utilities(cuda, prec):
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(9)
+    A = rng.randn(2, 77, 77).astype(ndt)
+    At = T(A, cuda, tdt)
+    At_T = np.swapaxes(A, -1, -2)
+    np.testing.assert_array_equal(_raw.copy_ltu(At).cpu().numpy(), np.tril(A) + np.swapaxes(np.tril(A, -1), -1, -2))
+    np.testing.assert_allclose(_raw.symmetrize(At, 0.5).cpu().numpy(), 0.5 * (A + At_T), rtol=1e-6)
+    np.testing.assert_array_equal(_raw.tril(At).cpu().numpy(), np.tril(A))
+    np.testing.assert_array_equal(_raw.tril(At, strict=True).cpu().numpy(), np.tril(A, -1))
+    R = rng.randn(2, 45, 131).astype(ndt)
+    np.testing.assert_array_equal(_raw.transpose(T(R, cuda, tdt)).cpu().numpy(), np.swapaxes(R, -1, -2))
+    d = rng.randn(2, 77).astype(ndt)
+    want = A + ol.make_diagonal(d) + np.eye(77, dtype=ndt) * ndt(0.25)
+    got = _raw.add_diag_(T(A, cuda, tdt), T(d, cuda, tdt), 0.25).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(_raw.get_diag(At).cpu().numpy(), ol.make_diagonal_backward(A))
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('shape', [(2, 1, 1), (2, 33, 7), (1, 1000, 1024), (3, 517, 129)])
+def test_reductions(cuda, prec, shape):
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(10)
+    a = rng.uniform(0.5, 1.5, shape)
+    b = rng.randn(*shape)
+    at, bt = T(a, cuda, tdt), T(b, cuda, tdt)
+    for op, want in [(_raw.RED_SUM, a.sum((1, 2))), (_raw.RED_SUMSQ, (a * a).sum((1, 2))),
+                     (_raw.RED_DOT, (a * b).sum((1, 2))), (_raw.RED_SUMLOG, np.log(a).sum((1, 2)))]:
+        got = _raw.reduce(op, at, bt if op == _raw.RED_DOT else None, scale=0.5)
+        np.testing.assert_allclose(got.cpu().numpy(), 0.5 * want, rtol=rtol, atol=atol * 100)
+    A = rng.uniform(0.5, 2, (2, 40, 40))
+    np.testing.assert_allclose(_raw.sumlogdiag(T(A, cuda, tdt)).cpu().numpy(), ol.sumlogdiag(A), rtol=rtol)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+def test_normal_logpdf_sum_and_adjoint(cuda, prec):
+    from mxfusion_b200 import _raw
+    from oracle import torch_ref
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(11)
+    S, shape = 3, (41, 5)
+    x = rng.randn(S, *shape)
+    m = rng.randn(1, *shape)
+    v = rng.uniform(0.5, 2.0, (1,) + shape)
+    want = 1.7 * on.factor_reduce(on.log_pdf(m, v, x))
+    got = _raw.normal_logpdf_sum(T(x, cuda, tdt), T(m, cuda, tdt), T(v, cuda, tdt), scale=1.7)
+    np.testing.assert_allclose(got.cpu().numpy()[0], want, rtol=rtol * 5)
+    xt = torch.tensor(x, requires_grad=True)
+    mt = torch.tensor(m, requires_grad=True)
+    vt = torch.tensor(v, requires_grad=True)
+    (1.7 * torch.sum(torch.mean(torch_ref.normal_log_pdf(mt, vt, xt), dim=0)) * 0.3).backward()
+    gx, gm, gv = _raw.normal_logpdf_sum_bwd(T(x, cuda, tdt), T(m, cuda, tdt), T(v, cuda, tdt),
+                                            torch.tensor([0.3], dtype=tdt, device=cuda), scale=1.7)
+    np.testing.assert_allclose(gx.cpu().numpy(), xt.grad.numpy(), rtol=rtol * 5, atol=atol)
+    np.testing.assert_allclose(gm.cpu().numpy(), mt.grad.numpy(), rtol=rtol * 5, atol=atol * 10)
+    np.testing.assert_allclose(gv.cpu().numpy(), vt.grad.numpy(), rtol=rtol * 5, atol=atol * 10)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+def test_normal_reparam_injected_eps(cuda, prec):
+    """normal_test.py:78-109 pattern: the standard-normal draw is injected (MockMXNetRandomGenerator)."""
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(12)
+    S, shape = 4, (13, 3)
+    eps = rng.randn(S, *shape)
+    m = rng.randn(1, *shape)
+    v = rng.uniform(0.5, 2.0, (1,) + shape)
+    got = _raw.normal_reparam(T(m, cuda, tdt), T(v, cuda, tdt), S, eps=T(eps, cuda, tdt))
+    np.testing.assert_allclose(got.cpu().numpy(), on.draw_samples(m, v, eps), rtol=rtol, atol=atol)
+
+
+def test_normal_reparam_philox_moments(cuda):
+    from mxfusion_b200 import _raw
+    m = torch.zeros((1, 1 << 20), device=cuda)
+    v = torch.ones((1, 1 << 20), device=cuda)
+    w, eps = _raw.normal_reparam(m, v, 4, seed=123, offset=0, return_eps=True)
+    assert torch.equal(w, eps)
+    z = w.double().cpu().numpy().ravel()
+    assert abs(z.mean()) < 3e-3 and abs(z.std() - 1) < 3e-3
+    assert abs(((z - z.mean()) ** 4).mean() - 3) < 3e-2
+    w2 = _raw.normal_reparam(m, v, 4, seed=123, offset=0)
+    assert torch.equal(w, w2), "counter-based stream must be reproducible"
+    w3 = _raw.normal_reparam(m, v, 4, seed=123, offset=1)
+    assert not torch.equal(w, w3)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+def test_adam_matches_mxnet_update_rule(cuda, prec):
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(13)
+    n = 1000
+    w = rng.randn(n)
+    m = np.zeros(n)
+    v = np.zeros(n)
+    wt, mt, vt = T(w, cuda, tdt), T(m, cuda, tdt), T(v, cuda, tdt)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=cuda)
+    for t in range(1, 6):
+        g = rng.randn(n)
+        w, m, v = oloop.adam_step(w, g, m, v, t, lr=0.01, rescale_grad=1. / 16)
+        _raw.adam_step_(wt, T(g, cuda, tdt), mt, vt, cnt, lr=0.01, rescale=1. / 16)
+    assert int(cnt.item()) == 5
+    np.testing.assert_allclose(wt.cpu().numpy(), w, rtol=rtol, atol=atol)
+
+
+def test_gather_rows_bit_exact(cuda):
+    from mxfusion_b200 import _raw
+    rng = np.random.RandomState(14)
+    src = rng.randn(1000, 9).astype(np.float32)
+    idx = rng.permutation(1000).astype(np.int64)
+    off = torch.tensor([128], dtype=torch.int64, device=cuda)
+    got = _raw.gather_rows(torch.as_tensor(src, device=cuda), torch.as_tensor(idx, device=cuda), off, 64)
+    np.testing.assert_array_equal(got.cpu().numpy(), src[idx[128:192]])
