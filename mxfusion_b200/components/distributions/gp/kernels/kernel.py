@@ -1,0 +1,106 @@
+"""Kernel base classes (mxfusion/components/distributions/gp/kernels/kernel.py:25-373)."""
+from copy import copy
+
+import torch
+
+from ....functions.mxfusion_function import MXFusionFunction
+from ....variables.variable import Variable
+from .....common.exceptions import ModelSpecificationError
+
+
+def slice_axis(F, array, axis, indices):
+    """active_dims gather along one axis (mxfusion/util/util.py:23-62); index work, bit-exact."""
+    idx = torch.as_tensor(list(indices), dtype=torch.long, device=array.device)
+    return torch.index_select(array, axis if axis >= 0 else array.dim() + axis, idx)
+
+
+class Kernel(MXFusionFunction):
+    broadcastable = False
+
+    def __init__(self, input_dim, name, active_dims=None, dtype=None, ctx=None):
+        self.__dict__['_parameter_names'] = []
+        super(Kernel, self).__init__(func_name=name, dtype=dtype, broadcastable=self.broadcastable)
+        self.input_dim = input_dim
+        self.ctx = ctx
+        self.active_dims = active_dims
+
+    def __setattr__(self, name, value):
+        if isinstance(value, Variable) and name not in self._parameter_names:
+            self._parameter_names.append(name)
+        super(Kernel, self).__setattr__(name, value)
+
+    @property
+    def local_parameters(self):
+        return {getattr(self, n) for n in self._parameter_names}
+
+    @property
+    def parameters(self):
+        raise NotImplementedError
+
+    @property
+    def input_names(self):
+        return ['X', 'X2']
+
+    @property
+    def output_names(self):
+        return ['covariance']
+
+    def _strip(self, kernel_params):
+        off = len(self.name) + 1
+        return {k[off:]: v for k, v in kernel_params.items() if k.startswith(self.name + '_')}
+
+    def K(self, F, X, X2=None, **kernel_params):
+        """kernel.py:96-123."""
+        params = self._strip(kernel_params)
+        if self.active_dims is not None:
+            X = slice_axis(F, X, -1, self.active_dims)
+            if X2 is not None:
+                X2 = slice_axis(F, X2, -1, self.active_dims)
+        return self._compute_K(F=F, X=X, X2=X2, **params)
+
+    def Kdiag(self, F, X, **kernel_params):
+        """kernel.py:125-147."""
+        params = self._strip(kernel_params)
+        if self.active_dims is not None:
+            X = slice_axis(F, X, -1, self.active_dims)
+        return self._compute_Kdiag(F=F, X=X, **params)
+
+    def _compute_K(self, F, X, X2=None, **kernel_params):
+        raise NotImplementedError
+
+    def _compute_Kdiag(self, F, X, **kernel_params):
+        raise NotImplementedError
+
+    def fetch_parameters(self, params):
+        """kernel.py:232-245."""
+        return {n: params[v.uuid] for n, v in self.parameters.items()}
+
+    def eval(self, F, X, X2=None, **kernel_params):
+        return self.K(F, X, X2, **kernel_params)
+
+    def replicate_self(self, attribute_map=None):
+        rep = copy(self)
+        rep.__dict__['_parameter_names'] = []
+        for n in self._parameter_names:
+            setattr(rep, n, getattr(self, n).replicate_self(attribute_map))
+        rep.active_dims = copy(self.active_dims)
+        return rep
+
+    def add(self, other, name='add'):
+        raise ModelSpecificationError("kernel addition is outside the hot-path scope of this build (SURVEY 8f-4)")
+
+    def multiply(self, other, name='mul'):
+        raise ModelSpecificationError("kernel multiplication is outside the hot-path scope of this build (SURVEY 8f-4)")
+
+    __add__ = add
+    __mul__ = multiply
+
+
+class NativeKernel(Kernel):
+    @property
+    def parameters(self):
+        return {self.name + '_' + n: getattr(self, n) for n in self._parameter_names}
+
+    @property
+    def parameter_names(self):
+        return [self.name + '_' + n for n in self._parameter_names]

@@ -1,0 +1,56 @@
+"""Univariate Normal (mxfusion/components/distributions/normal.py:26-116), the distribution behind the
+mean-field MC-ELBO (BASELINE config 4)."""
+import math
+
+import torch
+
+from .distribution import Distribution
+from ..variables.variable import Variable
+from ..variables.runtime_variable import arrays_as_samples
+from ... import ops
+
+
+class Normal(Distribution):
+    def __init__(self, mean, variance, rand_gen=None, dtype=None, ctx=None):
+        inputs = [('mean', mean), ('variance', variance)]
+        super(Normal, self).__init__(inputs=inputs, outputs=None, input_names=['mean', 'variance'],
+                                     output_names=['random_variable'], rand_gen=rand_gen, dtype=dtype, ctx=ctx)
+
+    def log_pdf_impl(self, mean, variance, random_variable, F=None):
+        """normal.py:52-70, elementwise (used when the per-element values are needed)."""
+        logvar = math.log(2 * math.pi) / -2 + torch.log(variance) / -2
+        return (logvar + torch.square(random_variable - mean) / (-2 * variance)) * self.log_pdf_scaling
+
+    def log_pdf_sum(self, F, variables):
+        """normal.py:67-69 + factor_graph.py:223 fused: one pass, one scalar."""
+        kw = self.fetch_runtime_inputs(variables)
+        kw.update(self.fetch_runtime_outputs(variables))
+        x, m, v = kw['random_variable'], kw['mean'], kw['variance']
+        n = max(x[0].numel(), m[0].numel(), v[0].numel())
+        if not (x[0].numel() == m[0].numel() == v[0].numel() == n):
+            shape = torch.broadcast_shapes(x.shape[1:], m.shape[1:], v.shape[1:])
+            x, m, v = [t.expand((t.shape[0],) + tuple(shape)) for t in (x, m, v)]
+        return ops.normal_log_pdf_sum(x, m, v, self.log_pdf_scaling).reshape(())
+
+    def draw_samples_impl(self, mean, variance, rv_shape, num_samples=1, F=None):
+        """normal.py:72-92: eps * sqrt(variance) + mean with eps ~ N(0,1) of shape (S,) + rv_shape."""
+        full = (num_samples,) + tuple(rv_shape)
+        mean = mean.expand((mean.shape[0],) + tuple(rv_shape)) if tuple(mean.shape[1:]) != tuple(rv_shape) else mean
+        variance = variance.expand((variance.shape[0],) + tuple(rv_shape)) \
+            if tuple(variance.shape[1:]) != tuple(rv_shape) else variance
+        gen = self._rand_gen
+        if getattr(gen, 'in_kernel', False):
+            seed, offset = gen.next_stream()
+            return ops.normal_draw(mean, variance, num_samples, seed=seed, offset=offset)
+        eps = gen.sample_normal(shape=full, dtype=self.dtype, ctx=self.ctx)
+        return ops.normal_draw(mean, variance, num_samples, eps=eps)
+
+    @staticmethod
+    def define_variable(mean=0., variance=1., shape=None, rand_gen=None, dtype=None, ctx=None):
+        normal = Normal(mean=mean, variance=variance, rand_gen=rand_gen, dtype=dtype, ctx=ctx)
+        normal._generate_outputs(shape=shape)
+        return normal.random_variable
+
+    def _generate_outputs(self, shape):
+        self.set_outputs([Variable(value=None, shape=shape if shape is not None else (1,))])
+        # Variable(value=None) made a plain parameter node; attaching it as our output makes it a RANDVAR

@@ -1,0 +1,66 @@
+"""One optimisation step of the hot loop as a replayable unit.
+
+The reference's loop body (minibatch_loop.py:81-92, batch_loop.py:52-60) is: record -> executor ->
+backward -> Trainer.step(batch_size) -> loss.asscalar().  Here the forward+backward of a fixed-shape
+step is captured once into a CUDA graph (about a hundred kernel launches replayed with one driver
+call), the gradient bucket is all-reduced over NCCL when running data-parallel, and one fused Adam
+launch updates the flat parameter buffer.  Nothing synchronises with the host."""
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..common.exceptions import InferenceError
+
+
+class Stepper(object):
+    def __init__(self, infr_executor, params, optimizer, learning_rate, rescale_grad, example_batch,
+                 use_cuda_graph=True, warmup_steps=2):
+        if optimizer != 'adam':
+            raise InferenceError("only optimizer='adam' (the reference's default, grad_based_inference.py:67) is "
+                                 "implemented on the fused update path; got %r" % (optimizer,))
+        self.executor, self.params = infr_executor, params
+        self.lr = float(learning_rate)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rescale = float(rescale_grad) / self.world          # all-reduce(SUM) / world = average over ranks
+        self.static_in = [torch.empty_like(b) for b in example_batch]
+        self.loss = None
+        self.graph = None
+        self.use_graph = bool(use_cuda_graph) and self.static_in[0].is_cuda if self.static_in else False
+        self.warmup_steps = warmup_steps
+        self.n_calls = 0
+
+    def _fwd_bwd(self):
+        self.params.gflat.zero_()
+        loss, loss_for_gradient = self.executor(None, *self.static_in)
+        loss_for_gradient.backward()
+        return loss.detach().reshape(())
+
+    def _update(self):
+        p = self.params
+        if self.world > 1:
+            dist.all_reduce(p.gflat, op=dist.ReduceOp.SUM)
+        ops.R.adam_step_(p.flat, p.gflat, p.adam_m, p.adam_v, p.adam_t, lr=self.lr, rescale=self.rescale)
+
+    def step(self, batch=None):
+        """Runs one step on `batch` (copied into the static inputs) and returns the device loss scalar."""
+        if batch is not None:
+            for dst, src in zip(self.static_in, batch):
+                dst.copy_(src, non_blocking=True)
+        self.n_calls += 1
+        if not self.use_graph:
+            self.loss = self._fwd_bwd()
+        elif self.graph is None and self.n_calls <= self.warmup_steps:
+            self.loss = self._fwd_bwd()                           # eager warm-up before capture
+        elif self.graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._static_loss = self._fwd_bwd()
+            self.graph = g
+            g.replay()
+            self.loss = self._static_loss
+        else:
+            self.graph.replay()
+            self.loss = self._static_loss
+        self._update()
+        return self.loss

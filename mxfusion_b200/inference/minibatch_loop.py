@@ -1,0 +1,113 @@
+"""Minibatch gradient loop (mxfusion/inference/minibatch_loop.py:21-95).
+
+Semantics kept from the reference: `max_iter` counts EPOCHS (:75); batches come from a shuffled
+sampler with ``last_batch='rollover'`` (:68-70); gradients are rescaled by 1/batch_size
+(`trainer.step(batch_size=...)`, :90-91); `rv_scaling` re-weights the likelihood of the listed random
+variables (:39).  B200-side: the data set is copied to HBM once and each step's rows are gathered on
+the device by a kernel reading the epoch's permutation (`data_resident=True`, default), or -- when
+`data_resident=False` -- gathered on the host into pinned memory and streamed host-to-device every
+step.  The loss is accumulated on the device; the host reads it once per epoch (or per step when
+verbose, as the reference always does, :92)."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .grad_loop import GradLoop
+from ._stepper import Stepper
+from .. import ops
+
+
+class RolloverBatchSampler(object):
+    """Index batches of one epoch after another: shuffle `arange(n)` with the NumPy global generator (what
+    gluon's RandomSampler does), prepend the remainder kept from the previous epoch, emit the full batches,
+    keep the new remainder (BatchSampler(last_batch='rollover')).  Integer work: bit-exact."""
+
+    def __init__(self, n, batch_size, rng=None, shuffle=True):
+        self.n, self.batch_size, self.shuffle = int(n), int(batch_size), shuffle
+        self.rng = np.random if rng is None else rng
+        self._prev = np.zeros((0,), dtype=np.int64)
+
+    def epoch_indices(self):
+        idx = np.arange(self.n, dtype=np.int64)
+        if self.shuffle:
+            self.rng.shuffle(idx)
+        idx = np.concatenate([self._prev, idx])
+        nfull = idx.shape[0] // self.batch_size
+        self._prev = idx[nfull * self.batch_size:].copy()
+        return idx[:nfull * self.batch_size], nfull
+
+
+class MinibatchInferenceLoop(GradLoop):
+    def __init__(self, batch_size=100, rv_scaling=None, data_resident=True, use_cuda_graph=True, rng=None):
+        super(MinibatchInferenceLoop, self).__init__()
+        self.batch_size = batch_size
+        self.rv_scaling = {v.uuid: s for v, s in rv_scaling.items()} if rv_scaling is not None else rv_scaling
+        self.data_resident = data_resident
+        self.use_cuda_graph = use_cuda_graph
+        self.rng = rng
+        self.h2d_bytes_per_step = 0
+        self.d2h_bytes_per_step = 0
+
+    def run(self, infr_executor, data, param_dict, ctx, optimizer='adam', learning_rate=1e-3, max_iter=1000,
+            verbose=False, update_shape_constants=None, max_steps=None, on_step=None):
+        B = self.batch_size
+        n = data[0].shape[0]
+        sampler = RolloverBatchSampler(n, B, rng=self.rng)
+        dev = torch.device(ctx)
+        cols = [int(np.prod(d.shape[1:])) for d in data]
+        if self.data_resident:
+            src = [d.to(dev).reshape(n, c).contiguous() for d, c in zip(data, cols)]
+            idx_dev = torch.empty((n + B,), dtype=torch.int64, device=dev)
+            off = torch.zeros((1,), dtype=torch.int64, device=dev)
+        else:
+            src = [d.detach().cpu().reshape(n, c).contiguous() for d, c in zip(data, cols)]
+            pinned = [torch.empty((B, c), dtype=d.dtype).pin_memory() if dev.type == 'cuda'
+                      else torch.empty((B, c), dtype=d.dtype) for d, c in zip(src, cols)]
+            self.h2d_bytes_per_step = sum(p.numel() * p.element_size() for p in pinned)
+        example = [torch.empty((B,) + tuple(d.shape[1:]), dtype=d.dtype, device=dev) for d in data]
+        if update_shape_constants is not None:
+            update_shape_constants(example)
+        stepper = Stepper(infr_executor, param_dict, optimizer, learning_rate, 1.0 / B, example,
+                          use_cuda_graph=self.use_cuda_graph)
+        flat_in = [s.reshape(B, c) for s, c in zip(stepper.static_in, cols)]
+        loss_acc = torch.zeros((), dtype=example[0].dtype, device=dev)
+        loss_host = torch.empty((1,), dtype=example[0].dtype)
+        if dev.type == 'cuda':
+            loss_host = loss_host.pin_memory()
+        self.d2h_bytes_per_step = loss_host.element_size()
+        epoch_losses, steps_done = [], 0
+        for e in range(max_iter):
+            idx, nfull = sampler.epoch_indices()
+            if self.data_resident:
+                idx_dev[:idx.shape[0]].copy_(torch.from_numpy(idx), non_blocking=True)
+            else:
+                idx_t = torch.from_numpy(idx)
+            loss_acc.zero_()
+            for i in range(nfull):
+                if self.data_resident:
+                    off.fill_(i * B)
+                    for s, dst in zip(src, flat_in):
+                        ops.R.gather_rows(s, idx_dev, off, B, out=dst)
+                    loss = stepper.step()
+                else:
+                    sel = idx_t[i * B:(i + 1) * B]
+                    for s, p, dst in zip(src, pinned, flat_in):
+                        torch.index_select(s, 0, sel, out=p)
+                        dst.copy_(p, non_blocking=True)
+                    loss = stepper.step()
+                    loss_host.copy_(loss.reshape(1), non_blocking=True)       # the reference's asscalar()
+                loss_acc += loss
+                steps_done += 1
+                if on_step is not None:
+                    on_step(steps_done, loss)
+                if verbose:
+                    print('\repoch {} Iteration {} loss: {}\t\t\t'.format(e + 1, i + 1, float(loss)), end='')
+                if max_steps is not None and steps_done >= max_steps:
+                    break
+            if verbose:
+                print('epoch-loss: {} '.format(float(loss_acc) / max(nfull, 1)))
+            epoch_losses.append(loss_acc / max(nfull, 1))
+            if max_steps is not None and steps_done >= max_steps:
+                break
+        self.last_stepper = stepper
+        return epoch_losses

@@ -1,0 +1,2 @@
+from .gp_regression import GPRegression, GPRegressionLogPdf, GPRegressionMeanVariancePrediction  # noqa: F401
+from .svgp_regression import SVGPRegression, SVGPRegressionLogPdf, SVGPRegressionMeanVariancePrediction  # noqa: F401
