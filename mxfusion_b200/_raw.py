@@ -8,7 +8,7 @@ ops.py) and no fallback: a CPU tensor or a missing library raises.
 import torch
 
 from . import _lib
-from ._lib import lib, ptr, stream_ptr, check, dtype_code, require_cuda
+from ._lib import lib, ptr, stream_ptr, check, dtype_code, require_cuda, launch_count  # noqa: F401
 
 RBF, MATERN12, MATERN32, MATERN52 = 0, 1, 2, 3
 RED_SUM, RED_SUMSQ, RED_DOT, RED_SUMLOG, RED_SUMSQDIFF = 0, 1, 2, 3, 4

@@ -28,6 +28,7 @@ class Stepper(object):
         self.use_graph = bool(use_cuda_graph) and self.static_in[0].is_cuda if self.static_in else False
         self.warmup_steps = warmup_steps
         self.n_calls = 0
+        self.launches_per_step = None    # library kernels launched by one forward+backward (counted on an eager step)
 
     def _fwd_bwd(self):
         self.params.gflat.zero_()
@@ -47,10 +48,10 @@ class Stepper(object):
             for dst, src in zip(self.static_in, batch):
                 dst.copy_(src, non_blocking=True)
         self.n_calls += 1
-        if not self.use_graph:
+        if not self.use_graph or (self.graph is None and self.n_calls <= self.warmup_steps):
+            c0 = ops.R.launch_count()                             # eager step (also the warm-up before capture)
             self.loss = self._fwd_bwd()
-        elif self.graph is None and self.n_calls <= self.warmup_steps:
-            self.loss = self._fwd_bwd()                           # eager warm-up before capture
+            self.launches_per_step = ops.R.launch_count() - c0
         elif self.graph is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
