@@ -22,10 +22,14 @@ class Stepper(object):
         self.lr = float(learning_rate)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rescale = float(rescale_grad) / self.world          # all-reduce(SUM) / world = average over ranks
+        params.refresh_leaves()
         self.static_in = [torch.empty_like(b) for b in example_batch]
         self.loss = None
         self.graph = None
         self.use_graph = bool(use_cuda_graph) and self.static_in[0].is_cuda if self.static_in else False
+        # forward+backward always runs on this side stream, so the autograd nodes that are created during the
+        # eager warm-up steps live on the stream the capture will use
+        self.stream = torch.cuda.Stream(device=self.static_in[0].device) if self.use_graph else None
         self.warmup_steps = warmup_steps
         self.n_calls = 0
         self.launches_per_step = None    # library kernels launched by one forward+backward (counted on an eager step)
@@ -48,14 +52,22 @@ class Stepper(object):
             for dst, src in zip(self.static_in, batch):
                 dst.copy_(src, non_blocking=True)
         self.n_calls += 1
-        if not self.use_graph or (self.graph is None and self.n_calls <= self.warmup_steps):
-            c0 = ops.R.launch_count()                             # eager step (also the warm-up before capture)
+        if not self.use_graph:
+            c0 = ops.R.launch_count()
             self.loss = self._fwd_bwd()
             self.launches_per_step = ops.R.launch_count() - c0
+        elif self.graph is None and self.n_calls <= self.warmup_steps:
+            cur = torch.cuda.current_stream()                     # eager warm-up on the capture stream
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                c0 = ops.R.launch_count()
+                self.loss = self._fwd_bwd()
+                self.launches_per_step = ops.R.launch_count() - c0
+            cur.wait_stream(self.stream)
         elif self.graph is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.stream):
                 self._static_loss = self._fwd_bwd()
             self.graph = g
             g.replay()

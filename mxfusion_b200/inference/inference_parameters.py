@@ -168,6 +168,16 @@ class InferenceParameters(object):
             p.tensor = view.data.requires_grad_(True)          # own version counter, storage shared with `flat`
             p.tensor.grad = self.gflat[p.offset:p.offset + n].view(p.shape)
 
+    def refresh_leaves(self):
+        """Re-wrap every parameter view as a brand-new autograd leaf.  A leaf's AccumulateGrad node remembers the
+        stream it was created on and stays alive while any earlier result (e.g. a loss the user still holds)
+        references it; fresh leaves let a loop run -- and be graph-captured -- on its own stream."""
+        for p in self._params.values():
+            n = p.tensor.numel()
+            view = self.flat[p.offset:p.offset + n].view(p.shape)
+            p.tensor = view.data.requires_grad_(True)
+            p.tensor.grad = self.gflat[p.offset:p.offset + n].view(p.shape)
+
     def fix_all(self):
         for p in self._params.values():
             p.grad_req = 'null'

@@ -61,9 +61,13 @@ class MinibatchInferenceLoop(GradLoop):
             off = torch.zeros((1,), dtype=torch.int64, device=dev)
         else:
             src = [d.detach().cpu().reshape(n, c).contiguous() for d, c in zip(data, cols)]
-            pinned = [torch.empty((B, c), dtype=d.dtype).pin_memory() if dev.type == 'cuda'
-                      else torch.empty((B, c), dtype=d.dtype) for d, c in zip(src, cols)]
-            self.h2d_bytes_per_step = sum(p.numel() * p.element_size() for p in pinned)
+            # ring of pinned staging buffers: a slot is refilled by the host only after the H2D copy that read it
+            # has completed (event), so the host can run ahead of the device by RING-1 steps
+            RING = 4
+            pinned = [[torch.empty((B, c), dtype=d.dtype).pin_memory() if dev.type == 'cuda'
+                       else torch.empty((B, c), dtype=d.dtype) for d, c in zip(src, cols)] for _ in range(RING)]
+            copied = [torch.cuda.Event() if dev.type == 'cuda' else None for _ in range(RING)]
+            self.h2d_bytes_per_step = sum(p.numel() * p.element_size() for p in pinned[0])
         example = [torch.empty((B,) + tuple(d.shape[1:]), dtype=d.dtype, device=dev) for d in data]
         if update_shape_constants is not None:
             update_shape_constants(example)
@@ -91,9 +95,14 @@ class MinibatchInferenceLoop(GradLoop):
                     loss = stepper.step()
                 else:
                     sel = idx_t[i * B:(i + 1) * B]
-                    for s, p, dst in zip(src, pinned, flat_in):
+                    slot = steps_done % RING
+                    if copied[slot] is not None and steps_done >= RING:
+                        copied[slot].synchronize()
+                    for s, p, dst in zip(src, pinned[slot], flat_in):
                         torch.index_select(s, 0, sel, out=p)
                         dst.copy_(p, non_blocking=True)
+                    if copied[slot] is not None:
+                        copied[slot].record()
                     loss = stepper.step()
                     loss_host.copy_(loss.reshape(1), non_blocking=True)       # the reference's asscalar()
                 loss_acc += loss
