@@ -166,6 +166,31 @@ int gemm_simt(int transA, int transB, int m, int n, int k, double alpha, const T
     return after_launch();
 }
 
+int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const float* A, int64_t lda, int64_t sA,
+                const float* B, int64_t ldb, int64_t sB, double beta, float* C, int64_t ldc, int64_t sC, int S, int tri,
+                cudaStream_t st);
+
+// Tensor-core path (tcgen05, 3xTF32) for FP32 problems it supports, FMA-pipe kernel otherwise (FP64, transposed A,
+// unaligned leading dimensions, tiny problems).
+template <typename T>
+int gemm_any(int transA, int transB, int m, int n, int k, double alpha, const T* A, int64_t lda, int64_t sA,
+             const T* B, int64_t ldb, int64_t sB, double beta, T* C, int64_t ldc, int64_t sC, int S, int tri,
+             cudaStream_t st) {
+    if (m == 0 || n == 0 || S == 0) return MXF_OK;
+    if constexpr (sizeof(T) == 4) {
+        if ((int64_t)m * n >= 64 * 64 && k >= 16) {
+            int rc = gemm_tc_f32(transA, transB, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, S, tri, st);
+            if (rc != MXF_ENOTIMPL) return rc;
+        }
+    }
+    return gemm_simt<T>(transA, transB, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, S, tri, st);
+}
+
+template int gemm_any<float>(int, int, int, int, int, double, const float*, int64_t, int64_t, const float*, int64_t,
+                             int64_t, double, float*, int64_t, int64_t, int, int, cudaStream_t);
+template int gemm_any<double>(int, int, int, int, int, double, const double*, int64_t, int64_t, const double*, int64_t,
+                              int64_t, double, double*, int64_t, int64_t, int, int, cudaStream_t);
+
 template int gemm_simt<float>(int, int, int, int, int, double, const float*, int64_t, int64_t, const float*,
                               int64_t, int64_t, double, float*, int64_t, int64_t, int, int, cudaStream_t);
 template int gemm_simt<double>(int, int, int, int, int, double, const double*, int64_t, int64_t, const double*,
@@ -181,7 +206,7 @@ extern "C" int mxf_gemm(int dtype, int transA, int transB, int m, int n, int k, 
     if (m < 0 || n < 0 || k < 0 || S < 0 || !C) return MXF_EINVAL;
     if (k > 0 && (!A || !B)) return MXF_EINVAL;
     if (S > 65535) return MXF_ENOTIMPL;
-    MXF_DISPATCH_DTYPE(dtype, return gemm_simt<T>(transA, transB, m, n, k, alpha, (const T*)A, lda, sA,
+    MXF_DISPATCH_DTYPE(dtype, return gemm_any<T>(transA, transB, m, n, k, alpha, (const T*)A, lda, sA,
                                                   (const T*)B, ldb, sB, beta, (T*)C, ldc, sC, S, tri,
                                                   (cudaStream_t)stream));
 }

@@ -1,0 +1,376 @@
+// FP32 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), FP32-accurate through the 3xTF32
+// split:   C = alpha * A * op(B) + beta * C,   A (m x k) row-major,
+//          op(B) = B^T with B (n x k) row-major ("NT", both operands K-major), or
+//          op(B) = B   with B (k x n) row-major ("NN", B operand MN-major).
+//
+// This is the update engine of the blocked potrf / trsm (trailing update A22 -= L21 L21^T is the NT
+// form with A == B) and of every dense product of the SVGP bound and its gradient
+// (svgp_regression.py:76,82,89,90 and their adjoints).
+//
+// Structure (one 128 x BN output tile per CTA, 6 warps):
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw FP32 A / B tiles (128B-swizzled)
+//               into a STAGES-deep shared-memory ring, completion on mbarriers;
+//   warps 2..5  converters: split every raw element x into hi = tf32(x) (written in place) and
+//               lo = tf32(x - hi) (second buffer, same swizzled position), then, after the main loop,
+//               the epilogue: tcgen05.ld of the accumulator, alpha/beta, store to global;
+//   warp 1      one elected thread issues, per 8-wide K slice,  D += Ahi Bhi + Ahi Blo + Alo Bhi  with
+//               tcgen05.mma.kind::tf32 (accumulator in TMEM), and frees ring slots with tcgen05.commit.
+// tcgen05 has no FP32-input kind; a single TF32 pass (10-bit mantissa) would break the stated FP32
+// tolerance on the ill-conditioned Kuu of a GP, hence the split (error ~ 3 * 2^-22 per product).
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+#include "common.cuh"
+
+namespace mxf {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) with 2 = SWIZZLE_128B.
+// An MN-major TF32 operand must use layout type 1 = SWIZZLE_128B_BASE32B (32-byte swizzle atoms, pattern period 4 rows;
+// TMA counterpart CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) -- "for mn-major tf32 operands, SW128_32B is the only available
+// smem layout" (cutlass/gemm/collective/builders/sm100_common.inl).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                  // 32 floats = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_CONV_THREADS = 128;
+
+template <int BN>
+struct TcCfg {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 4;               // 16 KB
+    static constexpr int B_BYTES = BN * TC_BK * 4;
+    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);     // [A hi | B hi | A lo | B lo]
+    static constexpr int STAGES = (BN == 128) ? 3 : 4;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// B_MN = false: B (n x k) row-major, K-major operand.   B_MN = true: B (k x n) row-major, MN-major operand.
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               float* __restrict__ C, int64_t ldc, int64_t sC, int m, int n, int k, float alpha, float beta,
+               int tri, int batchA, int batchB) {
+    using Cfg = TcCfg<BN>;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    if (tri && n0 > m0 + TC_BM - 1) return;          // tile strictly above the diagonal: nothing to do
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;     // full[S], ready[S], empty[S], tmem_full, tmem slot
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_ready = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * Cfg::STAGES + s); };
+    const uint32_t bar_tmem = bars + 8u * (3 * Cfg::STAGES);
+    const uint32_t tmem_slot = bar_tmem + 8u;
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (3 * Cfg::STAGES) + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (k + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_ready(s), TC_CONV_THREADS);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const int zA = batchA ? (int)blockIdx.z : 0, zB = batchB ? (int)blockIdx.z : 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                mbar_wait(bar_empty(s), ph ^ 1u);
+                const uint32_t st = base + s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(bar_full(s), Cfg::A_BYTES + Cfg::B_BYTES);
+                tma_load_3d(st, &tmA, bar_full(s), kb * TC_BK, m0, zA);
+                if (!B_MN) {
+                    tma_load_3d(st + Cfg::A_BYTES, &tmB, bar_full(s), kb * TC_BK, n0, zB);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BN / 32; ++c)    // one 32-column (128-byte) slab of B per box
+                        tma_load_3d(st + Cfg::A_BYTES + c * (TC_BK * 128), &tmB, bar_full(s), n0 + c * 32, kb * TC_BK, zB);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
+            // a_major [15]=0 (K), b_major [16], N>>3 [17,23), M>>4 [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                mbar_wait(bar_ready(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = base + s * Cfg::STAGE_BYTES, b_hi = a_hi + Cfg::A_BYTES;
+                const uint32_t a_lo = a_hi + Cfg::A_BYTES + Cfg::B_BYTES, b_lo = a_lo + Cfg::A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    // K-major, 128B swizzle: 8-row groups 1024 B apart; a K slice of 8 floats is 32 B along the row.
+                    const uint64_t dah = smem_desc(a_hi + kk * 32, 16, 1024), dal = smem_desc(a_lo + kk * 32, 16, 1024);
+                    uint64_t dbh, dbl;
+                    if (!B_MN) {
+                        dbh = smem_desc(b_hi + kk * 32, 16, 1024);
+                        dbl = smem_desc(b_lo + kk * 32, 16, 1024);
+                    } else {
+                        // MN-major, 128B swizzle with 32B atoms: K rows are 128 B (32 columns of N) apart, the swizzle
+                        // pattern repeats every 4 K-rows (SBO = 512 B); a K slice of 8 is 1024 B; the next 32 columns
+                        // of N are one slab (LBO = TC_BK * 128 B) further on.
+                        dbh = smem_desc(b_hi + kk * 1024, TC_BK * 128, 512, 1);
+                        dbl = smem_desc(b_lo + kk * 1024, TC_BK * 128, 512, 1);
+                    }
+                    umma_tf32(tmem_d, dal, dbh, idesc, (kb | kk) != 0);     // small terms first
+                    umma_tf32(tmem_d, dah, dbl, idesc, 1);
+                    umma_tf32(tmem_d, dah, dbh, idesc, 1);
+                }
+                umma_commit(bar_empty(s));       // slot reusable once these MMAs have read it
+            }
+            umma_commit(bar_tmem);               // accumulator complete
+        }
+    } else {
+        // ------------------------------------------------------------------ converters, then epilogue
+        const int t = threadIdx.x - 64;          // 0..127
+        constexpr int VEC = (Cfg::A_BYTES + Cfg::B_BYTES) / 16;     // 16-byte vectors per stage (hi region)
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % Cfg::STAGES;
+            const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+            mbar_wait(bar_full(s), ph);
+            float4* hi = reinterpret_cast<float4*>(base_ptr + s * Cfg::STAGE_BYTES);
+            float4* lo = reinterpret_cast<float4*>(base_ptr + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll 4
+            for (int i = t; i < VEC; i += TC_CONV_THREADS) {
+                const float4 x = hi[i];
+                float4 h, l;
+                h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+                l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+                hi[i] = h;
+                lo[i] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+            mbar_arrive(bar_ready(s));
+        }
+        mbar_wait(bar_tmem, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        float* Cb = C + (int64_t)blockIdx.z * sC;
+        const bool vec_ok = ((ldc & 3) == 0) && ((sC & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+            uint32_t v[32];
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+            if (row < m) {
+                float* crow = Cb + (int64_t)row * ldc;
+                const int c0 = n0 + j * 32;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const int c = c0 + e;
+                    if (c >= n) break;
+                    float o0 = alpha * __uint_as_float(v[e]), o1 = alpha * __uint_as_float(v[e + 1]);
+                    float o2 = alpha * __uint_as_float(v[e + 2]), o3 = alpha * __uint_as_float(v[e + 3]);
+                    if (vec_ok && c + 3 < n) {
+                        float4* dst = reinterpret_cast<float4*>(crow + c);
+                        if (beta != 0.f) {
+                            const float4 old = *dst;
+                            o0 = fmaf(beta, old.x, o0); o1 = fmaf(beta, old.y, o1);
+                            o2 = fmaf(beta, old.z, o2); o3 = fmaf(beta, old.w, o3);
+                        }
+                        *dst = make_float4(o0, o1, o2, o3);
+                    } else {
+                        const float o[4] = {o0, o1, o2, o3};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c + u < n) crow[c + u] = (beta != 0.f) ? fmaf(beta, crow[c + u], o[u]) : o[u];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static bool tc_enabled() {
+    static int on = [] {
+        const char* e = getenv("MXF_GEMM_TC");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
+
+// 3-D map over a row-major (rows x cols) fp32 matrix with row stride ld, batch stride sB (elements), nb batches.
+static bool make_map(CUtensorMap* tm, const float* p, int64_t rows, int64_t cols, int64_t ld, int64_t sB, int nb,
+                     uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(nb > 0 ? nb : 1)};
+    cuuint64_t batch_stride = (nb > 1) ? (cuuint64_t)sB * 4 : (cuuint64_t)rows * (cuuint64_t)ld * 4;
+    if (batch_stride < 16) batch_stride = 16;
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, batch_stride};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool B_MN>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int64_t ldc, int64_t sC, int m, int n,
+                     int k, float alpha, float beta, int S, int tri, int batchA, int batchB, cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    auto kern = gemm_tc_kernel<BN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+            return (int)cudaGetLastError();
+        attr_set = true;
+    }
+    dim3 grid(cdiv(n, BN), cdiv(m, TC_BM), S);
+    kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, C, ldc, sC, m, n, k, alpha, beta, tri, batchA, batchB);
+    return after_launch();
+}
+
+// Returns MXF_ENOTIMPL when the problem does not fit the tensor-core path (caller falls back to the FMA kernel).
+int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const float* A, int64_t lda, int64_t sA,
+                const float* B, int64_t ldb, int64_t sB, double beta, float* C, int64_t ldc, int64_t sC, int S, int tri,
+                cudaStream_t st) {
+    if (!tc_enabled() || transA || m <= 0 || n <= 0 || k <= 0 || S <= 0) return MXF_ENOTIMPL;
+    if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return MXF_ENOTIMPL;
+    if (S > 1 && (((sA != 0) && (sA & 3)) || ((sB != 0) && (sB & 3)))) return MXF_ENOTIMPL;
+    const int batchA = (S > 1 && sA != 0) ? 1 : 0, batchB = (S > 1 && sB != 0) ? 1 : 0;
+    // tile width: 64-wide tiles when 128-wide ones would leave most SMs idle
+    const int64_t tiles128 = (int64_t)cdiv(n, 128) * cdiv(m, TC_BM) * S;
+    const bool bn64 = tiles128 < 100;
+    const int BN = bn64 ? 64 : 128;
+    CUtensorMap tmA, tmB;
+    if (!make_map(&tmA, A, m, k, lda, sA, batchA ? S : 1, TC_BK, TC_BM)) return MXF_ENOTIMPL;
+    const bool b_mn = (transB == 0);
+    if (!b_mn) {
+        if (!make_map(&tmB, B, n, k, ldb, sB, batchB ? S : 1, TC_BK, BN)) return MXF_ENOTIMPL;
+    } else {
+        if (!make_map(&tmB, B, k, n, ldb, sB, batchB ? S : 1, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+            return MXF_ENOTIMPL;
+    }
+    const float al = (float)alpha, be = (float)beta;
+    if (bn64) {
+        return b_mn ? launch_tc<64, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
+                    : launch_tc<64, false>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
+    }
+    return b_mn ? launch_tc<128, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
+                : launch_tc<128, false>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
+}
+
+}  // namespace mxf
