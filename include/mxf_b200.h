@@ -107,6 +107,21 @@ int mxf_trsm(int dtype, int transpose, int n, int nrhs, double alpha,
              const void* A, int64_t lda, int64_t sA,
              void* B, int64_t ldb, int64_t sB, int S, void* stream);
 
+/* ---- tensor-core formulation of potrf / trsm --------------------------------------------------
+ * The "pack" of a lower factor L (n x n), per sample, is  [ Dinv | DinvT | LT ]:  the inverses of the NB x NB diagonal
+ * blocks of L (NB = mxf_tri_block(dtype): 128 for f32, 64 for f64; the last block is padded with the identity), their
+ * transposes, and L^T (row stride (n+3)&~3).  It holds mxf_tri_pack_elems(dtype, n) elements per sample (a multiple
+ * of 4).  mxf_potrf_packed factors A in place exactly like mxf_potrf AND emits the pack as a by-product (the panel
+ * solve and the trailing update are GEMMs -- tcgen05 for f32); mxf_tri_pack builds the pack of an existing factor;
+ * mxf_trsm_packed solves with it as a chain of GEMMs  X_k = Dinv_k B_k ; B_rest -= L_rest,k X_k.
+ * sP = batch stride of the pack in elements (0 = one factor shared by all S right-hand sides). */
+int mxf_tri_block(int dtype);
+size_t mxf_tri_pack_elems(int dtype, int n);
+int mxf_tri_pack(int dtype, const void* L, int64_t lda, int64_t sA, int S, int n, void* pack, void* stream);
+int mxf_potrf_packed(int dtype, void* A, int64_t lda, int64_t sA, int S, int n, int* info, void* pack, void* stream);
+int mxf_trsm_packed(int dtype, int transpose, int n, int nrhs, double alpha, const void* L, int64_t lda, int64_t sA,
+                    const void* pack, int64_t sP, void* B, int64_t ldb, int64_t sB, int S, void* stream);
+
 /* Cholesky adjoint helper: out = phi(P) + phi(P)^T with phi = lower triangle, i.e. the
  * symmetric matrix whose lower triangle (diagonal included) is copied from P. */
 int mxf_copy_ltu(int dtype, const void* P, int64_t ldp, int64_t sP,
@@ -163,9 +178,10 @@ int mxf_softplus_bwd(int dtype, const void* x, const void* gy, void* gx, int64_t
  *   E   = coef2 mt mt^T + coef0 (T - I) - c1 Phi + c1 (U + U^T) - coef3 (v mt^T + mt v^T)
  *   E_S = coef0 I + c1 Phi
  *   E_R = -coef4 (T - I) - coef5 mt mt^T
- * into out (S, M, 3M) as [E | E_S | E_R] (row stride 3M). */
+ * into out as [E | E_S | E_R] (row stride ldo >= 3M, batch stride sO; extra columns are left untouched so that more
+ * right-hand sides can ride along in the same triangular solve). */
 int mxf_svgp_bwd_assemble(int dtype, const void* Phi, const void* T, const void* U, const void* mt, const void* v,
-                          const void* coef, void* out, int S, int M, int P, void* stream);
+                          const void* coef, void* out, int64_t ldo, int64_t sO, int S, int M, int P, void* stream);
 
 /* ---- Normal distribution: MC-ELBO pieces (normal.py:52-92, factor_graph.py:223) ----
  * Fused log-density + sample-mean + sum:

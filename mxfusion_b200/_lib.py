@@ -34,6 +34,11 @@ def _declare(lib):
         'mxf_gemm': (i, [i, i, i, i, i, i, d, p, l, l, p, l, l, d, p, l, l, i, i, p]),
         'mxf_potrf': (i, [i, p, l, l, i, i, p, p]),
         'mxf_trsm': (i, [i, i, i, i, d, p, l, l, p, l, l, i, p]),
+        'mxf_tri_block': (i, [i]),
+        'mxf_tri_pack_elems': (z, [i, i]),
+        'mxf_tri_pack': (i, [i, p, l, l, i, i, p, p]),
+        'mxf_potrf_packed': (i, [i, p, l, l, i, i, p, p, p]),
+        'mxf_trsm_packed': (i, [i, i, i, i, d, p, l, l, p, l, p, l, l, i, p]),
         'mxf_copy_ltu': (i, [i, p, l, l, p, l, l, i, i, p]),
         'mxf_symmetrize': (i, [i, d, p, l, l, p, l, l, i, i, p]),
         'mxf_tril': (i, [i, i, p, l, l, p, l, l, i, i, p]),
@@ -45,7 +50,7 @@ def _declare(lib):
         'mxf_axpby_dev': (i, [i, p, p, l, p, p, l, p, l, i, l, p]),
         'mxf_softplus_fwd': (i, [i, p, d, p, l, p]),
         'mxf_softplus_bwd': (i, [i, p, p, p, l, p]),
-        'mxf_svgp_bwd_assemble': (i, [i, p, p, p, p, p, p, p, i, i, i, p]),
+        'mxf_svgp_bwd_assemble': (i, [i, p, p, p, p, p, p, p, l, l, i, i, i, p]),
         'mxf_normal_logpdf_sum': (i, [i, p, l, p, l, p, l, i, l, d, p, p]),
         'mxf_normal_logpdf_sum_bwd': (i, [i, p, l, p, l, p, l, i, l, d, p, p, p, p, p]),
         'mxf_normal_reparam': (i, [i, p, p, l, p, l, i, l, u, u, p, p, p]),

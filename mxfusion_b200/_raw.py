@@ -123,17 +123,64 @@ def trsm_(L, B, transpose=False, alpha=1.0):
     return B
 
 
-def _sq(fn, name, A, *extra):
+def _new_pack(A):
+    S, n, _ = A.shape
+    elems = lib().mxf_tri_pack_elems(dtype_code(A), n)
+    return torch.empty((S, max(int(elems), 1)), dtype=A.dtype, device=A.device)
+
+
+def new_pack(A):
+    return _new_pack(A)
+
+
+def potrf_packed_(A, info=None, pack=None):
+    """In-place lower Cholesky of A (S,n,n) on the GEMM-based path; returns (A, info, pack) where `pack` holds the
+    inverted diagonal blocks and L^T that turn later solves with this factor into GEMMs (mxf_trsm_packed)."""
     require_cuda(A)
     S, n, _ = A.shape
-    out = torch.empty((S, n, n), dtype=A.dtype, device=A.device)
+    if info is None:
+        info = torch.empty((S,), dtype=torch.int32, device=A.device)
+    if pack is None:
+        pack = _new_pack(A)
+    check(lib().mxf_potrf_packed(dtype_code(A), ptr(A), A.stride(1), A.stride(0), S, n, ptr(info), ptr(pack),
+                                 stream_ptr()), 'mxf_potrf_packed')
+    return A, info, pack
+
+
+def tri_pack(L):
+    """Pack of an existing lower factor L (S,n,n)."""
+    require_cuda(L)
+    if L.stride(2) != 1:
+        L = L.contiguous()
+    S, n, _ = L.shape
+    pack = _new_pack(L)
+    check(lib().mxf_tri_pack(dtype_code(L), ptr(L), L.stride(1), L.stride(0), S, n, ptr(pack), stream_ptr()),
+          'mxf_tri_pack')
+    return pack
+
+
+def trsm_packed_(L, pack, B, transpose=False, alpha=1.0):
+    """In-place B := alpha op(L)^-1 B as a chain of GEMMs; L (Sl,n,n), pack (Sl,*), B (S,n,nrhs)."""
+    require_cuda(L, pack, B)
+    S, n, nrhs = B.shape
+    check(lib().mxf_trsm_packed(dtype_code(B), int(transpose), n, nrhs, float(alpha), ptr(L), L.stride(1),
+                                _bstride(L, S), ptr(pack), pack.stride(0) if pack.shape[0] > 1 else 0,
+                                ptr(B), B.stride(1), B.stride(0), S, stream_ptr()), 'mxf_trsm_packed')
+    return B
+
+
+def _sq(fn, name, A, *extra, out=None):
+    require_cuda(A, out)
+    S, n, _ = A.shape
+    if out is None:
+        out = torch.empty((S, n, n), dtype=A.dtype, device=A.device)
     check(fn(dtype_code(A), *extra, ptr(A), A.stride(1), A.stride(0), ptr(out), out.stride(1), out.stride(0),
              S, n, stream_ptr()), name)
     return out
 
 
-def copy_ltu(P):
-    return _sq(lib().mxf_copy_ltu, 'mxf_copy_ltu', P)
+def copy_ltu(P, out=None):
+    return _sq(lib().mxf_copy_ltu, 'mxf_copy_ltu', P, out=out)
 
 
 def symmetrize(A, alpha=1.0):
@@ -316,11 +363,14 @@ def softplus_bwd(x, gy):
     return gx
 
 
-def svgp_bwd_assemble(Phi, T, U, mt, v, coef):
-    require_cuda(Phi, T, U, mt, v, coef)
+def svgp_bwd_assemble(Phi, T, U, mt, v, coef, out=None):
+    """[E | E_S | E_R] into out[:, :, :3M] (out may be wider: extra right-hand-side columns are left untouched)."""
+    require_cuda(Phi, T, U, mt, v, coef, out)
     S, M, _ = Phi.shape
     P = mt.shape[2]
-    out = torch.empty((S, M, 3 * M), dtype=Phi.dtype, device=Phi.device)
+    if out is None:
+        out = torch.empty((S, M, 3 * M), dtype=Phi.dtype, device=Phi.device)
     check(lib().mxf_svgp_bwd_assemble(dtype_code(Phi), ptr(_c(Phi)), ptr(_c(T)), ptr(_c(U)), ptr(_c(mt)), ptr(_c(v)),
-                                      ptr(_c(coef)), ptr(out), S, M, P, stream_ptr()), 'mxf_svgp_bwd_assemble')
+                                      ptr(_c(coef)), ptr(out), out.stride(1), out.stride(0), S, M, P, stream_ptr()),
+          'mxf_svgp_bwd_assemble')
     return out

@@ -166,20 +166,150 @@ int gemm_simt(int transA, int transB, int m, int n, int k, double alpha, const T
     return after_launch();
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Skinny products (n <= 8 columns): the matrix-vector shaped pieces of the SVGP bound -- A^T (L^-1 mu), A Y, Phi mt
+// (svgp_regression.py:82,89) -- are bandwidth-bound passes over A, not tile GEMMs.
+//   non-transposed A (m x k): one warp per output row, lanes stride over k, warp-shuffle reduction;
+//   transposed A (stored k x m): 32 consecutive output rows per CTA (coalesced 128-byte reads of A), the 8 warps
+//   split k, partial sums combined through shared memory (deterministic).
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int NCOL>
+__global__ void __launch_bounds__(256)
+gemm_skinny_n_kernel(int transB, int m, int n, int k, T alpha, const T* __restrict__ A, int64_t lda, int64_t sA,
+                     const T* __restrict__ B, int64_t ldb, int64_t sB, T beta, T* __restrict__ C, int64_t ldc,
+                     int64_t sC) {
+    const int s = blockIdx.y;
+    A += (int64_t)s * sA; B += (int64_t)s * sB; C += (int64_t)s * sC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= m) return;
+    T acc[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) acc[j] = T(0);
+    const T* arow = A + (int64_t)i * lda;
+    for (int kk = lane; kk < k; kk += 32) {
+        const T a = arow[kk];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (j < n) acc[j] = fma(a, transB ? B[(int64_t)j * ldb + kk] : B[(int64_t)kk * ldb + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (j < n) {
+                T* dst = C + (int64_t)i * ldc + j;
+                T v = alpha * acc[j];
+                if (beta != T(0)) v = fma(beta, *dst, v);
+                *dst = v;
+            }
+    }
+}
+
+template <typename T, int NCOL>
+__global__ void __launch_bounds__(256)
+gemm_skinny_t_kernel(int transB, int m, int n, int k, T alpha, const T* __restrict__ A, int64_t lda, int64_t sA,
+                     const T* __restrict__ B, int64_t ldb, int64_t sB, T beta, T* __restrict__ C, int64_t ldc,
+                     int64_t sC) {
+    __shared__ T part[8][NCOL][33];
+    const int s = blockIdx.y;
+    A += (int64_t)s * sA; B += (int64_t)s * sB; C += (int64_t)s * sC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 32 + lane;
+    T acc[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) acc[j] = T(0);
+    if (i < m) {
+        for (int kk = warp; kk < k; kk += 8) {
+            const T a = A[(int64_t)kk * lda + i];
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j)
+                if (j < n) acc[j] = fma(a, transB ? B[(int64_t)j * ldb + kk] : B[(int64_t)kk * ldb + j], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) part[warp][j][lane] = acc[j];
+    __syncthreads();
+    if (warp == 0 && i < m) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (j < n) {
+                T t = T(0);
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += part[w][j][lane];
+                T* dst = C + (int64_t)i * ldc + j;
+                T v = alpha * t;
+                if (beta != T(0)) v = fma(beta, *dst, v);
+                *dst = v;
+            }
+    }
+}
+
+// k <= 8 (outer products such as  Kuf_bar += (g s beta w) Y^T ): one coalesced pass over C.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_rank_k_kernel(int transA, int transB, int m, int n, int k, T alpha, const T* __restrict__ A, int64_t lda, int64_t sA,
+                   const T* __restrict__ B, int64_t ldb, int64_t sB, T beta, T* __restrict__ C, int64_t ldc, int64_t sC) {
+    const int s = blockIdx.z;
+    A += (int64_t)s * sA; B += (int64_t)s * sB; C += (int64_t)s * sC;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    T b[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) b[kk] = (kk < k) ? (transB ? B[(int64_t)j * ldb + kk] : B[(int64_t)kk * ldb + j]) : T(0);
+    for (int i = blockIdx.y; i < m; i += gridDim.y) {
+        T acc = T(0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+            if (kk < k) acc = fma(transA ? A[(int64_t)kk * lda + i] : A[(int64_t)i * lda + kk], b[kk], acc);
+        T* dst = C + (int64_t)i * ldc + j;
+        T v = alpha * acc;
+        if (beta != T(0)) v = fma(beta, *dst, v);
+        *dst = v;
+    }
+}
+
+template <typename T>
+static int gemm_skinny(int transA, int transB, int m, int n, int k, double alpha, const T* A, int64_t lda, int64_t sA,
+                       const T* B, int64_t ldb, int64_t sB, double beta, T* C, int64_t ldc, int64_t sC, int S,
+                       cudaStream_t st) {
+    if (!transA) {
+        dim3 grid(cdiv(m, 8), S);
+        if (n <= 1) gemm_skinny_n_kernel<T, 1><<<grid, 256, 0, st>>>(transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);
+        else if (n <= 4) gemm_skinny_n_kernel<T, 4><<<grid, 256, 0, st>>>(transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);
+        else gemm_skinny_n_kernel<T, 8><<<grid, 256, 0, st>>>(transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);
+    } else {
+        dim3 grid(cdiv(m, 32), S);
+        if (n <= 1) gemm_skinny_t_kernel<T, 1><<<grid, 256, 0, st>>>(transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);
+        else if (n <= 4) gemm_skinny_t_kernel<T, 4><<<grid, 256, 0, st>>>(transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);
+        else gemm_skinny_t_kernel<T, 8><<<grid, 256, 0, st>>>(transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);
+    }
+    return after_launch();
+}
+
 int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const float* A, int64_t lda, int64_t sA,
                 const float* B, int64_t ldb, int64_t sB, double beta, float* C, int64_t ldc, int64_t sC, int S, int tri,
-                cudaStream_t st);
+                int wide, cudaStream_t st);
 
 // Tensor-core path (tcgen05, 3xTF32) for FP32 problems it supports, FMA-pipe kernel otherwise (FP64, transposed A,
 // unaligned leading dimensions, tiny problems).
 template <typename T>
 int gemm_any(int transA, int transB, int m, int n, int k, double alpha, const T* A, int64_t lda, int64_t sA,
              const T* B, int64_t ldb, int64_t sB, double beta, T* C, int64_t ldc, int64_t sC, int S, int tri,
-             cudaStream_t st) {
+             cudaStream_t st, int wide) {
     if (m == 0 || n == 0 || S == 0) return MXF_OK;
+    if (k <= 8 && !tri && (int64_t)m * n >= 4096) {
+        dim3 grid(cdiv(n, 256), std::min(m, 2048), S);
+        gemm_rank_k_kernel<T><<<grid, 256, 0, st>>>(transA, transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);
+        return after_launch();
+    }
+    if (n <= 8 && k >= 32 && !tri && (const void*)C != (const void*)A && (const void*)C != (const void*)B)
+        return gemm_skinny<T>(transA, transB, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, S, st);
     if constexpr (sizeof(T) == 4) {
         if ((int64_t)m * n >= 64 * 64 && k >= 16) {
-            int rc = gemm_tc_f32(transA, transB, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, S, tri, st);
+            int rc = gemm_tc_f32(transA, transB, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, S, tri, wide,
+                                 st);
             if (rc != MXF_ENOTIMPL) return rc;
         }
     }
@@ -187,9 +317,9 @@ int gemm_any(int transA, int transB, int m, int n, int k, double alpha, const T*
 }
 
 template int gemm_any<float>(int, int, int, int, int, double, const float*, int64_t, int64_t, const float*, int64_t,
-                             int64_t, double, float*, int64_t, int64_t, int, int, cudaStream_t);
+                             int64_t, double, float*, int64_t, int64_t, int, int, cudaStream_t, int);
 template int gemm_any<double>(int, int, int, int, int, double, const double*, int64_t, int64_t, const double*, int64_t,
-                              int64_t, double, double*, int64_t, int64_t, int, int, cudaStream_t);
+                              int64_t, double, double*, int64_t, int64_t, int, int, cudaStream_t, int);
 
 template int gemm_simt<float>(int, int, int, int, int, double, const float*, int64_t, int64_t, const float*,
                               int64_t, int64_t, double, float*, int64_t, int64_t, int, int, cudaStream_t);
@@ -208,5 +338,5 @@ extern "C" int mxf_gemm(int dtype, int transA, int transB, int m, int n, int k, 
     if (S > 65535) return MXF_ENOTIMPL;
     MXF_DISPATCH_DTYPE(dtype, return gemm_any<T>(transA, transB, m, n, k, alpha, (const T*)A, lda, sA,
                                                   (const T*)B, ldb, sB, beta, (T*)C, ldc, sC, S, tri,
-                                                  (cudaStream_t)stream));
+                                                  (cudaStream_t)stream, 0));
 }

@@ -345,7 +345,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, i
 // Returns MXF_ENOTIMPL when the problem does not fit the tensor-core path (caller falls back to the FMA kernel).
 int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const float* A, int64_t lda, int64_t sA,
                 const float* B, int64_t ldb, int64_t sB, double beta, float* C, int64_t ldc, int64_t sC, int S, int tri,
-                cudaStream_t st) {
+                int wide, cudaStream_t st) {
     if (!tc_enabled() || transA || m <= 0 || n <= 0 || k <= 0 || S <= 0) return MXF_ENOTIMPL;
     if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return MXF_ENOTIMPL;
@@ -353,7 +353,7 @@ int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const
     const int batchA = (S > 1 && sA != 0) ? 1 : 0, batchB = (S > 1 && sB != 0) ? 1 : 0;
     // tile width: 64-wide tiles when 128-wide ones would leave most SMs idle
     const int64_t tiles128 = (int64_t)cdiv(n, 128) * cdiv(m, TC_BM) * S;
-    const bool bn64 = tiles128 < 100;
+    const bool bn64 = !wide && tiles128 < 100;   // `wide`: C aliases A (in-place panel), one CTA must own full rows
     const int BN = bn64 ? 64 : 128;
     CUtensorMap tmA, tmB;
     if (!make_map(&tmA, A, m, k, lda, sA, batchA ? S : 1, TC_BK, TC_BM)) return MXF_ENOTIMPL;

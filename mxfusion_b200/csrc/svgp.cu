@@ -51,7 +51,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 svgp_bwd_assemble_kernel(const T* __restrict__ Phi, const T* __restrict__ Tm, const T* __restrict__ U,
                          const T* __restrict__ mt, const T* __restrict__ v, const T* __restrict__ coef,
-                         T* __restrict__ out, int M, int P) {
+                         T* __restrict__ out, int64_t ldo, int64_t sO, int M, int P) {
     __shared__ T ut[32][33];
     const int s = blockIdx.z;
     const int64_t mo = (int64_t)s * M * M;
@@ -61,7 +61,7 @@ svgp_bwd_assemble_kernel(const T* __restrict__ Phi, const T* __restrict__ Tm, co
     const T* mts = mt + (int64_t)s * M * P;
     const T* vs = v + (int64_t)s * M * P;
     const T* cf = coef + (int64_t)s * 6;
-    T* os = out + (int64_t)s * M * 3 * M;
+    T* os = out + (int64_t)s * sO;
     const T c0 = cf[0], c1 = cf[1], c2 = cf[2], c3 = cf[3], c4 = cf[4], c5 = cf[5];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
@@ -82,7 +82,7 @@ svgp_bwd_assemble_kernel(const T* __restrict__ Phi, const T* __restrict__ Tm, co
             vm = fma(mi, vs[j * P + p], vm);
         }
         const T dl = (i == j) ? T(1) : T(0);
-        T* orow = os + (int64_t)i * 3 * M;
+        T* orow = os + (int64_t)i * ldo;
         orow[j] = c2 * mm + c0 * (t - dl) - c1 * ph + c1 * (u + uT) - c3 * vm;
         orow[M + j] = c0 * dl + c1 * ph;
         orow[2 * M + j] = -c4 * (t - dl) - c5 * mm;
@@ -125,14 +125,14 @@ extern "C" int mxf_softplus_bwd(int dtype, const void* x, const void* gy, void* 
 }
 
 extern "C" int mxf_svgp_bwd_assemble(int dtype, const void* Phi, const void* T_, const void* U, const void* mt,
-                                     const void* v, const void* coef, void* out, int S, int M, int P,
-                                     void* stream) {
-    if (!Phi || !T_ || !U || !mt || !v || !coef || !out || S < 0 || M < 0 || P < 0) return MXF_EINVAL;
+                                     const void* v, const void* coef, void* out, int64_t ldo, int64_t sO, int S,
+                                     int M, int P, void* stream) {
+    if (!Phi || !T_ || !U || !mt || !v || !coef || !out || S < 0 || M < 0 || P < 0 || ldo < 3 * (int64_t)M) return MXF_EINVAL;
     if (S == 0 || M == 0) return MXF_OK;
     if (S > 65535) return MXF_ENOTIMPL;
     dim3 grid(cdiv(M, 32), cdiv(M, 32), S);
     MXF_DISPATCH_DTYPE(dtype, svgp_bwd_assemble_kernel<T><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
                                   (const T*)Phi, (const T*)T_, (const T*)U, (const T*)mt, (const T*)v,
-                                  (const T*)coef, (T*)out, M, P));
+                                  (const T*)coef, (T*)out, ldo, sO, M, P));
     return after_launch();
 }

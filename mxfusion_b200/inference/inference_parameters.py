@@ -148,6 +148,8 @@ class InferenceParameters(object):
         dt, dev = torch_dtype(self.dtype), self.mxnet_context
         total = 0
         for p in self._params.values():
+            # every view starts on a 128-byte boundary: TMA / vectorised kernels read parameters in place
+            total = (total + 31) & ~31
             p.offset = total
             total += int(np.prod(p.shape)) if len(p.shape) else 1
         self.flat = torch.zeros((total,), dtype=dt, device=dev)

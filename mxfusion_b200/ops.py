@@ -84,8 +84,8 @@ def kernel_matrix(kind, X, X2, lengthscale, variance, diag_add=None, diag_const=
 class _Potrf(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A):
-        L, info = R.potrf_(A.clone())
-        ctx.save_for_backward(L)
+        L, info, pack = R.potrf_packed_(A.clone())
+        ctx.save_for_backward(L, pack)
         ctx.mark_non_differentiable(info)
         return L, info
 
@@ -93,12 +93,12 @@ class _Potrf(torch.autograd.Function):
     def backward(ctx, Lbar, _):
         # Murray (2016): Abar = 1/2 L^-T (P + P^T) L^-1 with P = Phi(L^T Lbar), Phi = lower triangle with the
         # diagonal halved, so P + P^T is the symmetric matrix built from the lower triangle of L^T Lbar.
-        (L,) = ctx.saved_tensors
+        L, pack = ctx.saved_tensors
         G = R.gemm(L, R.tril(Lbar), transA=True)
         Psym = R.copy_ltu(G)
-        R.trsm_(L, Psym, transpose=True)
+        R.trsm_packed_(L, pack, Psym, transpose=True)
         Y = R.transpose(Psym)
-        R.trsm_(L, Y, transpose=True)
+        R.trsm_packed_(L, pack, Y, transpose=True)
         return R.symmetrize(Y, 0.25)      # 1/2 * (Y + Y^T)/2: symmetric by construction, cleans rounding
 
 
@@ -111,15 +111,16 @@ def potrf(A, return_info=False):
 class _Trsm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, L, B, transpose, alpha):
-        X = R.trsm_(L, B.clone(), transpose=transpose, alpha=alpha)
+        pack = R.tri_pack(L)
+        X = R.trsm_packed_(L, pack, B.clone(), transpose=transpose, alpha=alpha)
         ctx.transpose, ctx.alpha = transpose, alpha
-        ctx.save_for_backward(L, X)
+        ctx.save_for_backward(L, X, pack)
         return X
 
     @staticmethod
     def backward(ctx, Xbar):
-        L, X = ctx.saved_tensors
-        Bbar = R.trsm_(L, Xbar.clone(), transpose=not ctx.transpose, alpha=ctx.alpha)
+        L, X, pack = ctx.saved_tensors
+        Bbar = R.trsm_packed_(L, pack, Xbar.clone(), transpose=not ctx.transpose, alpha=ctx.alpha)
         Lbar = None
         if ctx.needs_input_grad[0]:
             # X = alpha op(L)^-1 B:  Lbar = -(1/alpha) tril(Bbar X^T)  (no transpose),  -(1/alpha) tril(X Bbar^T)
@@ -261,15 +262,47 @@ class _SVGPLogPdf(torch.autograd.Function):
     @staticmethod
     def forward(ctx, kind, jitter, scale, X, Y, Z, noise, mu, W, dvec, ls, kvar):
         S, B, P, M = X.shape[0], X.shape[1], Y.shape[2], Z.shape[1]
+        dt, dev = X.dtype, X.device
+        PP = (P + 3) & ~3                                       # keep every row stride a multiple of 4 elements
         Kuu = R.kbuild_fwd(kind, Z, None, ls, kvar, diag_const=jitter)
-        A = R.kbuild_fwd(kind, Z, X, ls, kvar)                  # Kuf (:73), overwritten below by L^-1 Kuf
+        # all right-hand sides of the solves with L ride in ONE buffer [Kuf | Ls | mu]: one GEMM chain, not three
+        RH = torch.empty((S, M, B + M + PP), dtype=dt, device=dev)
+        A, C, mt = RH[:, :, :B], RH[:, :, B:B + M], RH[:, :, B + M:B + M + P]
+        R.kbuild_fwd(kind, Z, X, ls, kvar, out=A)               # Kuf (:73), overwritten below by L^-1 Kuf
         Sm = R.gemm(W, W, transB=True, tri=True)                # :76 syrk (lower tiles) ...
         R.add_diag_(Sm, dvec)                                   # ... + make_diagonal
-        L, info = R.potrf_(Kuu)                                 # :83
-        Ls, info_s = R.potrf_(Sm)                               # :84
-        C = R.trsm_(L, Ls.clone())                              # :85
-        mt = R.trsm_(L, mu.clone())                             # :86
-        R.trsm_(L, A)                                           # :87
+        pk, pks = R.new_pack(Kuu), R.new_pack(Sm)
+        info = torch.empty((2, S), dtype=torch.int32, device=dev)
+        side = _side_stream(dev)
+        # S^-1 = Ls^-T Ls^-1 is only needed by the adjoint (d logdet S), but it depends on nothing else: it is
+        # computed here, on the side stream, while the main stream factors Kuu and runs the solves with L
+        eyeS = torch.eye(M, dtype=dt, device=dev).unsqueeze(0).repeat(S, 1, 1)
+        LsT = torch.empty((S, M, M), dtype=dt, device=dev)
+        Sinv_l = torch.zeros((S, M, M), dtype=dt, device=dev)
+        Sinv = torch.empty((S, M, M), dtype=dt, device=dev)
+        Ls_copy = torch.empty((S, M, M), dtype=dt, device=dev)
+        if side is not None:                                    # the two factorisations are independent: overlap them
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
+            join_ls = torch.cuda.Event()
+            with torch.cuda.stream(side):
+                R.potrf_packed_(Sm, info[1], pks)               # :84
+                Ls_copy.copy_(Sm)
+                join_ls.record()
+                _sinv_chain(Sm, pks, eyeS, LsT, Sinv_l, Sinv)
+            R.potrf_packed_(Kuu, info[0], pk)                   # :83
+            cur.wait_event(join_ls)
+        else:
+            R.potrf_packed_(Kuu, info[0], pk)
+            R.potrf_packed_(Sm, info[1], pks)
+            Ls_copy.copy_(Sm)
+            _sinv_chain(Sm, pks, eyeS, LsT, Sinv_l, Sinv)
+        L, Ls = Kuu, Sm
+        C.copy_(Ls_copy)
+        mt.copy_(mu)
+        if PP > P:
+            RH[:, :, B + M + P:].zero_()
+        R.trsm_packed_(L, pk, RH)                               # :85-87  C = L^-1 Ls, mt = L^-1 mu, A = L^-1 Kuf
         Phi = R.copy_ltu(R.gemm(A, A, transB=True, tri=True))
         T = R.copy_ltu(R.gemm(C, C, transB=True, tri=True))
         G1 = R.gemm(A, mt, transA=True)                         # :89  (S,B,P)
@@ -285,15 +318,20 @@ class _SVGPLogPdf(torch.autograd.Function):
         data = beta * Q - (0.5 * B * P) * (_LOG2PI + torch.log(nv))          # :98-107
         neg_kl = P * (0.5 * M + sldLs - sldL) - (0.5 * P) * trT - 0.5 * mm   # :94-96 (`KL_u` is minus the KL)
         logL = scale * data + neg_kl                                         # :108
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)                    # join: S^-1 is ready for the adjoint
         ctx.kind, ctx.scale, ctx.dims = kind, scale, (S, B, P, M)
-        ctx.save_for_backward(X, Y, Z, ls, kvar, W, L, Ls, A, Phi, T, mt, G1, beta, Q)
-        ctx.info = (info, info_s)
+        ctx.save_for_backward(X, Y, Z, ls, kvar, W, L, Sinv, RH, Phi, T, G1, beta, Q, pk)
+        ctx.info = info
         return logL
 
     @staticmethod
     def backward(ctx, g):
-        X, Y, Z, ls, kvar, W, L, Ls, A, Phi, T, mt, G1, beta, Q = ctx.saved_tensors
+        X, Y, Z, ls, kvar, W, L, Sinv, RH, Phi, T, G1, beta, Q, pk = ctx.saved_tensors
         S, B, P, M = ctx.dims
+        dt, dev = RH.dtype, RH.device
+        PP = (P + 3) & ~3
+        A, mt = RH[:, :, :B], RH[:, :, B + M:B + M + P].contiguous()
         sc = ctx.scale
         need = ctx.needs_input_grad      # (kind, jitter, scale, X, Y, Z, noise, mu, W, dvec, ls, kvar)
         g = g.contiguous()
@@ -302,35 +340,64 @@ class _SVGPLogPdf(torch.autograd.Function):
         U = R.gemm(Phi, T)
         v = R.gemm(A, Y)
         R.gemm(Phi, mt, alpha=-1.0, beta=1.0, C=v)              # v = A (Y - A^T mt)
-        E3 = R.svgp_bwd_assemble(Phi, T, U, mt, v, coef)        # [E | E_S | E_R]
-        R.trsm_(L, E3, transpose=True)                          # L^-T [.]
+        # first solve with L^T: [E | E_S | E_R | mt]  (mt rides along: w = L^-T mt)
+        E4 = torch.empty((S, M, 3 * M + PP), dtype=dt, device=dev)
+        R.svgp_bwd_assemble(Phi, T, U, mt, v, coef, out=E4)
+        E4[:, :, 3 * M:3 * M + P].copy_(mt)
+        if PP > P:
+            E4[:, :, 3 * M + P:].zero_()
+        R.trsm_packed_(L, pk, E4, transpose=True)
         # Kuf adjoint: (L^-T E_R) A + g s beta (L^-T mt) Y^T
-        dKuf = R.gemm(E3[:, :, 2 * M:], A)
-        w = R.trsm_(L, mt.clone(), transpose=True)
+        dKuf = R.gemm(E4[:, :, 2 * M:3 * M], A)
+        w = E4[:, :, 3 * M:3 * M + P]
         R.gemm(R.axpby_dev(gsb, w), Y, transB=True, beta=1.0, C=dKuf)
-        # second side of the two symmetric solves: L^-T E L^-1 = L^-T (L^-T E)^T
-        F2 = torch.empty((S, M, 2 * M), dtype=A.dtype, device=A.device)
-        R.transpose(E3[:, :, :M], out=F2[:, :, :M])
-        R.transpose(E3[:, :, M:2 * M], out=F2[:, :, M:])
-        R.trsm_(L, F2, transpose=True)
+        # second solve with L^T: [(L^-T E)^T | (L^-T E_S)^T | g (s beta v - mt)]  ->  [Kuu adjoint | L^-T E_S L^-1 | mu adjoint]
+        F2 = torch.empty((S, M, 2 * M + PP), dtype=dt, device=dev)
+        R.transpose(E4[:, :, :M], out=F2[:, :, :M])
+        R.transpose(E4[:, :, M:2 * M], out=F2[:, :, M:2 * M])
+        F2[:, :, 2 * M:2 * M + P].copy_(R.axpby_dev(gsb, v, -g, mt))
+        if PP > P:
+            F2[:, :, 2 * M + P:].zero_()
+        R.trsm_packed_(L, pk, F2, transpose=True)
         dKuu = F2[:, :, :M]
+        dmu = F2[:, :, 2 * M:2 * M + P].contiguous()
         dZ1, dX, dls1, dvar1 = R.kbuild_bwd(ctx.kind, Z, X, ls, kvar, dKuf, need_dX=True, need_dX2=need[3])
         dZ2, _, dls2, dvar2 = R.kbuild_bwd(ctx.kind, Z, None, ls, kvar, dKuu)
         dZ = dZ1 + dZ2
         dls = dls1 + dls2
         dkvar = dvar1 + dvar2 - (gsb * (0.5 * P * B)).unsqueeze(1)          # Kff_diag term (:100)
-        # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 ; W adjoint 2 Sbar W ; diag adjoint diag(Sbar)
-        eye = torch.eye(M, dtype=A.dtype, device=A.device).unsqueeze(0).expand(S, M, M).contiguous()
-        Sinv = R.trsm_(Ls, R.trsm_(Ls, eye), transpose=True)
-        minus1 = torch.full((S,), -1.0, dtype=A.dtype, device=A.device)
-        Sbar = R.axpby_dev(coef[:, 0], Sinv, minus1, F2[:, :, M:].contiguous())
+        # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 (S^-1 from the forward pass); W adjoint 2 Sbar W ; diag adjoint diag(Sbar)
+        minus1 = torch.full((S,), -1.0, dtype=dt, device=dev)
+        Sbar = R.axpby_dev(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M].contiguous())
         dW = R.gemm(Sbar, W, alpha=2.0)
         dd = R.get_diag(Sbar)
-        # mu adjoint: g L^-T (s beta v - mt)
-        dmu = R.trsm_(L, R.axpby_dev(gsb, v, -g, mt), transpose=True)
         dnoise = (g * sc * (-beta * beta * Q - (0.5 * B * P) * beta)).unsqueeze(1)
         dY = R.axpby_dev(-gsb, Y, gsb, G1) if need[4] else None             # -g s beta (Y - A^T mt)
         return None, None, None, dX, dY, dZ, dnoise, dmu, dW, dd, dls, dkvar
+
+
+def _sinv_chain(Ls, pks, eye, LsT, Sinv_l, Sinv):
+    """S^-1 = Ls^-T Ls^-1: one solve with the identity, one lower-tiles product, mirror.  Writes into preallocated
+    buffers (they are created on the main stream and only filled on the side stream)."""
+    R.trsm_packed_(Ls, pks, eye)                                # eye <- Ls^-1
+    R.transpose(eye, out=LsT)
+    R.gemm(LsT, eye, beta=0.0, C=Sinv_l, tri=True)
+    R.copy_ltu(Sinv_l, out=Sinv)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """A second stream per device for independent kernel chains (capturable fork/join)."""
+    if device.type != 'cuda':
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = s
+    return s
 
 
 def svgp_log_pdf(kind, X, Y, Z, noise_var, qU_mean, qU_cov_W, qU_cov_diag, lengthscale, variance,
@@ -358,26 +425,26 @@ class _GPLogPdf(torch.autograd.Function):
     def forward(ctx, kind, jitter, X, Y, noise, ls, kvar):
         S, N, P = X.shape[0], X.shape[1], Y.shape[2]
         K = R.kbuild_fwd(kind, X, None, ls, kvar, diag_add=noise, diag_const=jitter)   # :55-60
-        L, info = R.potrf_(K)                                                           # :61
-        LinvY = R.trsm_(L, Y.clone())                                                   # :66
+        L, info, pk = R.potrf_packed_(K)                                                # :61
+        LinvY = R.trsm_packed_(L, pk, Y.clone())                                        # :66
         logdet_l = R.sumlogdiag(L)                                                      # :67 (diag(L) > 0)
         ss = R.reduce(R.RED_SUMSQ, LinvY)
         logL = -logdet_l * P - 0.5 * ss - (0.5 * N * P) * _LOG2PI                       # :68-70
         ctx.kind, ctx.dims = kind, (S, N, P)
-        ctx.save_for_backward(X, ls, kvar, L, LinvY)
+        ctx.save_for_backward(X, ls, kvar, L, LinvY, pk)
         ctx.mark_non_differentiable(L, LinvY)
         ctx.info = info
         return logL, L, LinvY
 
     @staticmethod
     def backward(ctx, g, _gL, _gLY):
-        X, ls, kvar, L, LinvY = ctx.saved_tensors
+        X, ls, kvar, L, LinvY, pk = ctx.saved_tensors
         S, N, P = ctx.dims
         g = g.contiguous()
         # Kbar = g (1/2 a a^T - P/2 K^-1),  a = K^-1 Y = L^-T LinvY ;  Ybar = -g a
-        a = R.trsm_(L, LinvY.clone(), transpose=True)
+        a = R.trsm_packed_(L, pk, LinvY.clone(), transpose=True)
         eye = torch.eye(N, dtype=X.dtype, device=X.device).unsqueeze(0).expand(S, N, N).contiguous()
-        Kinv = R.trsm_(L, R.trsm_(L, eye), transpose=True)
+        Kinv = R.trsm_packed_(L, pk, R.trsm_packed_(L, pk, eye), transpose=True)
         aaT = R.gemm(a, a, transB=True)
         Kbar = R.axpby_dev(0.5 * g, aaT, (-0.5 * P) * g, Kinv)
         dX, _, dls, dvar = R.kbuild_bwd(ctx.kind, X, None, ls, kvar, Kbar)

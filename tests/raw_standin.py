@@ -67,6 +67,23 @@ def potrf_(A, info=None):
     return A, inf.to(torch.int32)
 
 
+def new_pack(A):
+    return torch.zeros((A.shape[0], 1), dtype=A.dtype)
+
+
+def potrf_packed_(A, info=None, pack=None):
+    A, inf = potrf_(A, info)
+    return A, inf, new_pack(A) if pack is None else pack
+
+
+def tri_pack(L):
+    return torch.zeros((L.shape[0], 1), dtype=L.dtype)
+
+
+def trsm_packed_(L, pack, B, transpose=False, alpha=1.0):
+    return trsm_(L, B, transpose=transpose, alpha=alpha)
+
+
 def trsm_(L, B, transpose=False, alpha=1.0):
     Lt = torch.tril(L)
     if transpose:
@@ -77,8 +94,12 @@ def trsm_(L, B, transpose=False, alpha=1.0):
     return B
 
 
-def copy_ltu(P):
-    return (torch.tril(P) + torch.tril(P, -1).transpose(-1, -2)).contiguous()
+def copy_ltu(P, out=None):
+    r = (torch.tril(P) + torch.tril(P, -1).transpose(-1, -2)).contiguous()
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
 
 
 def symmetrize(A, alpha=1.0):
@@ -191,7 +212,7 @@ def softplus_bwd(x, gy):
     return gy * torch.sigmoid(x)
 
 
-def svgp_bwd_assemble(Phi, T, U, mt, v, coef):
+def svgp_bwd_assemble(Phi, T, U, mt, v, coef, out=None):
     M = Phi.shape[-1]
     I = torch.eye(M, dtype=Phi.dtype).unsqueeze(0)
     c = [coef[:, i].reshape(-1, 1, 1) for i in range(6)]
@@ -200,4 +221,8 @@ def svgp_bwd_assemble(Phi, T, U, mt, v, coef):
     E = c[2] * mm + c[0] * (T - I) - c[1] * Phi + c[1] * (U + U.transpose(-1, -2)) - c[3] * (vm + vm.transpose(-1, -2))
     ES = c[0] * I + c[1] * Phi
     ER = -c[4] * (T - I) - c[5] * mm
-    return torch.cat([E, ES, ER], dim=-1).contiguous()
+    r = torch.cat([E, ES, ER], dim=-1).contiguous()
+    if out is not None:
+        out[:, :, :3 * M].copy_(r)
+        return out
+    return r

@@ -283,3 +283,85 @@ def test_gather_rows_bit_exact(cuda):
     off = torch.tensor([128], dtype=torch.int64, device=cuda)
     got = _raw.gather_rows(torch.as_tensor(src, device=cuda), torch.as_tensor(idx, device=cuda), off, 64)
     np.testing.assert_array_equal(got.cpu().numpy(), src[idx[128:192]])
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('n', [1, 3, 64, 65, 128, 130, 300, 513, 1024])
+def test_potrf_packed_and_pack_contents(cuda, prec, n):
+    """GEMM-based potrf (tcgen05 updates in f32): same factor as numpy.linalg.cholesky, MXNet zero-upper convention,
+    and a pack whose blocks really are the inverses of the diagonal blocks / the transpose of L."""
+    from mxfusion_b200 import _raw, _lib
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(6)
+    S = 2
+    W = rng.randn(S, n, n)
+    A = W @ np.swapaxes(W, -1, -2) + n * np.eye(n)[None]
+    want = ol.potrf(A)
+    L, info, pack = _raw.potrf_packed_(T(A, cuda, tdt))
+    assert info.cpu().tolist() == [0, 0]
+    got = L.cpu().numpy()
+    assert np.all(np.triu(got, 1) == 0)
+    if prec == 'f32':
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5 * np.sqrt(n))
+    else:
+        np.testing.assert_allclose(got, want, rtol=rtol * 5, atol=atol * 100)
+    NB = _lib.lib().mxf_tri_block(_lib.dtype_code(L))
+    nblk = (n + NB - 1) // NB
+    pk = pack.cpu().numpy().astype(np.float64)
+    dinv = pk[:, :nblk * NB * NB].reshape(S, nblk, NB, NB)
+    dinvT = pk[:, nblk * NB * NB:2 * nblk * NB * NB].reshape(S, nblk, NB, NB)
+    ldt = (n + 3) & ~3
+    LT = pk[:, 2 * nblk * NB * NB:2 * nblk * NB * NB + n * ldt].reshape(S, n, ldt)[:, :, :n]
+    np.testing.assert_allclose(LT, np.swapaxes(got, -1, -2), rtol=0, atol=0)
+    for b in range(nblk):
+        k0, k1 = b * NB, min(n, (b + 1) * NB)
+        blk = want[:, k0:k1, k0:k1]
+        inv = np.linalg.inv(blk)
+        np.testing.assert_allclose(dinv[:, b, :k1 - k0, :k1 - k0], inv, rtol=rtol * 20, atol=atol * 100)
+        np.testing.assert_allclose(dinvT[:, b, :k1 - k0, :k1 - k0], np.swapaxes(inv, -1, -2), rtol=rtol * 20,
+                                   atol=atol * 100)
+    pk2 = _raw.tri_pack(L).cpu().numpy().astype(np.float64)       # pack of an existing factor: same contents
+    np.testing.assert_allclose(pk2[:, :2 * nblk * NB * NB], pk[:, :2 * nblk * NB * NB], rtol=rtol * 20, atol=atol * 100)
+    LT2 = pk2[:, 2 * nblk * NB * NB:2 * nblk * NB * NB + n * ldt].reshape(S, n, ldt)[:, :, :n]
+    np.testing.assert_array_equal(LT2, LT)
+
+
+def test_potrf_packed_reports_first_bad_pivot(cuda):
+    from mxfusion_b200 import _raw
+    A = np.eye(300)[None].repeat(2, 0)
+    A[1, 170, 170] = -1.0
+    L, info, _ = _raw.potrf_packed_(T(A, cuda, torch.float32))
+    assert info.cpu().tolist() == [0, 171]
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('transpose', [False, True])
+@pytest.mark.parametrize('n,nrhs', [(1, 1), (3, 1), (64, 5), (65, 130), (200, 257), (513, 33), (1024, 1024),
+                                    (1024, 4096), (300, 3072)])
+def test_trsm_packed(cuda, prec, transpose, n, nrhs):
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(7)
+    S = 2
+    Lm = np.tril(rng.randn(S, n, n)) * (0.5 / np.sqrt(n)) + 2.0 * np.eye(n)[None]
+    B = rng.randn(S, n, nrhs)
+    want = ol.trsm(Lm, B, transpose=transpose, alpha=0.5)
+    Lt, Bt = T(Lm, cuda, tdt), T(B, cuda, tdt)
+    pack = _raw.tri_pack(Lt)
+    _raw.trsm_packed_(Lt, pack, Bt, transpose=transpose, alpha=0.5)
+    # well-conditioned factor: fp32 must stay at fp32 accuracy (3xTF32 updates, inverted diagonal blocks)
+    if prec == 'f32':
+        np.testing.assert_allclose(Bt.cpu().numpy(), want, rtol=5e-5, atol=5e-5)
+    else:
+        np.testing.assert_allclose(Bt.cpu().numpy(), want, rtol=rtol * 5, atol=atol * 100)
+
+
+def test_trsm_packed_shared_factor(cuda):
+    from mxfusion_b200 import _raw
+    rng = np.random.RandomState(8)
+    Lm = np.tril(rng.randn(1, 150, 150)) * 0.05 + 2.0 * np.eye(150)[None]
+    B = rng.randn(3, 150, 40)
+    want = ol.trsm(np.repeat(Lm, 3, 0), B)
+    Lt, Bt = T(Lm, cuda, torch.float32), T(B, cuda, torch.float32)
+    _raw.trsm_packed_(Lt, _raw.tri_pack(Lt), Bt)
+    np.testing.assert_allclose(Bt.cpu().numpy(), want, rtol=1e-3, atol=1e-4)
