@@ -28,8 +28,12 @@ class Normal(Distribution):
         x, m, v = kw['random_variable'], kw['mean'], kw['variance']
         n = max(x[0].numel(), m[0].numel(), v[0].numel())
         if not (x[0].numel() == m[0].numel() == v[0].numel() == n):
-            shape = torch.broadcast_shapes(x.shape[1:], m.shape[1:], v.shape[1:])
-            x, m, v = [t.expand((t.shape[0],) + tuple(shape)) for t in (x, m, v)]
+            shape = tuple(torch.broadcast_shapes(x.shape[1:], m.shape[1:], v.shape[1:]))
+
+            def bc(t):      # broadcast everything after the sample axis (NumPy rules: align trailing dimensions)
+                t = t.reshape((t.shape[0],) + (1,) * (len(shape) - (t.dim() - 1)) + tuple(t.shape[1:]))
+                return t.expand((t.shape[0],) + shape)
+            x, m, v = bc(x), bc(m), bc(v)
         return ops.normal_log_pdf_sum(x, m, v, self.log_pdf_scaling).reshape(())
 
     def draw_samples_impl(self, mean, variance, rv_shape, num_samples=1, F=None):

@@ -22,8 +22,12 @@ Parity pinning
   2. an independent formulation of every quantity (dense Hensman bound,
      ``scipy.stats.multivariate_normal``, ``scipy.stats.norm``), replacing the
      GPy asserts of the reference tests (GPy is absent too);
-  3. fixtures under ``tests/golden/`` produced by running the reference's
-     *own Python source* from /root/reference on top of a NumPy stand-in for
-     the ``mxnet`` module (``tests/golden/make_golden.py``).
+  3. fixtures under ``tests/golden/*.npz`` produced by running the reference's
+     *own Python source* from /root/reference on top of a stand-in for the
+     ``mxnet`` module (``tests/golden/make_golden.py`` +
+     ``tests/golden/_mxnet_standin``): kernels, SVGP / GP values AND gradients,
+     the minibatch loop's trajectory, Normal, mean-field SVI.  The stand-in is
+     itself validated by reproducing the loss the reference's GP notebook
+     prints after 100 Adam steps (-16.903135 vs -16.903127 here).
 """
 from . import kernels, linalg, transforms, normal, gp, svgp, loop  # noqa: F401

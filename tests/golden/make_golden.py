@@ -1,0 +1,280 @@
+"""Generates tests/golden/*.npz by running the REFERENCE'S OWN Python source (/root/reference) on the stand-in
+`mxnet` package of tests/golden/_mxnet_standin (torch CPU float64; see its __init__ for what that pins).
+
+    python tests/golden/make_golden.py          # only in the build container: /root/reference must exist
+
+Scenarios follow the reference's tests and notebooks:
+  kernels   testing/components/distributions/gp/kernel_test.py (RBF / Matern, ARD, sample axis, active_dims)
+  svgp      testing/modules/svgpregression_test.py:41-115 fixture (+ Matern52, P=2, rv_scaling), value and gradients
+  gp        testing/modules/gpregression_test.py:40-96 fixture, value, gradients, cached L / LinvY
+  gp_nb     examples/notebooks/gp_regression.ipynb: loss at init, 100 Adam steps (printed -16.903135093930537)
+  svgp_mb   MinibatchInferenceLoop trajectory (shuffled rollover batches, rv_scaling, grads / B)
+  normal    testing/components/distributions/normal_test.py:35-109 (log_pdf, reparameterised draw with injected eps)
+  svi       StochasticVariationalInference on a conjugate toy model with injected posterior samples
+Each .npz stores the inputs next to the outputs, so tests need nothing but the file.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+sys.path.insert(0, os.path.join(HERE, '_mxnet_standin'))
+sys.path.insert(0, '/root/reference')
+warnings.filterwarnings('ignore')
+
+import mxnet as mx  # noqa: E402  (the stand-in)
+import mxfusion  # noqa: E402  (the reference)
+from mxfusion import Model, Variable  # noqa: E402
+from mxfusion.common import config  # noqa: E402
+from mxfusion.components.variables import PositiveTransformation  # noqa: E402
+from mxfusion.components.distributions import Normal  # noqa: E402
+from mxfusion.components.distributions.gp.kernels import RBF, Matern12, Matern32, Matern52  # noqa: E402
+from mxfusion.modules.gp_modules import GPRegression, SVGPRegression  # noqa: E402
+from mxfusion.inference import (Inference, GradBasedInference, MAP, BatchInferenceLoop, MinibatchInferenceLoop,  # noqa: E402
+                                StochasticVariationalInference, create_Gaussian_meanfield)
+from mxfusion.util.testutils import MockMXNetRandomGenerator  # noqa: E402
+
+config.DEFAULT_DTYPE = 'float64'
+DT = 'float64'
+KERNELS = {'rbf': RBF, 'matern12': Matern12, 'matern32': Matern32, 'matern52': Matern52}
+
+
+def nd(a):
+    return mx.nd.array(a, dtype=DT)
+
+
+def save(name, **arrays):
+    np.savez(os.path.join(HERE, name + '.npz'), **{k: np.asarray(v) for k, v in arrays.items()})
+    print('wrote', name, sorted(arrays.keys()))
+
+
+def grads_of(infr, variables):
+    out = {}
+    for name, var in variables.items():
+        p = infr.params.param_dict[var.uuid]
+        out[name] = p.grad().asnumpy().copy()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+def golden_kernels():
+    rng = np.random.RandomState(0)
+    out = {}
+    for kname, cls in KERNELS.items():
+        for ard in (False, True):
+            for S in (1, 3):
+                D, N, N2 = 3, 7, 5
+                X = rng.rand(S, N, D)
+                X2 = rng.rand(S, N2, D)
+                ls = rng.rand(S, D if ard else 1) + 0.5
+                var = rng.rand(S, 1) + 0.5
+                k = cls(input_dim=D, ARD=ard, dtype=DT)
+                params = {k.name + '_lengthscale': nd(ls), k.name + '_variance': nd(var)}
+                tag = '%s_ard%d_S%d' % (kname, int(ard), S)
+                out[tag + '_X'], out[tag + '_X2'], out[tag + '_ls'], out[tag + '_var'] = X, X2, ls, var
+                out[tag + '_K'] = k.K(mx.nd, nd(X), **params).asnumpy()
+                out[tag + '_K2'] = k.K(mx.nd, nd(X), nd(X2), **params).asnumpy()
+                out[tag + '_Kdiag'] = k.Kdiag(mx.nd, nd(X), **params).asnumpy()
+    # active_dims (kernel_test.py active-dims cases): only dims [0, 2] of a 4-d input
+    X = rng.rand(1, 6, 4)
+    ls, var = rng.rand(1, 2) + 0.5, rng.rand(1, 1) + 0.5
+    k = RBF(input_dim=2, ARD=True, active_dims=[0, 2], dtype=DT)
+    out['active_X'], out['active_ls'], out['active_var'] = X, ls, var
+    out['active_K'] = k.K(mx.nd, nd(X), **{'rbf_lengthscale': nd(ls), 'rbf_variance': nd(var)}).asnumpy()
+    save('kernels', **out)
+
+
+# ------------------------------------------------------------------------------------------------ SVGP fixture
+def svgp_case(kname, P, seed, rv_scaling=None, N=10, M=3, Din=3, jitter=1e-8):
+    np.random.seed(seed)
+    X, Y, Z = np.random.rand(N, Din), np.random.rand(N, P), np.random.rand(M, Din)
+    qU_mean, qU_cov_W, qU_cov_diag = np.random.rand(M, P), np.random.rand(M, M), np.random.rand(M,)
+    noise_var, lengthscale, variance = np.random.rand(1), np.random.rand(Din), np.random.rand(1)
+    m = Model()
+    m.N = Variable()
+    m.X = Variable(shape=(m.N, Din))
+    m.Z = Variable(shape=(M, Din), initial_value=nd(Z))
+    m.noise_var = Variable(transformation=PositiveTransformation(), initial_value=nd(noise_var))
+    kernel = KERNELS[kname](input_dim=Din, ARD=True, variance=nd(variance), lengthscale=nd(lengthscale), dtype=DT)
+    m.Y = SVGPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                         shape=(m.N, P), dtype=DT)
+    gp = m.Y.factor
+    gp.svgp_log_pdf.jitter = jitter
+    loop = MinibatchInferenceLoop(batch_size=N, rv_scaling={m.Y: rv_scaling}) if rv_scaling else BatchInferenceLoop()
+    infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), grad_loop=loop, dtype=DT)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    post = gp._extra_graphs[0]
+    infr.params[post.qU_mean] = nd(qU_mean)
+    infr.params[post.qU_cov_W] = nd(qU_cov_W)
+    infr.params[post.qU_cov_diag] = nd(qU_cov_diag)
+    executor = infr.create_executor()
+    with mx.autograd.record():
+        loss, loss_g = executor(mx.nd.zeros(1), nd(X), nd(Y))
+        loss_g.backward()
+    g = grads_of(infr, dict(Z=m.Z, noise_var=m.noise_var, qU_mean=post.qU_mean, qU_cov_W=post.qU_cov_W,
+                            qU_cov_diag=post.qU_cov_diag, lengthscale=kernel.lengthscale, variance=kernel.variance))
+    return dict(X=X, Y=Y, Z=Z, qU_mean=qU_mean, qU_cov_W=qU_cov_W, qU_cov_diag=qU_cov_diag, noise_var=noise_var,
+                lengthscale=lengthscale, variance=variance, jitter=jitter, rv_scaling=rv_scaling or 1.0,
+                loss=loss.asnumpy(), **{'grad_' + k: v for k, v in g.items()})
+
+
+def golden_svgp():
+    out = {}
+    cases = [('rbf', 1, 0, None), ('matern52', 1, 1, None), ('rbf', 2, 2, None), ('rbf', 1, 3, 12.5),
+             ('matern32', 2, 4, 3.0), ('matern12', 1, 5, None)]
+    for i, (kname, P, seed, sc) in enumerate(cases):
+        r = svgp_case(kname, P, seed, sc)
+        out['case%d_kernel' % i] = kname
+        for k, v in r.items():
+            out['case%d_%s' % (i, k)] = v
+    out['n_cases'] = len(cases)
+    save('svgp_fixture', **out)
+
+
+# ------------------------------------------------------------------------------------------------ exact GP fixture
+def golden_gp():
+    out = {}
+    for i, (kname, P, seed) in enumerate([('rbf', 2, 0), ('matern52', 1, 1), ('matern32', 3, 2)]):
+        np.random.seed(seed)
+        N, Din = 10, 3
+        X, Y = np.random.rand(N, Din), np.random.rand(N, P)
+        noise_var, lengthscale, variance = np.random.rand(1), np.random.rand(Din), np.random.rand(1)
+        m = Model()
+        m.N = Variable()
+        m.X = Variable(shape=(m.N, Din))
+        m.noise_var = Variable(transformation=PositiveTransformation(), initial_value=nd(noise_var))
+        kernel = KERNELS[kname](input_dim=Din, ARD=True, variance=nd(variance), lengthscale=nd(lengthscale), dtype=DT)
+        m.Y = GPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, shape=(m.N, P), dtype=DT)
+        infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), dtype=DT)
+        infr.initialize(X=X.shape, Y=Y.shape)
+        executor = infr.create_executor()
+        with mx.autograd.record():
+            loss, loss_g = executor(mx.nd.zeros(1), nd(X), nd(Y))
+            loss_g.backward()
+        g = grads_of(infr, dict(noise_var=m.noise_var, lengthscale=kernel.lengthscale, variance=kernel.variance))
+        post = m.Y.factor._extra_graphs[0]
+        r = dict(X=X, Y=Y, noise_var=noise_var, lengthscale=lengthscale, variance=variance, loss=loss.asnumpy(),
+                 L=infr.params[post.L].asnumpy(), LinvY=infr.params[post.LinvY].asnumpy(),
+                 **{'grad_' + k: v for k, v in g.items()})
+        out['case%d_kernel' % i] = kname
+        for k, v in r.items():
+            out['case%d_%s' % (i, k)] = v
+    out['n_cases'] = 3
+    save('gp_fixture', **out)
+
+
+# ------------------------------------------------------------------------------------------------ GP notebook
+def golden_gp_notebook():
+    np.random.seed(0)
+    X = np.random.uniform(-3., 3., (20, 1))
+    Y = np.sin(X) + np.random.randn(20, 1) * 0.05
+    m = Model()
+    m.N = Variable()
+    m.X = Variable(shape=(m.N, 1))
+    m.noise_var = Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=0.01)
+    m.kernel = RBF(input_dim=1, variance=1, lengthscale=1)
+    m.Y = GPRegression.define_variable(X=m.X, kernel=m.kernel, noise_var=m.noise_var, shape=(m.N, 1))
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]))
+    infr.initialize(X=X.shape, Y=Y.shape)
+    loss0, _ = infr.create_executor()(mx.nd.zeros(1), nd(X), nd(Y))
+    infr.run(X=nd(X), Y=nd(Y), max_iter=100, learning_rate=0.05, verbose=False)
+    loss1, _ = infr.create_executor()(mx.nd.zeros(1), nd(X), nd(Y))
+    save('gp_notebook', X=X, Y=Y, loss_init=loss0.asnumpy(), loss_final=loss1.asnumpy(),
+         variance=infr.params[m.kernel.variance].asnumpy(), lengthscale=infr.params[m.kernel.lengthscale].asnumpy(),
+         noise_var=infr.params[m.noise_var].asnumpy(), printed_loss=-16.903135093930537,
+         printed_params=np.array([0.616992, 1.649073, 0.002251]))
+    print('  stand-in vs the notebook\'s printed loss:', float(loss1.asnumpy()), 'vs -16.903135093930537')
+
+
+# ------------------------------------------------------------------------------------------------ SVGP minibatch loop
+def golden_svgp_minibatch():
+    np.random.seed(0)
+    N, B, M, epochs = 203, 20, 8, 3
+    X = np.random.uniform(-3., 3., (N, 1))
+    Y = np.sin(X) + np.random.randn(N, 1) * 0.05
+    Z0 = np.linspace(-3, 3, M)[:, None]
+    m = Model()
+    m.N = Variable()
+    m.X = Variable(shape=(m.N, 1))
+    m.noise_var = Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=0.01)
+    m.kernel = RBF(input_dim=1, variance=1, lengthscale=1)
+    m.Y = SVGPRegression.define_variable(X=m.X, kernel=m.kernel, noise_var=m.noise_var, shape=(m.N, 1), num_inducing=M)
+    m.Y.factor.svgp_log_pdf.jitter = 1e-6
+    loop = MinibatchInferenceLoop(batch_size=B, rv_scaling={m.Y: N / B})
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]), grad_loop=loop)
+    infr.initialize(X=(N, 1), Y=(N, 1))
+    post = m.Y.factor._extra_graphs[0]
+    infr.params[m.Y.factor.inducing_inputs] = nd(Z0)
+    infr.params[post.qU_mean] = nd(np.zeros((M, 1)))
+    infr.params[post.qU_cov_W] = nd(np.eye(M) * 0.1)
+    infr.params[post.qU_cov_diag] = nd(np.ones(M) * 0.5)
+    np.random.seed(123)                        # the sampler's shuffles come from the NumPy global generator
+    infr.run(X=nd(X), Y=nd(Y), max_iter=epochs, learning_rate=0.05, verbose=False)
+    loss_full, _ = infr.create_executor()(mx.nd.zeros(1), nd(X), nd(Y))
+    save('svgp_minibatch', X=X, Y=Y, Z0=Z0, N=N, B=B, M=M, epochs=epochs, shuffle_seed=123, lr=0.05,
+         final_Z=infr.params[m.Y.factor.inducing_inputs].asnumpy(), final_qU_mean=infr.params[post.qU_mean].asnumpy(),
+         final_qU_cov_diag=infr.params[post.qU_cov_diag].asnumpy(),
+         final_lengthscale=infr.params[m.kernel.lengthscale].asnumpy(),
+         final_variance=infr.params[m.kernel.variance].asnumpy(), final_noise_var=infr.params[m.noise_var].asnumpy(),
+         final_full_data_loss_at_batch_scaling=loss_full.asnumpy())
+
+
+# ------------------------------------------------------------------------------------------------ Normal
+def golden_normal():
+    rng = np.random.RandomState(0)
+    out = {}
+    S, shape = 3, (5, 2)
+    mean, var, rv = rng.randn(S, *shape), rng.rand(S, *shape) + 0.2, rng.randn(S, *shape)
+    m = Normal.define_variable(shape=shape, dtype=DT).factor
+    variables = {m.mean.uuid: nd(mean), m.variance.uuid: nd(var), m.random_variable.uuid: nd(rv)}
+    out['mean'], out['var'], out['rv'] = mean, var, rv
+    out['log_pdf'] = m.log_pdf(F=mx.nd, variables=variables).asnumpy()
+    m.log_pdf_scaling = 2.5
+    out['log_pdf_scaled_2p5'] = m.log_pdf(F=mx.nd, variables=variables).asnumpy()
+    eps = rng.randn(S, *shape)
+    m2 = Normal.define_variable(shape=shape, dtype=DT, rand_gen=MockMXNetRandomGenerator(nd(eps.flatten()))).factor
+    variables = {m2.mean.uuid: nd(mean[:1]), m2.variance.uuid: nd(var[:1])}
+    out['eps'] = eps
+    out['draw'] = m2.draw_samples(F=mx.nd, variables=variables, num_samples=S).asnumpy()
+    save('normal', **out)
+
+
+# ------------------------------------------------------------------------------------------------ mean-field SVI
+def golden_svi():
+    rng = np.random.RandomState(1)
+    N, S = 6, 4
+    y = rng.randn(N, 1)
+    eps_mu = rng.randn(S, 1)
+    m = Model()
+    m.mu = Normal.define_variable(mean=nd([0.]), variance=nd([4.]), shape=(1,), dtype=DT)
+    m.s2 = Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=nd([0.7]))
+    m.y = Normal.define_variable(mean=mxfusion.components.functions.operators.broadcast_to(m.mu, (N, 1)),
+                                 variance=mxfusion.components.functions.operators.broadcast_to(m.s2, (N, 1)),
+                                 shape=(N, 1), dtype=DT)
+    q = create_Gaussian_meanfield(model=m, observed=[m.y], dtype=DT)
+    q.mu.factor._rand_gen = MockMXNetRandomGenerator(nd(eps_mu.flatten()))
+    alg = StochasticVariationalInference(num_samples=S, model=m, posterior=q, observed=[m.y])
+    infr = GradBasedInference(inference_algorithm=alg, dtype=DT)
+    infr.initialize(y=y.shape)
+    infr.params[q.mu.factor.mean] = nd([0.3])
+    infr.params[q.mu.factor.variance] = nd([0.5])
+    executor = infr.create_executor()
+    with mx.autograd.record():
+        loss, loss_g = executor(mx.nd.zeros(1), nd(y))
+        loss_g.backward()
+    g = grads_of(infr, dict(q_mean=q.mu.factor.mean, q_var=q.mu.factor.variance, s2=m.s2))
+    save('svi_toy', y=y, eps=eps_mu, S=S, prior_mean=0., prior_var=4., s2=0.7, q_mean=0.3, q_var=0.5,
+         loss=loss.asnumpy(), **{'grad_' + k: v for k, v in g.items()})
+
+
+if __name__ == '__main__':
+    golden_kernels()
+    golden_svgp()
+    golden_gp()
+    golden_gp_notebook()
+    golden_svgp_minibatch()
+    golden_normal()
+    golden_svi()

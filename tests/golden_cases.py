@@ -1,0 +1,140 @@
+"""Shared drivers for the golden-fixture tests (tests/golden/*.npz were produced by the reference's own source,
+see tests/golden/make_golden.py).  Used by the CPU tier (CUDA binding replaced by tests/raw_standin.py) and by the
+GPU tier (real kernels)."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False))
+
+
+def kernel_class(name):
+    from mxfusion_b200.components.distributions.gp.kernels import RBF, Matern12, Matern32, Matern52
+    return {'rbf': RBF, 'matern12': Matern12, 'matern32': Matern32, 'matern52': Matern52}[str(name)]
+
+
+def param_grad(infr, var):
+    return infr.params.param_dict[var.uuid].tensor.grad.detach().cpu().numpy().copy()
+
+
+def run_svgp_case(mf, g, i, device):
+    """Rebuilds case i of svgp_fixture.npz through the public API; returns (loss, grads wrt stored parameters)."""
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.modules.gp_modules import SVGPRegression
+    from mxfusion_b200.inference import GradBasedInference, MAP, MinibatchInferenceLoop, BatchInferenceLoop
+    c = lambda k: g['case%d_%s' % (i, k)]
+    X, Y, Z = c('X'), c('Y'), c('Z')
+    N, Din = X.shape
+    M, P = Z.shape[0], Y.shape[1]
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, Din))
+    m.Z = mf.Variable(shape=(M, Din), initial_value=Z)
+    m.noise_var = mf.Variable(transformation=PositiveTransformation(), initial_value=c('noise_var'))
+    kernel = kernel_class(c('kernel'))(input_dim=Din, ARD=True, variance=c('variance'), lengthscale=c('lengthscale'))
+    m.Y = SVGPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                         shape=(m.N, P))
+    gp = m.Y.factor
+    gp.svgp_log_pdf.jitter = float(c('jitter'))
+    sc = float(c('rv_scaling'))
+    loop = MinibatchInferenceLoop(batch_size=N, rv_scaling={m.Y: sc}) if sc != 1.0 else BatchInferenceLoop()
+    infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), grad_loop=loop, context=device)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    post = gp._extra_graphs[0]
+    infr.params[post.qU_mean] = c('qU_mean')
+    infr.params[post.qU_cov_W] = c('qU_cov_W')
+    infr.params[post.qU_cov_diag] = c('qU_cov_diag')
+    infr.params.gflat.zero_()
+    loss, loss_g = infr.create_executor()(None, torch.tensor(X, device=device), torch.tensor(Y, device=device))
+    loss_g.backward()
+    grads = dict(Z=param_grad(infr, m.Z), noise_var=param_grad(infr, m.noise_var),
+                 qU_mean=param_grad(infr, post.qU_mean), qU_cov_W=param_grad(infr, post.qU_cov_W),
+                 qU_cov_diag=param_grad(infr, post.qU_cov_diag), lengthscale=param_grad(infr, kernel.lengthscale),
+                 variance=param_grad(infr, kernel.variance))
+    return float(loss), grads
+
+
+def run_gp_case(mf, g, i, device):
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.modules.gp_modules import GPRegression
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    c = lambda k: g['case%d_%s' % (i, k)]
+    X, Y = c('X'), c('Y')
+    N, Din = X.shape
+    P = Y.shape[1]
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, Din))
+    m.noise_var = mf.Variable(transformation=PositiveTransformation(), initial_value=c('noise_var'))
+    kernel = kernel_class(c('kernel'))(input_dim=Din, ARD=True, variance=c('variance'), lengthscale=c('lengthscale'))
+    m.Y = GPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, shape=(m.N, P))
+    infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), context=device)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    infr.params.gflat.zero_()
+    loss, loss_g = infr.create_executor()(None, torch.tensor(X, device=device), torch.tensor(Y, device=device))
+    loss_g.backward()
+    post = m.Y.factor._extra_graphs[0]
+    grads = dict(noise_var=param_grad(infr, m.noise_var), lengthscale=param_grad(infr, kernel.lengthscale),
+                 variance=param_grad(infr, kernel.variance))
+    return float(loss), grads, infr.params[post.L].cpu().numpy(), infr.params[post.LinvY].cpu().numpy()
+
+
+def run_svgp_minibatch(mf, g, device, **loop_kw):
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.components.distributions.gp.kernels import RBF
+    from mxfusion_b200.modules.gp_modules import SVGPRegression
+    from mxfusion_b200.inference import GradBasedInference, MAP, MinibatchInferenceLoop
+    N, B, M, epochs = int(g['N']), int(g['B']), int(g['M']), int(g['epochs'])
+    X, Y = g['X'], g['Y']
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, 1))
+    m.noise_var = mf.Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=0.01)
+    m.kernel = RBF(input_dim=1, variance=1, lengthscale=1)
+    m.Y = SVGPRegression.define_variable(X=m.X, kernel=m.kernel, noise_var=m.noise_var, shape=(m.N, 1),
+                                         num_inducing=M)
+    m.Y.factor.svgp_log_pdf.jitter = 1e-6
+    loop = MinibatchInferenceLoop(batch_size=B, rv_scaling={m.Y: N / B}, **loop_kw)
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]), grad_loop=loop, context=device)
+    infr.initialize(X=(N, 1), Y=(N, 1))
+    post = m.Y.factor._extra_graphs[0]
+    infr.params[m.Y.factor.inducing_inputs] = g['Z0']
+    infr.params[post.qU_mean] = np.zeros((M, 1))
+    infr.params[post.qU_cov_W] = np.eye(M) * 0.1
+    infr.params[post.qU_cov_diag] = np.ones(M) * 0.5
+    np.random.seed(int(g['shuffle_seed']))
+    infr.run(X=X, Y=Y, max_iter=epochs, learning_rate=float(g['lr']))
+    return dict(final_Z=infr.params[m.Y.factor.inducing_inputs], final_qU_mean=infr.params[post.qU_mean],
+                final_qU_cov_diag=infr.params[post.qU_cov_diag], final_lengthscale=infr.params[m.kernel.lengthscale],
+                final_variance=infr.params[m.kernel.variance], final_noise_var=infr.params[m.noise_var])
+
+
+def run_svi_toy(mf, g, device):
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.components.distributions import Normal, MockMXNetRandomGenerator
+    from mxfusion_b200.inference import GradBasedInference, StochasticVariationalInference, create_Gaussian_meanfield
+    y = g['y']
+    N, S = y.shape[0], int(g['S'])
+    t = lambda a: torch.tensor(np.atleast_1d(a), dtype=torch.float64)
+    m = mf.Model()
+    m.mu = Normal.define_variable(mean=t(g['prior_mean']), variance=t(g['prior_var']), shape=(1,))
+    m.s2 = mf.Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=t(g['s2']))
+    m.y = Normal.define_variable(mean=m.mu, variance=m.s2, shape=(N, 1))
+    q = create_Gaussian_meanfield(model=m, observed=[m.y])
+    q.mu.factor._rand_gen = MockMXNetRandomGenerator(torch.tensor(g['eps'].flatten(), device=device))
+    alg = StochasticVariationalInference(num_samples=S, model=m, posterior=q, observed=[m.y])
+    infr = GradBasedInference(inference_algorithm=alg, context=device)
+    infr.initialize(y=y.shape)
+    infr.params[q.mu.factor.mean] = t(g['q_mean'])
+    infr.params[q.mu.factor.variance] = t(g['q_var'])
+    infr.params.gflat.zero_()
+    loss, loss_g = infr.create_executor()(None, torch.tensor(y, device=device))
+    loss_g.backward()
+    grads = dict(q_mean=param_grad(infr, q.mu.factor.mean), q_var=param_grad(infr, q.mu.factor.variance),
+                 s2=param_grad(infr, m.s2))
+    return float(loss), grads
