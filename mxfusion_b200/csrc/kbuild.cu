@@ -166,6 +166,7 @@ kbuild_fwd_kernel(const T* __restrict__ X, const T* __restrict__ X2, const T* __
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             T r2 = acc[r][c] + na + nb[c];
+            if (SYM && i == j0 + c) r2 = T(0);       // exact on the diagonal of K(X,X) (see the streaming kernel)
             o[c] = kern_value<T, KIND>(r2, v);
             if (SYM && i == j0 + c) o[c] += dadd;
         }
@@ -213,12 +214,187 @@ static int launch_fwd(const T* X, const T* X2, const T* ls, int ls_len, const T*
     return after_launch();
 }
 
+// ------------------------------------------------------------------------------------------
+// forward, streaming variant (D <= 16): the kernel behind the K(X,Z) HBM figure.
+//
+// A CTA (8 warps arranged WR x WC) owns WC*128 output columns and `chunk_rows` output rows.  Each warp keeps the
+// scaled vectors of its 128 columns (4 per lane) in registers for the whole CTA lifetime and walks the rows RM at a
+// time; the scaled row vectors of the chunk sit in shared memory (staged once, read as warp-uniform 16-byte
+// broadcasts).  Every store is a 16-byte streaming store, a warp writes 512 contiguous bytes per row.
+// RBF folds all constants into the operands:  K = 2^(log2 var - c r2),  c = log2(e)/2, so an element costs
+// 1 FADD + D FFMA + 1 MUFU.EX2.
+// ------------------------------------------------------------------------------------------
+template <int DP> struct KsRM { static constexpr int value = DP <= 8 ? 8 : 4; };
+
+template <typename T> __device__ __forceinline__ void store4_stream(T* dst, const T (&o)[4]);
+template <> __device__ __forceinline__ void store4_stream<float>(float* dst, const float (&o)[4]) {
+    __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+}
+template <> __device__ __forceinline__ void store4_stream<double>(double* dst, const double (&o)[4]) {
+    __stcs(reinterpret_cast<double2*>(dst), make_double2(o[0], o[1]));
+    __stcs(reinterpret_cast<double2*>(dst + 2), make_double2(o[2], o[3]));
+}
+
+template <typename T, int KIND, int DP, int WC, bool SYM>
+__global__ void __launch_bounds__(256, 2)
+kbuild_fwd_stream_kernel(const T* __restrict__ X, const T* __restrict__ X2, const T* __restrict__ ls, int ls_len,
+                         const T* __restrict__ var, const T* __restrict__ diag_add, T diag_const,
+                         T* __restrict__ out, int64_t ldo, int N, int N2, int D, int chunk_rows, int64_t sX,
+                         int64_t sX2, int64_t sLs, int64_t sVar, int64_t sDiag, int64_t sOut, int vec_ok) {
+    constexpr int WR = 8 / WC;
+    constexpr int KS_RM = KsRM<DP>::value;
+    constexpr bool RBF_FOLD = (KIND == MXF_KERN_RBF);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* a_s = reinterpret_cast<T*>(smem_raw);          // [chunk_rows][DP]  -2 * scaled row vectors
+    T* na_s = a_s + (size_t)chunk_rows * DP;          // [chunk_rows]      |scaled row|^2
+    T* sc_s = na_s + chunk_rows;                      // [DP]              per-dimension scale (0 in the padding)
+
+    const int s = blockIdx.z;
+    const T* Xs = X + (int64_t)s * sX;
+    const T* X2s = X2 + (int64_t)s * sX2;
+    const T* lss = ls + (int64_t)s * sLs;
+    const T v = var[(int64_t)s * sVar];
+    T* outs = out + (int64_t)s * sOut;
+    const int i0 = blockIdx.y * chunk_rows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wc = warp % WC, wr = warp / WC;
+    const int j0 = (blockIdx.x * WC + wc) * 128 + lane * 4;
+    const T csq = RBF_FOLD ? T(0.84932180028801904272) : T(1);      // sqrt(log2(e)/2)
+
+    for (int d = threadIdx.x; d < DP; d += 256) sc_s[d] = d < D ? csq / lss[ls_len == 1 ? 0 : d] : T(0);
+    __syncthreads();
+    const int nrows = min(chunk_rows, N - i0);
+    for (int e = threadIdx.x; e < chunk_rows * DP; e += 256) {
+        const int r = e / DP, d = e - r * DP;
+        const T x = (r < nrows && d < D) ? Xs[(int64_t)(i0 + r) * D + d] : T(0);
+        a_s[e] = T(-2) * x * sc_s[d];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < chunk_rows; r += 256) {
+        T acc = 0;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { const T a = a_s[r * DP + d]; acc = fma(a, a, acc); }
+        na_s[r] = T(0.25) * acc;
+    }
+    // scaled column vectors of this lane's 4 columns
+    T b[4][DP];
+    T nb[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int j = j0 + c;
+        T n2 = 0;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            T x = (j < N2 && d < D) ? X2s[(int64_t)j * D + d] : T(0);
+            x *= sc_s[d];
+            b[c][d] = x;
+            n2 = fma(x, x, n2);
+        }
+        nb[c] = RBF_FOLD ? n2 - log2(v) : n2;
+    }
+    __syncthreads();
+    if (j0 >= N2) return;
+    T dadd = T(0);
+    if (SYM) dadd = diag_const + (diag_add ? diag_add[(int64_t)s * sDiag] : T(0));
+    const bool full4 = vec_ok && (j0 + 3 < N2);
+
+    for (int rt = wr * KS_RM; rt < nrows; rt += WR * KS_RM) {
+        T acc[KS_RM][4];
+#pragma unroll
+        for (int r = 0; r < KS_RM; ++r) {
+            const T na = na_s[rt + r];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = na + nb[c];
+        }
+#pragma unroll
+        for (int r = 0; r < KS_RM; ++r) {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                const T a = a_s[(rt + r) * DP + d];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fma(a, b[c][d], acc[r][c]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < KS_RM; ++r) {
+            const int i = i0 + rt + r;
+            if (rt + r >= nrows) break;
+            T o[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                T e = acc[r][c];
+                // K(X,X): on the diagonal r2 is exactly 0; the expanded form only leaves cancellation noise there, which
+                // the Matern square root would amplify (sqrt(1e-7) in f32)
+                if (SYM && i == j0 + c) e = RBF_FOLD ? -log2(v) : T(0);
+                if (RBF_FOLD) o[c] = (sizeof(T) == 4) ? (T)exp2f(-(float)e) : (T)exp2(-(double)e);
+                else o[c] = kern_value<T, KIND>(e, v);
+                if (SYM && i == j0 + c) o[c] += dadd;
+            }
+            T* dst = outs + (int64_t)i * ldo + j0;
+            if (full4) {
+                store4_stream<T>(dst, o);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (j0 + c < N2) dst[c] = o[c];
+            }
+        }
+    }
+}
+
+template <typename T, int KIND, int DP, int WC>
+static int launch_fwd_stream(const T* X, const T* X2, const T* ls, int ls_len, const T* var, const T* diag_add,
+                             double diag_const, T* out, int64_t ldo, int S, int N, int N2, int D, int64_t sX,
+                             int64_t sX2, int64_t sLs, int64_t sVar, int64_t sDiag, int64_t sOut, cudaStream_t st) {
+    constexpr int WR = 8 / WC;
+    constexpr int KS_RM = KsRM<DP>::value;
+    const bool sym = (X2 == nullptr);
+    const T* X2e = sym ? X : X2;
+    const int64_t sX2e = sym ? sX : sX2;
+    const int colblocks = cdiv(N2, WC * 128);
+    // rows per CTA: a multiple of WR*RM, at most 256, small enough to give every SM several CTAs
+    const int unit = WR * KS_RM;
+    int chunk = 256;
+    while (chunk > unit && (int64_t)colblocks * cdiv(N, chunk) * S < 4 * kNumSMs) chunk >>= 1;
+    chunk = std::max(unit, (chunk / unit) * unit);
+    const size_t smem = sizeof(T) * ((size_t)chunk * DP + chunk + DP);
+    dim3 grid(colblocks, cdiv(N, chunk), S);
+    if (grid.y > 65535) return MXF_ENOTIMPL;
+    const int vec_ok = (ldo % 4 == 0) && (sOut % 4 == 0) && (((uintptr_t)out) % 16 == 0);
+    if (sym)
+        kbuild_fwd_stream_kernel<T, KIND, DP, WC, true><<<grid, 256, smem, st>>>(
+            X, X2e, ls, ls_len, var, diag_add, (T)diag_const, out, ldo, N, N2, D, chunk, sX, sX2e, sLs, sVar, sDiag, sOut, vec_ok);
+    else
+        kbuild_fwd_stream_kernel<T, KIND, DP, WC, false><<<grid, 256, smem, st>>>(
+            X, X2e, ls, ls_len, var, diag_add, (T)diag_const, out, ldo, N, N2, D, chunk, sX, sX2e, sLs, sVar, sDiag, sOut, vec_ok);
+    return after_launch();
+}
+
+template <typename T, int KIND, int DP>
+static int dispatch_fwd_stream_wc(const T* X, const T* X2, const T* ls, int ls_len, const T* var, const T* diag_add,
+                                  double diag_const, T* out, int64_t ldo, int S, int N, int N2, int D, int64_t sX,
+                                  int64_t sX2, int64_t sLs, int64_t sVar, int64_t sDiag, int64_t sOut, cudaStream_t st) {
+#define MXF_KS_ARGS X, X2, ls, ls_len, var, diag_add, diag_const, out, ldo, S, N, N2, D, sX, sX2, sLs, sVar, sDiag, sOut, st
+    if (N2 > 512) return launch_fwd_stream<T, KIND, DP, 8>(MXF_KS_ARGS);
+    if (N2 > 256) return launch_fwd_stream<T, KIND, DP, 4>(MXF_KS_ARGS);
+    if (N2 > 128) return launch_fwd_stream<T, KIND, DP, 2>(MXF_KS_ARGS);
+    return launch_fwd_stream<T, KIND, DP, 1>(MXF_KS_ARGS);
+#undef MXF_KS_ARGS
+}
+
 template <typename T, int KIND>
 static int dispatch_fwd_dc(const T* X, const T* X2, const T* ls, int ls_len, const T* var,
                            const T* diag_add, double diag_const, T* out, int64_t ldo, int S, int N,
                            int N2, int D, int64_t sX, int64_t sX2, int64_t sLs, int64_t sVar,
                            int64_t sDiag, int64_t sOut, cudaStream_t st) {
     constexpr int RM = sizeof(T) == 4 ? 16 : 8;
+    if (N2 >= 32) {
+#define MXF_KS_ARGS X, X2, ls, ls_len, var, diag_add, diag_const, out, ldo, S, N, N2, D, sX, sX2, sLs, sVar, sDiag, sOut, st
+        if (D <= 4) return dispatch_fwd_stream_wc<T, KIND, 4>(MXF_KS_ARGS);
+        if (D <= 8) return dispatch_fwd_stream_wc<T, KIND, 8>(MXF_KS_ARGS);
+        if (D <= 16 && sizeof(T) == 4) return dispatch_fwd_stream_wc<T, KIND, 16>(MXF_KS_ARGS);
+#undef MXF_KS_ARGS
+    }
     if (D <= 4)
         return launch_fwd<T, KIND, 4, RM>(X, X2, ls, ls_len, var, diag_add, diag_const, out, ldo, S, N, N2, D,
                                           sX, sX2, sLs, sVar, sDiag, sOut, st);

@@ -22,7 +22,10 @@ def variables_to_UUID(variables):
 class ObjectiveBlock(object):
     def __init__(self, infr_method, constants, data_def, var_trans, var_ties, excluded, params=None):
         self._infr_method = infr_method
-        self._constants = constants
+        # constants given as arrays live next to the parameters (same device / dtype); shape constants stay ints
+        dev, dt = params.mxnet_context, params.flat.dtype if params.flat is not None else None
+        self._constants = {k: (v.to(device=dev, dtype=dt if v.is_floating_point() and dt is not None else v.dtype)
+                               if isinstance(v, torch.Tensor) else v) for k, v in constants.items()}
         self._data_def = data_def
         self._var_trans = var_trans
         self._var_ties = var_ties
