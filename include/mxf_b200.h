@@ -122,6 +122,16 @@ int mxf_potrf_packed(int dtype, void* A, int64_t lda, int64_t sA, int S, int n, 
 int mxf_trsm_packed(int dtype, int transpose, int n, int nrhs, double alpha, const void* L, int64_t lda, int64_t sA,
                     const void* pack, int64_t sP, void* B, int64_t ldb, int64_t sB, int S, void* stream);
 
+/* When n is a multiple of 2*NB the pack also holds hierarchically built inverses of larger diagonal blocks
+ * ([[Wa,0],[-Wc Lca Wa, Wc]], doubling from NB up to mxf_tri_top_block(dtype, n) <= 512, env MXF_TRI_INV) and their
+ * transposes.  mxf_trsm_packed_oop then solves in n/top block steps of one or two LARGE GEMMs each (the triangular
+ * structure of the inverse blocks is used to skip the zero half of K): X = op(L)^-1 B, out of place; B is scratch.
+ * Returns MXF_ENOTIMPL when the pack has no level above NB (use mxf_trsm_packed). */
+int mxf_tri_top_block(int dtype, int n);
+int mxf_trsm_packed_oop(int dtype, int transpose, int n, int nrhs, const void* L, int64_t lda, int64_t sA,
+                        const void* pack, int64_t sP, void* B, int64_t ldb, int64_t sB, void* X, int64_t ldx, int64_t sX,
+                        int S, void* stream);
+
 /* Cholesky adjoint helper: out = phi(P) + phi(P)^T with phi = lower triangle, i.e. the
  * symmetric matrix whose lower triangle (diagonal included) is copied from P. */
 int mxf_copy_ltu(int dtype, const void* P, int64_t ldp, int64_t sP,

@@ -39,6 +39,8 @@ def _declare(lib):
         'mxf_tri_pack': (i, [i, p, l, l, i, i, p, p]),
         'mxf_potrf_packed': (i, [i, p, l, l, i, i, p, p, p]),
         'mxf_trsm_packed': (i, [i, i, i, i, d, p, l, l, p, l, p, l, l, i, p]),
+        'mxf_tri_top_block': (i, [i, i]),
+        'mxf_trsm_packed_oop': (i, [i, i, i, i, p, l, l, p, l, p, l, l, p, l, l, i, p]),
         'mxf_copy_ltu': (i, [i, p, l, l, p, l, l, i, i, p]),
         'mxf_symmetrize': (i, [i, d, p, l, l, p, l, l, i, i, p]),
         'mxf_tril': (i, [i, i, p, l, l, p, l, l, i, i, p]),

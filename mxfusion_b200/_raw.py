@@ -169,6 +169,21 @@ def trsm_packed_(L, pack, B, transpose=False, alpha=1.0):
     return B
 
 
+def trsm_solve(L, pack, B, transpose=False):
+    """X = op(L)^-1 B with the factor's pack.  Uses the large-block out-of-place chain when the pack has one (B is then
+    scratch and a NEW tensor is returned), else the in-place NB-block chain (returns B)."""
+    require_cuda(L, pack, B)
+    S, n, nrhs = B.shape
+    code = dtype_code(B)
+    if nrhs > 8 and lib().mxf_tri_top_block(code, n) > lib().mxf_tri_block(code):
+        X = torch.empty_like(B)
+        check(lib().mxf_trsm_packed_oop(code, int(transpose), n, nrhs, ptr(L), L.stride(1), _bstride(L, S), ptr(pack),
+                                        pack.stride(0) if pack.shape[0] > 1 else 0, ptr(B), B.stride(1), B.stride(0),
+                                        ptr(X), X.stride(1), X.stride(0), S, stream_ptr()), 'mxf_trsm_packed_oop')
+        return X
+    return trsm_packed_(L, pack, B, transpose=transpose)
+
+
 def _sq(fn, name, A, *extra, out=None):
     require_cuda(A, out)
     S, n, _ = A.shape

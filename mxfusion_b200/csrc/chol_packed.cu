@@ -15,6 +15,7 @@
 // transposed solve).  Inverting only the diagonal blocks (not L) keeps the solve backward-stable in the blocks'
 // condition numbers, the standard GPU trsm formulation.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 extern "C" int mxf_transpose(int dtype, const void* A, int64_t lda, int64_t sA, void* out, int64_t ldo, int64_t sO,
@@ -30,10 +31,20 @@ int gemm_any(int transA, int transB, int m, int n, int k, double alpha, const T*
 template <typename T> struct TriBlock { static constexpr int NB = 128; };
 template <> struct TriBlock<double> { static constexpr int NB = 64; };
 
+// Largest inverse block built hierarchically from the NB blocks (power-of-two multiple of NB dividing n).
+inline int tri_inv_max() {
+    static int v = [] {
+        const char* e = getenv("MXF_TRI_INV");
+        int x = e ? atoi(e) : 512;
+        return x < 64 ? 64 : x;
+    }();
+    return v;
+}
+
 template <typename T>
 struct PackLayout {
-    int n, nblk, ldt;
-    int64_t dinv, dinvT, lt, total;       // element offsets within one sample's pack
+    int n, nblk, ldt, top, nlvl;
+    int64_t dinv, dinvT, lt, lvl[8], topT, scratch, total;       // element offsets within one sample's pack
     explicit PackLayout(int n_) : n(n_) {
         constexpr int NB = TriBlock<T>::NB;
         nblk = (n + NB - 1) / NB;
@@ -41,7 +52,26 @@ struct PackLayout {
         dinv = 0;
         dinvT = (int64_t)nblk * NB * NB;
         lt = 2 * dinvT;
-        total = (lt + (int64_t)n * ldt + 3) & ~(int64_t)3;
+        int64_t off = (lt + (int64_t)n * ldt + 3) & ~(int64_t)3;
+        top = NB;
+        nlvl = 1;
+        lvl[0] = dinv;
+        topT = dinvT;
+        scratch = 0;
+        if (n % NB == 0) {
+            while (top * 2 <= tri_inv_max() && n % (top * 2) == 0 && nlvl < 8) {
+                top *= 2;
+                lvl[nlvl++] = off;
+                off += (int64_t)n * top;
+            }
+            if (top > NB) {
+                topT = off;
+                off += (int64_t)n * top;
+                scratch = off;
+                off += (int64_t)n * top / 2;
+            }
+        }
+        total = (off + 3) & ~(int64_t)3;
     }
 };
 
@@ -367,6 +397,10 @@ template <typename T>
 static int dtype_of() { return sizeof(T) == 4 ? MXF_F32 : MXF_F64; }
 
 template <typename T>
+static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int n, T* pack, const PackLayout<T>& pl,
+                                cudaStream_t st);
+
+template <typename T>
 static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* info, T* pack, cudaStream_t st) {
     constexpr int NB = TriBlock<T>::NB;
     const PackLayout<T> pl(n);
@@ -399,6 +433,8 @@ static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* i
     }
     int rc = mxf_transpose(dtype_of<T>(), A, lda, sA, pack + pl.lt, pl.ldt, pl.total, S, n, n, st);
     if (rc != MXF_OK) return rc;
+    rc = build_inverse_levels<T>(A, lda, sA, S, n, pack, pl, st);
+    if (rc != MXF_OK) return rc;
     return after_launch(launches);
 }
 
@@ -413,7 +449,112 @@ static int tri_pack_impl(const T* L, int64_t lda, int64_t sA, int S, int n, T* p
     k<<<grid, PD_THREADS, smem, st>>>(L, lda, sA, n, pack, pl.total, pl.dinv, pl.dinvT);
     int rc = mxf_transpose(dtype_of<T>(), L, lda, sA, pack + pl.lt, pl.ldt, pl.total, S, n, n, st);
     if (rc != MXF_OK) return rc;
+    rc = build_inverse_levels<T>(L, lda, sA, S, n, pack, pl, st);
+    if (rc != MXF_OK) return rc;
     return after_launch(1);
+}
+
+// ---- hierarchical inverse blocks -------------------------------------------------------------------------------
+// [[Wa, 0], [-Wc Lca Wa, Wc]] from the inverses Wa, Wc of two consecutive b x b diagonal blocks: copies + zero fill
+// (the product block is written by the GEMMs).
+template <typename T>
+__global__ void __launch_bounds__(256)
+inv_level_assemble_kernel(const T* __restrict__ src, T* __restrict__ dst, int b) {
+    const int q = blockIdx.y;
+    const T* wa = src + (int64_t)(2 * q) * b * b;
+    const T* wc = wa + (int64_t)b * b;
+    T* d = dst + (int64_t)q * 4 * b * b;
+    const int64_t tot = (int64_t)b * b;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / b), c = (int)(e - (int64_t)r * b);
+        d[(int64_t)r * 2 * b + c] = wa[e];
+        d[(int64_t)r * 2 * b + b + c] = T(0);
+        d[(int64_t)(b + r) * 2 * b + b + c] = wc[e];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_blocks_kernel(const T* __restrict__ src, T* __restrict__ dst, int b) {
+    __shared__ T tile[32][33];
+    const T* sp = src + (int64_t)blockIdx.z * b * b;
+    T* dp = dst + (int64_t)blockIdx.z * b * b;
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) tile[r][threadIdx.x] = sp[(int64_t)(by + r) * b + bx + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) dp[(int64_t)(bx + r) * b + by + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+template <typename T>
+static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int n, T* pack, const PackLayout<T>& pl,
+                                cudaStream_t st) {
+    constexpr int NB = TriBlock<T>::NB;
+    if (pl.top == NB) return MXF_OK;
+    int launches = 0;
+    for (int s = 0; s < S; ++s) {
+        const T* Ls = L + (int64_t)s * sA;
+        T* pk = pack + (int64_t)s * pl.total;
+        int b = NB;
+        for (int j = 0; j + 1 < pl.nlvl; ++j, b *= 2) {
+            const T* src = pk + pl.lvl[j];
+            T* dst = pk + pl.lvl[j + 1];
+            T* t1 = pk + pl.scratch;
+            const int np = n / (2 * b);
+            // T1_q = L[(2q+1)b.., 2qb..] * W_{2q}
+            int rc = gemm_any<T>(0, 0, b, b, b, 1.0, Ls + (int64_t)b * lda, lda, (int64_t)2 * b * lda + 2 * b, src, b,
+                                 (int64_t)2 * b * b, 0.0, t1, b, (int64_t)b * b, np, 0, st, 0);
+            if (rc != MXF_OK) return rc;
+            // dst_q[b.., 0..b) = -W_{2q+1} * T1_q      (W lower triangular)
+            rc = gemm_any<T>(0, 0, b, b, b, -1.0, src + (int64_t)b * b, b, (int64_t)2 * b * b, t1, b, (int64_t)b * b, 0.0,
+                             dst + (int64_t)b * 2 * b, 2 * b, (int64_t)4 * b * b, np, 2, st, 0);
+            if (rc != MXF_OK) return rc;
+            dim3 g(std::min(64, cdiv((int64_t)b * b, 256)), np);
+            inv_level_assemble_kernel<T><<<g, 256, 0, st>>>(src, dst, b);
+            ++launches;
+        }
+        dim3 gt(pl.top / 32, pl.top / 32, n / pl.top);
+        transpose_blocks_kernel<T><<<gt, dim3(32, 8), 0, st>>>(pk + pl.lvl[pl.nlvl - 1], pk + pl.topT, pl.top);
+        ++launches;
+    }
+    return after_launch(launches);
+}
+
+// Out-of-place solve with the top-level inverse blocks: X = op(L)^-1 B in (n / top) block steps, each one or two large
+// GEMMs.  B is used as scratch (its later block rows receive the updates); requires pl.top > NB.
+template <typename T>
+static int trsm_packed_oop_impl(int transpose, int n, int nrhs, const T* L, int64_t lda, int64_t sA, const T* pack,
+                                int64_t sP, T* B, int64_t ldb, int64_t sB, T* X, int64_t ldx, int64_t sX, int S,
+                                cudaStream_t st) {
+    const PackLayout<T> pl(n);
+    const int top = pl.top;
+    if (!transpose) {
+        for (int k0 = 0; k0 < n; k0 += top) {
+            const T* Wk = pack + pl.lvl[pl.nlvl - 1] + (int64_t)(k0 / top) * top * top;
+            int rc = gemm_any<T>(0, 0, top, nrhs, top, 1.0, Wk, top, sP, B + (int64_t)k0 * ldb, ldb, sB, 0.0,
+                                 X + (int64_t)k0 * ldx, ldx, sX, S, 2, st, 0);
+            if (rc != MXF_OK) return rc;
+            const int below = n - k0 - top;
+            if (below > 0) {
+                rc = gemm_any<T>(0, 0, below, nrhs, top, -1.0, L + (int64_t)(k0 + top) * lda + k0, lda, sA,
+                                 X + (int64_t)k0 * ldx, ldx, sX, 1.0, B + (int64_t)(k0 + top) * ldb, ldb, sB, S, 0, st, 0);
+                if (rc != MXF_OK) return rc;
+            }
+        }
+    } else {
+        const T* LT = pack + pl.lt;
+        for (int k0 = n - top; k0 >= 0; k0 -= top) {
+            const T* Wk = pack + pl.topT + (int64_t)(k0 / top) * top * top;
+            int rc = gemm_any<T>(0, 0, top, nrhs, top, 1.0, Wk, top, sP, B + (int64_t)k0 * ldb, ldb, sB, 0.0,
+                                 X + (int64_t)k0 * ldx, ldx, sX, S, 4, st, 0);
+            if (rc != MXF_OK) return rc;
+            if (k0 > 0) {
+                rc = gemm_any<T>(0, 0, k0, nrhs, top, -1.0, LT + k0, pl.ldt, sP, X + (int64_t)k0 * ldx, ldx, sX, 1.0, B, ldb,
+                                 sB, S, 0, st, 0);
+                if (rc != MXF_OK) return rc;
+            }
+        }
+    }
+    return MXF_OK;
 }
 
 template <typename T>
@@ -593,4 +734,19 @@ extern "C" int mxf_trsm_packed(int dtype, int transpose, int n, int nrhs, double
     if (S > 65535) return MXF_ENOTIMPL;
     MXF_DISPATCH_DTYPE(dtype, return trsm_packed_impl<T>(transpose, n, nrhs, alpha, (const T*)L, lda, sA, (const T*)pack,
                                                         sP, (T*)B, ldb, sB, S, (cudaStream_t)stream));
+}
+
+extern "C" int mxf_tri_top_block(int dtype, int n) {
+    if (n <= 0) return 0;
+    return dtype == MXF_F64 ? PackLayout<double>(n).top : PackLayout<float>(n).top;
+}
+
+extern "C" int mxf_trsm_packed_oop(int dtype, int transpose, int n, int nrhs, const void* L, int64_t lda, int64_t sA,
+                                   const void* pack, int64_t sP, void* B, int64_t ldb, int64_t sB, void* X, int64_t ldx,
+                                   int64_t sX, int S, void* stream) {
+    if (!L || !pack || !B || !X || n <= 0 || nrhs <= 0 || S <= 0 || lda < n || ldb < nrhs || ldx < nrhs) return MXF_EINVAL;
+    if (S > 65535) return MXF_ENOTIMPL;
+    if (mxf_tri_top_block(dtype, n) <= mxf_tri_block(dtype)) return MXF_ENOTIMPL;
+    MXF_DISPATCH_DTYPE(dtype, return trsm_packed_oop_impl<T>(transpose, n, nrhs, (const T*)L, lda, sA, (const T*)pack, sP,
+                                                            (T*)B, ldb, sB, (T*)X, ldx, sX, S, (cudaStream_t)stream));
 }

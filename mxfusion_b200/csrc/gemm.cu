@@ -77,7 +77,7 @@ gemm_kernel(int transA, int transB, int m, int n, int k, T alpha, const T* __res
     __shared__ __align__(16) T Bs[2][BK * Cfg::LDS_B];
 
     const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
-    if (tri && j0 > i0 + BM - 1) return;
+    if ((tri & 1) && j0 > i0 + BM - 1) return;      // bits 2/4 (triangular A) are hints: the full product is the same
     const int s = blockIdx.z;
     A += (int64_t)s * sA;
     B += (int64_t)s * sB;
@@ -299,12 +299,12 @@ int gemm_any(int transA, int transB, int m, int n, int k, double alpha, const T*
              const T* B, int64_t ldb, int64_t sB, double beta, T* C, int64_t ldc, int64_t sC, int S, int tri,
              cudaStream_t st, int wide) {
     if (m == 0 || n == 0 || S == 0) return MXF_OK;
-    if (k <= 8 && !tri && (int64_t)m * n >= 4096) {
+    if (k <= 8 && !(tri & 1) && (int64_t)m * n >= 4096) {
         dim3 grid(cdiv(n, 256), std::min(m, 2048), S);
         gemm_rank_k_kernel<T><<<grid, 256, 0, st>>>(transA, transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);
         return after_launch();
     }
-    if (n <= 8 && k >= 32 && !tri && (const void*)C != (const void*)A && (const void*)C != (const void*)B)
+    if (n <= 8 && k >= 32 && !(tri & 1) && (const void*)C != (const void*)A && (const void*)C != (const void*)B)
         return gemm_skinny<T>(transA, transB, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, S, st);
     if constexpr (sizeof(T) == 4) {
         if ((int64_t)m * n >= 64 * 64 && k >= 16) {

@@ -121,7 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int tri, int batchA, int batchB) {
     using Cfg = TcCfg<BN>;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-    if (tri && n0 > m0 + TC_BM - 1) return;          // tile strictly above the diagonal: nothing to do
+    if ((tri & 1) && n0 > m0 + TC_BM - 1) return;    // tile strictly above the diagonal: nothing to do
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -136,7 +136,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (3 * Cfg::STAGES) + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = (k + TC_BK - 1) / TC_BK;
+    // K range of this tile: all of K, or -- when A is known to be lower (tri & 2) / upper (tri & 4) triangular, as the
+    // inverted diagonal blocks of a Cholesky factor are -- only the part where this row block of A is non-zero
+    const int kb_begin = (tri & 4) ? m0 / TC_BK : 0;
+    const int k_end = (tri & 2) ? min(k, m0 + TC_BM) : k;
+    const int kb_end = (k_end + TC_BK - 1) / TC_BK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -162,9 +166,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             const int zA = batchA ? (int)blockIdx.z : 0, zB = batchB ? (int)blockIdx.z : 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+            for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+                const int s = it % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
                 mbar_wait(bar_empty(s), ph ^ 1u);
                 const uint32_t st = base + s * Cfg::STAGE_BYTES;
                 mbar_expect_tx(bar_full(s), Cfg::A_BYTES + Cfg::B_BYTES);
@@ -185,9 +189,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // a_major [15]=0 (K), b_major [16], N>>3 [17,23), M>>4 [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+            for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+                const int s = it % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
                 mbar_wait(bar_ready(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = base + s * Cfg::STAGE_BYTES, b_hi = a_hi + Cfg::A_BYTES;
@@ -207,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         dbh = smem_desc(b_hi + kk * 1024, TC_BK * 128, 512, 1);
                         dbl = smem_desc(b_lo + kk * 1024, TC_BK * 128, 512, 1);
                     }
-                    umma_tf32(tmem_d, dal, dbh, idesc, (kb | kk) != 0);     // small terms first
+                    umma_tf32(tmem_d, dal, dbh, idesc, (it | kk) != 0);     // small terms first
                     umma_tf32(tmem_d, dah, dbl, idesc, 1);
                     umma_tf32(tmem_d, dah, dbh, idesc, 1);
                 }
@@ -219,9 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ------------------------------------------------------------------ converters, then epilogue
         const int t = threadIdx.x - 64;          // 0..127
         constexpr int VEC = (Cfg::A_BYTES + Cfg::B_BYTES) / 16;     // 16-byte vectors per stage (hi region)
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % Cfg::STAGES;
-            const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+        for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+            const int s = it % Cfg::STAGES;
+            const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
             mbar_wait(bar_full(s), ph);
             float4* hi = reinterpret_cast<float4*>(base_ptr + s * Cfg::STAGE_BYTES);
             float4* lo = reinterpret_cast<float4*>(base_ptr + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + Cfg::B_BYTES);

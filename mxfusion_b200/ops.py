@@ -96,9 +96,8 @@ class _Potrf(torch.autograd.Function):
         L, pack = ctx.saved_tensors
         G = R.gemm(L, R.tril(Lbar), transA=True)
         Psym = R.copy_ltu(G)
-        R.trsm_packed_(L, pack, Psym, transpose=True)
-        Y = R.transpose(Psym)
-        R.trsm_packed_(L, pack, Y, transpose=True)
+        Psym = R.trsm_solve(L, pack, Psym, transpose=True)
+        Y = R.trsm_solve(L, pack, R.transpose(Psym), transpose=True)
         return R.symmetrize(Y, 0.25)      # 1/2 * (Y + Y^T)/2: symmetric by construction, cleans rounding
 
 
@@ -267,8 +266,7 @@ class _SVGPLogPdf(torch.autograd.Function):
         Kuu = R.kbuild_fwd(kind, Z, None, ls, kvar, diag_const=jitter)
         # all right-hand sides of the solves with L ride in ONE buffer [Kuf | Ls | mu]: one GEMM chain, not three
         RH = torch.empty((S, M, B + M + PP), dtype=dt, device=dev)
-        A, C, mt = RH[:, :, :B], RH[:, :, B:B + M], RH[:, :, B + M:B + M + P]
-        R.kbuild_fwd(kind, Z, X, ls, kvar, out=A)               # Kuf (:73), overwritten below by L^-1 Kuf
+        R.kbuild_fwd(kind, Z, X, ls, kvar, out=RH[:, :, :B])    # Kuf (:73)
         Sm = R.gemm(W, W, transB=True, tri=True)                # :76 syrk (lower tiles) ...
         R.add_diag_(Sm, dvec)                                   # ... + make_diagonal
         pk, pks = R.new_pack(Kuu), R.new_pack(Sm)
@@ -298,11 +296,12 @@ class _SVGPLogPdf(torch.autograd.Function):
             Ls_copy.copy_(Sm)
             _sinv_chain(Sm, pks, eyeS, LsT, Sinv_l, Sinv)
         L, Ls = Kuu, Sm
-        C.copy_(Ls_copy)
-        mt.copy_(mu)
+        RH[:, :, B:B + M].copy_(Ls_copy)
+        RH[:, :, B + M:B + M + P].copy_(mu)
         if PP > P:
             RH[:, :, B + M + P:].zero_()
-        R.trsm_packed_(L, pk, RH)                               # :85-87  C = L^-1 Ls, mt = L^-1 mu, A = L^-1 Kuf
+        RH = R.trsm_solve(L, pk, RH)                            # :85-87  A = L^-1 Kuf, C = L^-1 Ls, mt = L^-1 mu
+        A, C, mt = RH[:, :, :B], RH[:, :, B:B + M], RH[:, :, B + M:B + M + P]
         Phi = R.copy_ltu(R.gemm(A, A, transB=True, tri=True))
         T = R.copy_ltu(R.gemm(C, C, transB=True, tri=True))
         G1 = R.gemm(A, mt, transA=True)                         # :89  (S,B,P)
@@ -346,7 +345,7 @@ class _SVGPLogPdf(torch.autograd.Function):
         E4[:, :, 3 * M:3 * M + P].copy_(mt)
         if PP > P:
             E4[:, :, 3 * M + P:].zero_()
-        R.trsm_packed_(L, pk, E4, transpose=True)
+        E4 = R.trsm_solve(L, pk, E4, transpose=True)
         # Kuf adjoint: (L^-T E_R) A + g s beta (L^-T mt) Y^T
         dKuf = R.gemm(E4[:, :, 2 * M:3 * M], A)
         w = E4[:, :, 3 * M:3 * M + P]
@@ -358,7 +357,7 @@ class _SVGPLogPdf(torch.autograd.Function):
         F2[:, :, 2 * M:2 * M + P].copy_(R.axpby_dev(gsb, v, -g, mt))
         if PP > P:
             F2[:, :, 2 * M + P:].zero_()
-        R.trsm_packed_(L, pk, F2, transpose=True)
+        F2 = R.trsm_solve(L, pk, F2, transpose=True)
         dKuu = F2[:, :, :M]
         dmu = F2[:, :, 2 * M:2 * M + P].contiguous()
         dZ1, dX, dls1, dvar1 = R.kbuild_bwd(ctx.kind, Z, X, ls, kvar, dKuf, need_dX=True, need_dX2=need[3])
@@ -379,9 +378,9 @@ class _SVGPLogPdf(torch.autograd.Function):
 def _sinv_chain(Ls, pks, eye, LsT, Sinv_l, Sinv):
     """S^-1 = Ls^-T Ls^-1: one solve with the identity, one lower-tiles product, mirror.  Writes into preallocated
     buffers (they are created on the main stream and only filled on the side stream)."""
-    R.trsm_packed_(Ls, pks, eye)                                # eye <- Ls^-1
-    R.transpose(eye, out=LsT)
-    R.gemm(LsT, eye, beta=0.0, C=Sinv_l, tri=True)
+    Li = R.trsm_solve(Ls, pks, eye)                             # Ls^-1
+    R.transpose(Li, out=LsT)
+    R.gemm(LsT, Li, beta=0.0, C=Sinv_l, tri=True)
     R.copy_ltu(Sinv_l, out=Sinv)
 
 
@@ -444,7 +443,7 @@ class _GPLogPdf(torch.autograd.Function):
         # Kbar = g (1/2 a a^T - P/2 K^-1),  a = K^-1 Y = L^-T LinvY ;  Ybar = -g a
         a = R.trsm_packed_(L, pk, LinvY.clone(), transpose=True)
         eye = torch.eye(N, dtype=X.dtype, device=X.device).unsqueeze(0).expand(S, N, N).contiguous()
-        Kinv = R.trsm_packed_(L, pk, R.trsm_packed_(L, pk, eye), transpose=True)
+        Kinv = R.trsm_solve(L, pk, R.trsm_solve(L, pk, eye), transpose=True)
         aaT = R.gemm(a, a, transB=True)
         Kbar = R.axpby_dev(0.5 * g, aaT, (-0.5 * P) * g, Kinv)
         dX, _, dls, dvar = R.kbuild_bwd(ctx.kind, X, None, ls, kvar, Kbar)

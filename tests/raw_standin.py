@@ -84,6 +84,10 @@ def trsm_packed_(L, pack, B, transpose=False, alpha=1.0):
     return trsm_(L, B, transpose=transpose, alpha=alpha)
 
 
+def trsm_solve(L, pack, B, transpose=False):
+    return trsm_(L, B.clone(), transpose=transpose)
+
+
 def trsm_(L, B, transpose=False, alpha=1.0):
     Lt = torch.tril(L)
     if transpose:

@@ -365,3 +365,39 @@ def test_trsm_packed_shared_factor(cuda):
     Lt, Bt = T(Lm, cuda, torch.float32), T(B, cuda, torch.float32)
     _raw.trsm_packed_(Lt, _raw.tri_pack(Lt), Bt)
     np.testing.assert_allclose(Bt.cpu().numpy(), want, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('transpose', [False, True])
+@pytest.mark.parametrize('n,nrhs', [(256, 100), (512, 2048), (768, 260), (1024, 1024), (1024, 5124), (2048, 512), (300, 64)])
+def test_trsm_solve_large_blocks(cuda, prec, transpose, n, nrhs):
+    """Out-of-place solve through the hierarchically built inverse blocks (256 / 512): a few large GEMMs."""
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(17)
+    S = 2 if n <= 1024 else 1
+    Lm = np.tril(rng.randn(S, n, n)) * (0.5 / np.sqrt(n)) + 2.0 * np.eye(n)[None]
+    B = rng.randn(S, n, nrhs)
+    want = ol.trsm(Lm, B, transpose=transpose)
+    Lt, Bt = T(Lm, cuda, tdt), T(B, cuda, tdt)
+    X = _raw.trsm_solve(Lt, _raw.tri_pack(Lt), Bt, transpose=transpose)
+    if prec == 'f32':
+        np.testing.assert_allclose(X.cpu().numpy(), want, rtol=5e-5, atol=5e-5)
+    else:
+        np.testing.assert_allclose(X.cpu().numpy(), want, rtol=1e-9, atol=1e-10)
+
+
+def test_trsm_solve_after_potrf_matches_lapack(cuda):
+    """potrf_packed's own pack (built during the factorisation) drives the large-block solve."""
+    from mxfusion_b200 import _raw
+    rng = np.random.RandomState(18)
+    n = 1024
+    W = rng.randn(1, n, n)
+    A = W @ np.swapaxes(W, -1, -2) / n + np.eye(n)[None]
+    B = rng.randn(1, n, 300)
+    Lw = ol.potrf(A)
+    L, info, pack = _raw.potrf_packed_(T(A, cuda, torch.float32))
+    X = _raw.trsm_solve(L, pack, T(B, cuda, torch.float32))
+    np.testing.assert_allclose(X.cpu().numpy(), ol.trsm(Lw, B), rtol=2e-4, atol=2e-4)
+    Xt = _raw.trsm_solve(L, pack, T(B, cuda, torch.float32), transpose=True)
+    np.testing.assert_allclose(Xt.cpu().numpy(), ol.trsm(Lw, B, transpose=True), rtol=2e-4, atol=2e-4)
