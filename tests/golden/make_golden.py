@@ -35,6 +35,7 @@ from mxfusion.components.distributions.gp.kernels import RBF, Matern12, Matern32
 from mxfusion.modules.gp_modules import GPRegression, SVGPRegression  # noqa: E402
 from mxfusion.inference import (Inference, GradBasedInference, MAP, BatchInferenceLoop, MinibatchInferenceLoop,  # noqa: E402
                                 StochasticVariationalInference, create_Gaussian_meanfield)
+from mxfusion.inference import TransferInference, ModulePredictionAlgorithm  # noqa: E402
 from mxfusion.util.testutils import MockMXNetRandomGenerator  # noqa: E402
 
 config.DEFAULT_DTYPE = 'float64'
@@ -222,6 +223,53 @@ def golden_svgp_minibatch():
          final_full_data_loss_at_batch_scaling=loss_full.asnumpy())
 
 
+# ------------------------------------------------------------------------------------------------ prediction
+def golden_predict():
+    """svgpregression_test.py:171-242 / gpregression_test.py:169-226: mean / variance prediction in the four modes."""
+    out = {}
+    np.random.seed(0)
+    N, M, Din, P = 10, 3, 3, 1
+    X, Y, Z = np.random.rand(N, Din), np.random.rand(N, P), np.random.rand(M, Din)
+    qU_mean, qU_cov_W, qU_cov_diag = np.random.rand(M, P), np.random.rand(M, M), np.random.rand(M,)
+    noise_var, lengthscale, variance = np.random.rand(1), np.random.rand(Din), np.random.rand(1)
+    Xt = np.random.rand(5, Din)
+    out.update(X=X, Y=Y, Z=Z, qU_mean=qU_mean, qU_cov_W=qU_cov_W, qU_cov_diag=qU_cov_diag, noise_var=noise_var,
+               lengthscale=lengthscale, variance=variance, Xt=Xt)
+    for module in ('svgp', 'gp'):
+        m = Model()
+        m.N = Variable()
+        m.X = Variable(shape=(m.N, Din))
+        m.noise_var = Variable(transformation=PositiveTransformation(), initial_value=nd(noise_var))
+        kernel = RBF(input_dim=Din, ARD=True, variance=nd(variance), lengthscale=nd(lengthscale), dtype=DT)
+        if module == 'svgp':
+            m.Z = Variable(shape=(M, Din), initial_value=nd(Z))
+            m.Y = SVGPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                                 shape=(m.N, P), dtype=DT)
+            m.Y.factor.svgp_log_pdf.jitter = 1e-8
+        else:
+            m.Y = GPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, shape=(m.N, P), dtype=DT)
+        gp = m.Y.factor
+        infr = Inference(MAP(model=m, observed=[m.X, m.Y]), dtype=DT)
+        infr.initialize(X=X.shape, Y=Y.shape)
+        if module == 'svgp':
+            post = gp._extra_graphs[0]
+            infr.params[post.qU_mean] = nd(qU_mean)
+            infr.params[post.qU_cov_W] = nd(qU_cov_W)
+            infr.params[post.qU_cov_diag] = nd(qU_cov_diag)
+        infr.run(X=nd(X), Y=nd(Y))
+        alg = gp.svgp_predict if module == 'svgp' else gp.gp_predict
+        for noise_free in (True, False):
+            for diag in (True, False):
+                alg.noise_free, alg.diagonal_variance = noise_free, diag
+                infr2 = TransferInference(ModulePredictionAlgorithm(m, observed=[m.X], target_variables=[m.Y]),
+                                          infr_params=infr.params, dtype=np.float64)
+                res = infr2.run(X=nd(Xt))[0]
+                tag = '%s_nf%d_diag%d' % (module, int(noise_free), int(diag))
+                out[tag + '_mean'] = res[0].asnumpy()
+                out[tag + '_var'] = res[1].asnumpy()
+    save('predict', **out)
+
+
 # ------------------------------------------------------------------------------------------------ Normal
 def golden_normal():
     rng = np.random.RandomState(0)
@@ -278,3 +326,4 @@ if __name__ == '__main__':
     golden_svgp_minibatch()
     golden_normal()
     golden_svi()
+    golden_predict()

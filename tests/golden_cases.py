@@ -138,3 +138,46 @@ def run_svi_toy(mf, g, device):
     grads = dict(q_mean=param_grad(infr, q.mu.factor.mean), q_var=param_grad(infr, q.mu.factor.variance),
                  s2=param_grad(infr, m.s2))
     return float(loss), grads
+
+
+def run_predict(mf, g, module, device):
+    """Rebuilds the prediction scenario of predict.npz; returns {(noise_free, diag): (mean, var)}."""
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.components.distributions.gp.kernels import RBF
+    from mxfusion_b200.modules.gp_modules import SVGPRegression, GPRegression
+    from mxfusion_b200.inference import Inference, MAP, TransferInference, ModulePredictionAlgorithm
+    X, Y, Z, Xt = g['X'], g['Y'], g['Z'], g['Xt']
+    N, Din = X.shape
+    M, P = Z.shape[0], Y.shape[1]
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, Din))
+    m.noise_var = mf.Variable(transformation=PositiveTransformation(), initial_value=g['noise_var'])
+    kernel = RBF(input_dim=Din, ARD=True, variance=g['variance'], lengthscale=g['lengthscale'])
+    if module == 'svgp':
+        m.Z = mf.Variable(shape=(M, Din), initial_value=Z)
+        m.Y = SVGPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                             shape=(m.N, P))
+        m.Y.factor.svgp_log_pdf.jitter = 1e-8
+    else:
+        m.Y = GPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, shape=(m.N, P))
+    gp = m.Y.factor
+    infr = Inference(MAP(model=m, observed=[m.X, m.Y]), context=device)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    if module == 'svgp':
+        post = gp._extra_graphs[0]
+        infr.params[post.qU_mean] = g['qU_mean']
+        infr.params[post.qU_cov_W] = g['qU_cov_W']
+        infr.params[post.qU_cov_diag] = g['qU_cov_diag']
+    infr.run(X=X, Y=Y)
+    alg = gp.svgp_predict if module == 'svgp' else gp.gp_predict
+    out = {}
+    for noise_free in (True, False):
+        for diag in (True, False):
+            alg.noise_free, alg.diagonal_variance = noise_free, diag
+            infr2 = TransferInference(ModulePredictionAlgorithm(m, observed=[m.X], target_variables=[m.Y]),
+                                      infr_params=infr.params, context=device)
+            with torch.no_grad():
+                res = infr2.run(X=Xt)[0]
+            out[(noise_free, diag)] = (res[0].cpu().numpy(), res[1].cpu().numpy())
+    return out

@@ -147,3 +147,34 @@ def test_product_meanfield_svi_matches_reference(mf):
     np.testing.assert_allclose(loss, float(g['loss']), rtol=1e-10)
     for k, v in grads.items():
         np.testing.assert_allclose(v, g['grad_' + k], rtol=1e-8, atol=1e-10, err_msg=k)
+
+
+def test_oracle_prediction_matches_reference():
+    g = gc.load('predict')
+    a = lambda k: g[k][None]
+    for nf in (True, False):
+        for dg in (True, False):
+            mu, var = osvgp.svgp_predict(0, a('Xt'), a('Z'), a('noise_var'), a('qU_mean'), a('qU_cov_W'), a('qU_cov_diag'),
+                                         a('lengthscale'), a('variance'), jitter=0.0, noise_free=nf, diagonal_variance=dg)   # predict's own jitter
+            t = 'svgp_nf%d_diag%d' % (int(nf), int(dg))
+            np.testing.assert_allclose(mu, g[t + '_mean'], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(var, g[t + '_var'], rtol=1e-8, atol=1e-11)
+    _, L, LinvY = ogp.gp_log_pdf(0, a('X'), a('Y'), a('noise_var'), a('lengthscale'), a('variance'))
+    for nf in (True, False):
+        for dg in (True, False):
+            mu, var = ogp.gp_predict(0, a('Xt'), a('X'), L, LinvY, a('noise_var'), a('lengthscale'), a('variance'),
+                                     noise_free=nf, diagonal_variance=dg)
+            t = 'gp_nf%d_diag%d' % (int(nf), int(dg))
+            np.testing.assert_allclose(mu, g[t + '_mean'], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(var, g[t + '_var'], rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize('module', ['svgp', 'gp'])
+def test_product_prediction_matches_reference(mf, module):
+    """TransferInference + ModulePredictionAlgorithm (the step after training in every notebook), four modes."""
+    g = gc.load('predict')
+    got = gc.run_predict(mf, g, module, torch.device('cpu'))
+    for (nf, dg), (mu, var) in got.items():
+        t = '%s_nf%d_diag%d' % (module, int(nf), int(dg))
+        np.testing.assert_allclose(mu, g[t + '_mean'], rtol=1e-9, atol=1e-12, err_msg=t)
+        np.testing.assert_allclose(var.reshape(g[t + '_var'].shape), g[t + '_var'], rtol=1e-8, atol=1e-11, err_msg=t)
