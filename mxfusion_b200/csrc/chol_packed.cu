@@ -75,7 +75,7 @@ struct PackLayout {
     }
 };
 
-constexpr int PD_THREADS = 256;
+constexpr int PD_THREADS = 512;
 __device__ long long* g_prof = nullptr;          // debug: per-phase clock64 stamps of potrf_diag_kernel (thread 0)
 #define PD_STAMP(i) do { if (g_prof && threadIdx.x == 0 && blockIdx.x == 0) g_prof[i] = clock64(); } while (0)
 
@@ -157,9 +157,11 @@ __device__ __forceinline__ void inverse_offdiag(const T* D, T* W, T* Tmp) {
     constexpr int LD = NB + 1;
     constexpr int NS = NB / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = 4 * warp;                                  // 8 warps x 4 rows = 32 rows of the block row
+    const int nwarps = blockDim.x >> 5;
     for (int bi = 1; bi < NS; ++bi) {
-        for (int cg = 0; cg < bi; ++cg) {
+        // work items: (row group of 4 rows) x (column group of 32 columns), spread over the warps
+        for (int item = warp; item < 8 * bi; item += nwarps) {
+            const int i0 = 4 * (item & 7), cg = item >> 3;
             T acc[4] = {T(0), T(0), T(0), T(0)};
             const int col = 32 * cg + lane;
 #pragma unroll 8
@@ -172,7 +174,8 @@ __device__ __forceinline__ void inverse_offdiag(const T* D, T* W, T* Tmp) {
             for (int a = 0; a < 4; ++a) Tmp[(i0 + a) * LD + col] = acc[a];
         }
         __syncthreads();
-        for (int cg = 0; cg < bi; ++cg) {
+        for (int item = warp; item < 8 * bi; item += nwarps) {
+            const int i0 = 4 * (item & 7), cg = item >> 3;
             T acc[4] = {T(0), T(0), T(0), T(0)};
             const int col = 32 * cg + lane;
 #pragma unroll 8
@@ -204,11 +207,13 @@ potrf_diag_kernel(T* __restrict__ A, int64_t lda, int64_t sA, int n, int k0, int
     Pt = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(Pt) + 31) & ~(uintptr_t)31);
     __shared__ int bad_s;
 
+    pdl_launch_dependents();
     const int s = blockIdx.x;
     T* As = A + (int64_t)s * sA;
     const int nbk = min(NB, n - k0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) bad_s = 0;
+    pdl_wait();
 
 #pragma unroll 8
     for (int e = tid; e < NB * NB; e += PD_THREADS) {
@@ -338,6 +343,8 @@ static size_t diag_smem() {
 
 template <typename T>
 __global__ void zero_upper_kernel(T* __restrict__ A, int64_t lda, int64_t sA, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int s = blockIdx.z, r = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n && c > r) A[(int64_t)s * sA + (int64_t)r * lda + c] = T(0);
@@ -411,7 +418,9 @@ static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* i
     if (info) { zero_i32_kernel<T><<<cdiv(S, 128), 128, 0, st>>>(info, S); ++launches; }
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int nbk = std::min(NB, n - k0);
-        k<<<S, PD_THREADS, smem, st>>>(A, lda, sA, n, k0, info, pack, pl.total, pl.dinv, pl.dinvT);
+        cudaError_t le = launch_pdl(k, dim3(S), dim3(PD_THREADS), smem, st, A, lda, sA, n, k0, info, pack, pl.total, pl.dinv,
+                                    pl.dinvT);
+        if (le != cudaSuccess) return (int)le;
         ++launches;
         const int below = n - k0 - nbk;
         if (below > 0) {
@@ -428,7 +437,7 @@ static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* i
     if (n > 1) {
         if (n > 65535) return MXF_ENOTIMPL;
         dim3 g(cdiv(n, 256), n, S);
-        zero_upper_kernel<T><<<g, 256, 0, st>>>(A, lda, sA, n);
+        launch_pdl(zero_upper_kernel<T>, g, dim3(256), (size_t)0, st, A, lda, sA, n);
         ++launches;
     }
     int rc = mxf_transpose(dtype_of<T>(), A, lda, sA, pack + pl.lt, pl.ldt, pl.total, S, n, n, st);
@@ -460,6 +469,8 @@ static int tri_pack_impl(const T* L, int64_t lda, int64_t sA, int S, int n, T* p
 template <typename T>
 __global__ void __launch_bounds__(256)
 inv_level_assemble_kernel(const T* __restrict__ src, T* __restrict__ dst, int b) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int q = blockIdx.y;
     const T* wa = src + (int64_t)(2 * q) * b * b;
     const T* wc = wa + (int64_t)b * b;
@@ -477,6 +488,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 transpose_blocks_kernel(const T* __restrict__ src, T* __restrict__ dst, int b) {
     __shared__ T tile[32][33];
+    pdl_launch_dependents();
+    pdl_wait();
     const T* sp = src + (int64_t)blockIdx.z * b * b;
     T* dp = dst + (int64_t)blockIdx.z * b * b;
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
@@ -509,11 +522,12 @@ static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int 
                              dst + (int64_t)b * 2 * b, 2 * b, (int64_t)4 * b * b, np, 2, st, 0);
             if (rc != MXF_OK) return rc;
             dim3 g(std::min(64, cdiv((int64_t)b * b, 256)), np);
-            inv_level_assemble_kernel<T><<<g, 256, 0, st>>>(src, dst, b);
+            launch_pdl(inv_level_assemble_kernel<T>, g, dim3(256), (size_t)0, st, src, dst, b);
             ++launches;
         }
         dim3 gt(pl.top / 32, pl.top / 32, n / pl.top);
-        transpose_blocks_kernel<T><<<gt, dim3(32, 8), 0, st>>>(pk + pl.lvl[pl.nlvl - 1], pk + pl.topT, pl.top);
+        launch_pdl(transpose_blocks_kernel<T>, gt, dim3(32, 8), (size_t)0, st, (const T*)(pk + pl.lvl[pl.nlvl - 1]), pk + pl.topT,
+                   pl.top);
         ++launches;
     }
     return after_launch(launches);

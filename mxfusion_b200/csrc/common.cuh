@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <cstdlib>
 #include "../../include/mxf_b200.h"
 
 namespace mxf {
@@ -16,6 +17,39 @@ inline int after_launch(int n = 1) {
 }
 
 constexpr int kNumSMs = 148;   // B200
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The step is a long chain of short dependent kernels (blocked potrf / trsm).  A kernel that (a) calls
+// pdl_launch_dependents() on entry and (b) calls pdl_wait() before its first global-memory access can be launched with
+// launch_pdl(): its grid is scheduled while the predecessor drains, so launch latency and the prologue (mbarrier init,
+// TMEM allocation) leave the critical path.  pdl_wait() returns only when the predecessor grid has completed and its
+// writes are visible, so there is no hazard; a kernel that does not call pdl_wait() must NOT be launched this way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static int on = [] {
+        const char* e = getenv("MXF_PDL");      // measured on B200: no gain under CUDA-graph replay -> opt-in
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 template <typename T> struct Num;
 template <> struct Num<float> {

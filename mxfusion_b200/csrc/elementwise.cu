@@ -122,6 +122,8 @@ square_tile_kernel(const T* __restrict__ A, int64_t lda, int64_t sA, T* __restri
                    int m, int n, T alpha) {
     // out is (n x m) for MODE 4, else (m x n) with m == n.  32x32 tiles, 32x8 threads.
     __shared__ T tile[32][33];
+    pdl_launch_dependents();
+    pdl_wait();
     const int s = blockIdx.z;
     const T* As = A + (int64_t)s * sA;
     T* Os = out + (int64_t)s * sO;
@@ -158,7 +160,7 @@ static int square_tile_launch(const T* A, int64_t lda, int64_t sA, T* out, int64
     if (S == 0 || m == 0 || n == 0) return MXF_OK;
     const int orows = (MODE == 4) ? n : m, ocols = (MODE == 4) ? m : n;
     dim3 grid(cdiv(ocols, 32), cdiv(orows, 32), S);
-    square_tile_kernel<T, MODE><<<grid, dim3(32, 8), 0, st>>>(A, lda, sA, out, ldo, sO, m, n, (T)alpha);
+    launch_pdl(square_tile_kernel<T, MODE>, grid, dim3(32, 8), (size_t)0, st, A, lda, sA, out, ldo, sO, m, n, (T)alpha);
     return after_launch();
 }
 

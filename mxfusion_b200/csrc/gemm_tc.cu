@@ -120,6 +120,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                float* __restrict__ C, int64_t ldc, int64_t sC, int m, int n, int k, float alpha, float beta,
                int tri, int batchA, int batchB) {
     using Cfg = TcCfg<BN>;
+    pdl_launch_dependents();
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
     if ((tri & 1) && n0 > m0 + TC_BM - 1) return;    // tile strictly above the diagonal: nothing to do
 
@@ -161,6 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot_ptr;
+    pdl_wait();            // everything above touched no global memory; from here on the predecessor's output is read
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -342,7 +344,9 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, i
         attr_set = true;
     }
     dim3 grid(cdiv(n, BN), cdiv(m, TC_BM), S);
-    kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, C, ldc, sC, m, n, k, alpha, beta, tri, batchA, batchB);
+    cudaError_t e = launch_pdl(kern, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, C, ldc, sC, m, n, k, alpha, beta,
+                               tri, batchA, batchB);
+    if (e != cudaSuccess) return (int)e;
     return after_launch();
 }
 
