@@ -346,10 +346,23 @@ class _SVGPLogPdf(torch.autograd.Function):
         if PP > P:
             E4[:, :, 3 * M + P:].zero_()
         E4 = R.trsm_solve(L, pk, E4, transpose=True)
-        # Kuf adjoint: (L^-T E_R) A + g s beta (L^-T mt) Y^T
-        dKuf = R.gemm(E4[:, :, 2 * M:3 * M], A)
+        # The Kuf branch (one big product + kernel adjoint) and the Kuu branch (second solve + kernel adjoint) are
+        # independent from here on: fork the Kuf branch onto the side stream
         w = E4[:, :, 3 * M:3 * M + P]
-        R.gemm(R.axpby_dev(gsb, w), Y, transB=True, beta=1.0, C=dKuf)
+        wg = R.axpby_dev(gsb, w)
+        dKuf = torch.empty((S, M, B), dtype=dt, device=dev)
+        side = _side_stream(dev)
+        cur = torch.cuda.current_stream() if side is not None else None
+
+        def kuf_branch():
+            # Kuf adjoint: (L^-T E_R) A + g s beta (L^-T mt) Y^T, then through the kernel
+            R.gemm(E4[:, :, 2 * M:3 * M], A, C=dKuf)
+            R.gemm(wg, Y, transB=True, beta=1.0, C=dKuf)
+            return R.kbuild_bwd(ctx.kind, Z, X, ls, kvar, dKuf, need_dX=True, need_dX2=need[3])
+        if side is not None:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                dZ1, dX, dls1, dvar1 = kuf_branch()
         # second solve with L^T: [(L^-T E)^T | (L^-T E_S)^T | g (s beta v - mt)]  ->  [Kuu adjoint | L^-T E_S L^-1 | mu adjoint]
         F2 = torch.empty((S, M, 2 * M + PP), dtype=dt, device=dev)
         R.transpose(E4[:, :, :M], out=F2[:, :, :M])
@@ -360,11 +373,9 @@ class _SVGPLogPdf(torch.autograd.Function):
         F2 = R.trsm_solve(L, pk, F2, transpose=True)
         dKuu = F2[:, :, :M]
         dmu = F2[:, :, 2 * M:2 * M + P].contiguous()
-        dZ1, dX, dls1, dvar1 = R.kbuild_bwd(ctx.kind, Z, X, ls, kvar, dKuf, need_dX=True, need_dX2=need[3])
         dZ2, _, dls2, dvar2 = R.kbuild_bwd(ctx.kind, Z, None, ls, kvar, dKuu)
-        dZ = dZ1 + dZ2
-        dls = dls1 + dls2
-        dkvar = dvar1 + dvar2 - (gsb * (0.5 * P * B)).unsqueeze(1)          # Kff_diag term (:100)
+        if side is None:
+            dZ1, dX, dls1, dvar1 = kuf_branch()
         # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 (S^-1 from the forward pass); W adjoint 2 Sbar W ; diag adjoint diag(Sbar)
         minus1 = torch.full((S,), -1.0, dtype=dt, device=dev)
         Sbar = R.axpby_dev(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M].contiguous())
@@ -372,6 +383,11 @@ class _SVGPLogPdf(torch.autograd.Function):
         dd = R.get_diag(Sbar)
         dnoise = (g * sc * (-beta * beta * Q - (0.5 * B * P) * beta)).unsqueeze(1)
         dY = R.axpby_dev(-gsb, Y, gsb, G1) if need[4] else None             # -g s beta (Y - A^T mt)
+        if side is not None:
+            cur.wait_stream(side)                                            # join the Kuf branch
+        dZ = dZ1 + dZ2
+        dls = dls1 + dls2
+        dkvar = dvar1 + dvar2 - (gsb * (0.5 * P * B)).unsqueeze(1)          # Kff_diag term (:100)
         return None, None, None, dX, dY, dZ, dnoise, dmu, dW, dd, dls, dkvar
 
 
