@@ -109,7 +109,7 @@ struct TcCfg {
     static constexpr int A_BYTES = TC_BM * TC_BK * 4;               // 16 KB
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);     // [A hi | B hi | A lo | B lo]
-    static constexpr int STAGES = (BN == 128) ? 3 : 4;
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128) ? 3 : 4;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -362,7 +362,11 @@ int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const
     // tile width: 64-wide tiles when 128-wide ones would leave most SMs idle
     const int64_t tiles128 = (int64_t)cdiv(n, 128) * cdiv(m, TC_BM) * S;
     const bool bn64 = !wide && tiles128 < 100;   // `wide`: C aliases A (in-place panel), one CTA must own full rows
-    const int BN = bn64 ? 64 : 128;
+    // 256-wide tiles halve the A-operand traffic per flop (the kernel is shared-memory-bandwidth bound): worth it once
+    // they still fill the machine
+    static const int bn256_min = [] { const char* e = getenv("MXF_GEMM_BN256_MIN"); return e ? atoi(e) : 120; }();
+    const bool bn256 = !wide && !bn64 && (int64_t)cdiv(n, 256) * cdiv(m, TC_BM) * S >= bn256_min && n >= 256;
+    const int BN = bn64 ? 64 : (bn256 ? 256 : 128);
     CUtensorMap tmA, tmB;
     if (!make_map(&tmA, A, m, k, lda, sA, batchA ? S : 1, TC_BK, TC_BM)) return MXF_ENOTIMPL;
     const bool b_mn = (transB == 0);
@@ -373,6 +377,10 @@ int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const
             return MXF_ENOTIMPL;
     }
     const float al = (float)alpha, be = (float)beta;
+    if (bn256) {
+        return b_mn ? launch_tc<256, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
+                    : launch_tc<256, false>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
+    }
     if (bn64) {
         return b_mn ? launch_tc<64, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
                     : launch_tc<64, false>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
