@@ -288,6 +288,225 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Variant with the A operand in TENSOR MEMORY ("TS" form of tcgen05.mma).  The plain kernel above is
+// shared-memory-bandwidth bound: per K step the split writes A_hi/A_lo/B_hi/B_lo and the three MMAs read each of them
+// again.  Here the converter warps split their row of A in registers and write A_hi / A_lo straight to TMEM
+// (tcgen05.st); shared memory then only carries the raw landing tile of A and B_hi / B_lo, and the MMAs read only B
+// from it (per K step, BN = 128: 144 KB instead of 224 KB).  Used when the K loop is long enough to pay for the
+// larger prologue (k >= 256).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+          "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+          "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+template <int BN>
+struct TaCfg {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 4;               // raw landing tile of A (16 KB)
+    static constexpr int B_BYTES = BN * TC_BK * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;       // [A raw | B hi | B lo]
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128) ? 4 : 6;
+    static constexpr int TMEM_A0 = BN;                              // accumulator in columns [0, BN); A stages after it
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    static_assert(BN + STAGES * 64 <= 512, "tensor memory budget");
+};
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  float* __restrict__ C, int64_t ldc, int64_t sC, int m, int n, int k, float alpha, float beta,
+                  int tri, int batchA, int batchB) {
+    using Cfg = TaCfg<BN>;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    if ((tri & 1) && n0 > m0 + TC_BM - 1) return;
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_ready = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * Cfg::STAGES + s); };
+    const uint32_t bar_tmem = bars + 8u * (3 * Cfg::STAGES);
+    const uint32_t tmem_slot = bar_tmem + 8u;
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (3 * Cfg::STAGES) + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_begin = (tri & 4) ? m0 / TC_BK : 0;
+    const int k_end = (tri & 2) ? min(k, m0 + TC_BM) : k;
+    const int kb_end = (k_end + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_ready(s), TC_CONV_THREADS);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int zA = batchA ? (int)blockIdx.z : 0, zB = batchB ? (int)blockIdx.z : 0;
+            for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+                const int s = it % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+                mbar_wait(bar_empty(s), ph ^ 1u);
+                const uint32_t st = base + s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(bar_full(s), Cfg::A_BYTES + Cfg::B_BYTES);
+                tma_load_3d(st, &tmA, bar_full(s), kb * TC_BK, m0, zA);
+                if (!B_MN) {
+                    tma_load_3d(st + Cfg::A_BYTES, &tmB, bar_full(s), kb * TC_BK, n0, zB);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BN / 32; ++c)
+                        tma_load_3d(st + Cfg::A_BYTES + c * (TC_BK * 128), &tmB, bar_full(s), n0 + c * 32, kb * TC_BK, zB);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+                const int s = it % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+                mbar_wait(bar_ready(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_hi = base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+                const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::TMEM_A0 + s * 64), a_lo = a_hi + 32u;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    uint64_t dbh, dbl;
+                    if (!B_MN) {
+                        dbh = smem_desc(b_hi + kk * 32, 16, 1024);
+                        dbl = smem_desc(b_lo + kk * 32, 16, 1024);
+                    } else {
+                        dbh = smem_desc(b_hi + kk * 1024, TC_BK * 128, 512, 1);
+                        dbl = smem_desc(b_lo + kk * 1024, TC_BK * 128, 512, 1);
+                    }
+                    umma_tf32_ts(tmem_base, a_lo + kk * 8, dbh, idesc, (it | kk) != 0);
+                    umma_tf32_ts(tmem_base, a_hi + kk * 8, dbl, idesc, 1);
+                    umma_tf32_ts(tmem_base, a_hi + kk * 8, dbh, idesc, 1);
+                }
+                umma_commit(bar_empty(s));
+            }
+            umma_commit(bar_tmem);
+        }
+    } else {
+        const int t = threadIdx.x - 64;          // 0..127
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;           // row of the A tile this thread splits
+        constexpr int VECB = Cfg::B_BYTES / 16;
+        for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
+            const int s = it % Cfg::STAGES;
+            const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+            mbar_wait(bar_full(s), ph);
+            uint8_t* stage = base_ptr + s * Cfg::STAGE_BYTES;
+            // A: this thread's 128-byte row (16-byte chunk c of row r sits at chunk c ^ (r & 7): 128B swizzle)
+            {
+                uint32_t hi[32], lo[32];
+                const uint8_t* arow = stage + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+                    const float h0 = to_tf32(x.x), h1 = to_tf32(x.y), h2 = to_tf32(x.z), h3 = to_tf32(x.w);
+                    hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+                    hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+                    lo[4 * c] = __float_as_uint(to_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(to_tf32(x.y - h1));
+                    lo[4 * c + 2] = __float_as_uint(to_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(to_tf32(x.w - h3));
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::TMEM_A0 + s * 64);
+                tmem_st32(ta, hi);
+                tmem_st32(ta + 32u, lo);
+            }
+            // B: position-preserving split (hi in place, lo to the second buffer)
+            float4* bh = reinterpret_cast<float4*>(stage + Cfg::A_BYTES);
+            float4* bl = reinterpret_cast<float4*>(stage + Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll 4
+            for (int i = t; i < VECB; i += TC_CONV_THREADS) {
+                const float4 x = bh[i];
+                float4 h, l;
+                h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+                l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+                bh[i] = h;
+                bl[i] = l;
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_ready(s));
+        }
+        mbar_wait(bar_tmem, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int orow = m0 + q * 32 + lane;
+        float* Cb = C + (int64_t)blockIdx.z * sC;
+        const bool vec_ok = ((ldc & 3) == 0) && ((sC & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+            if (orow < m) {
+                float* crow = Cb + (int64_t)orow * ldc;
+                const int c0 = n0 + j * 32;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const int c = c0 + e;
+                    if (c >= n) break;
+                    float o0 = alpha * __uint_as_float(v[e]), o1 = alpha * __uint_as_float(v[e + 1]);
+                    float o2 = alpha * __uint_as_float(v[e + 2]), o3 = alpha * __uint_as_float(v[e + 3]);
+                    if (vec_ok && c + 3 < n) {
+                        float4* dst = reinterpret_cast<float4*>(crow + c);
+                        if (beta != 0.f) {
+                            const float4 old = *dst;
+                            o0 = fmaf(beta, old.x, o0); o1 = fmaf(beta, old.y, o1);
+                            o2 = fmaf(beta, old.z, o2); o3 = fmaf(beta, old.w, o3);
+                        }
+                        *dst = make_float4(o0, o1, o2, o3);
+                    } else {
+                        const float o[4] = {o0, o1, o2, o3};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c + u < n) crow[c + u] = (beta != 0.f) ? fmaf(beta, crow[c + u], o[u]) : o[u];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -350,6 +569,27 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, i
     return after_launch();
 }
 
+template <int BN, bool B_MN>
+static int launch_tc_ta(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int64_t ldc, int64_t sC, int m, int n,
+                        int k, float alpha, float beta, int S, int tri, int batchA, int batchB, cudaStream_t st) {
+    using Cfg = TaCfg<BN>;
+    auto kern = gemm_tc_ta_kernel<BN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+            return (int)cudaGetLastError();
+        attr_set = true;
+    }
+    dim3 grid(cdiv(n, BN), cdiv(m, TC_BM), S);
+    kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, C, ldc, sC, m, n, k, alpha, beta, tri, batchA, batchB);
+    return after_launch();
+}
+
+static int ta_mode() {      // 0 = off, 1 = on for long K loops (default)
+    static int v = [] { const char* e = getenv("MXF_GEMM_TA"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
 // Returns MXF_ENOTIMPL when the problem does not fit the tensor-core path (caller falls back to the FMA kernel).
 int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const float* A, int64_t lda, int64_t sA,
                 const float* B, int64_t ldb, int64_t sB, double beta, float* C, int64_t ldc, int64_t sC, int S, int tri,
@@ -377,6 +617,16 @@ int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const
             return MXF_ENOTIMPL;
     }
     const float al = (float)alpha, be = (float)beta;
+    if (ta_mode() && k >= 256) {
+        if (bn256)
+            return b_mn ? launch_tc_ta<256, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
+                        : launch_tc_ta<256, false>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
+        if (bn64)
+            return b_mn ? launch_tc_ta<64, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
+                        : launch_tc_ta<64, false>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
+        return b_mn ? launch_tc_ta<128, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
+                    : launch_tc_ta<128, false>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
+    }
     if (bn256) {
         return b_mn ? launch_tc<256, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
                     : launch_tc<256, false>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
