@@ -405,7 +405,7 @@ static int dtype_of() { return sizeof(T) == 4 ? MXF_F32 : MXF_F64; }
 
 template <typename T>
 static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int n, T* pack, const PackLayout<T>& pl,
-                                cudaStream_t st);
+                                cudaStream_t st, int row0 = 0, int nrows = -1);
 
 template <typename T>
 static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* info, T* pack, cudaStream_t st) {
@@ -416,22 +416,48 @@ static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* i
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int launches = 0;
     if (info) { zero_i32_kernel<T><<<cdiv(S, 128), 128, 0, st>>>(info, S); ++launches; }
-    for (int k0 = 0; k0 < n; k0 += NB) {
-        const int nbk = std::min(NB, n - k0);
-        cudaError_t le = launch_pdl(k, dim3(S), dim3(PD_THREADS), smem, st, A, lda, sA, n, k0, info, pack, pl.total, pl.dinv,
-                                    pl.dinvT);
-        if (le != cudaSuccess) return (int)le;
-        ++launches;
-        const int below = n - k0 - nbk;
-        if (below > 0) {
-            T* A21 = A + (int64_t)(k0 + nbk) * lda + k0;
-            T* A22 = A + (int64_t)(k0 + nbk) * lda + (k0 + nbk);
-            const T* Wk = pack + pl.dinv + (int64_t)(k0 / NB) * NB * NB;
-            // L21 = A21 W^T (in place; one CTA owns full rows)
-            int rc = gemm_any<T>(0, 1, below, NB, NB, 1.0, A21, lda, sA, Wk, NB, pl.total, 0.0, A21, lda, sA, S, 0, st, 1);
+    // Two-level blocking for large matrices: factor an OB x OB diagonal block with the NB-step algorithm, invert it
+    // hierarchically (128 -> 256 -> 512), then the panel and the trailing update are GEMMs with K = OB (deep K loops keep
+    // the tensor pipe busy; with K = NB the tile prologue / epilogue dominates).
+    const int OB = (n > 1024 && pl.top >= 512 && n % pl.top == 0) ? pl.top : n;
+    for (int o0 = 0; o0 < n; o0 += OB) {
+        const int oend = std::min(n, o0 + OB);
+        for (int k0 = o0; k0 < oend; k0 += NB) {
+            const int nbk = std::min(NB, n - k0);
+            cudaError_t le = launch_pdl(k, dim3(S), dim3(PD_THREADS), smem, st, A, lda, sA, n, k0, info, pack, pl.total, pl.dinv,
+                                        pl.dinvT);
+            if (le != cudaSuccess) return (int)le;
+            ++launches;
+            const int below = oend - k0 - nbk;
+            if (below > 0) {
+                T* A21 = A + (int64_t)(k0 + nbk) * lda + k0;
+                T* A22 = A + (int64_t)(k0 + nbk) * lda + (k0 + nbk);
+                const T* Wk = pack + pl.dinv + (int64_t)(k0 / NB) * NB * NB;
+                // L21 = A21 W^T (in place; one CTA owns full rows)
+                int rc = gemm_any<T>(0, 1, below, NB, NB, 1.0, A21, lda, sA, Wk, NB, pl.total, 0.0, A21, lda, sA, S, 0, st, 1);
+                if (rc != MXF_OK) return rc;
+                rc = gemm_any<T>(0, 1, below, below, NB, -1.0, A21, lda, sA, A21, lda, sA, 1.0, A22, lda, sA, S, 1, st, 0);
+                if (rc != MXF_OK) return rc;
+            }
+        }
+        if (OB < n) {
+            int rc = build_inverse_levels<T>(A, lda, sA, S, n, pack, pl, st, o0, OB);
             if (rc != MXF_OK) return rc;
-            rc = gemm_any<T>(0, 1, below, below, NB, -1.0, A21, lda, sA, A21, lda, sA, 1.0, A22, lda, sA, S, 1, st, 0);
-            if (rc != MXF_OK) return rc;
+            const int below = n - oend;
+            if (below > 0) {
+                T* A21 = A + (int64_t)oend * lda + o0;
+                T* A22 = A + (int64_t)oend * lda + oend;
+                const T* Wo = pack + pl.lvl[pl.nlvl - 1] + (int64_t)(o0 / OB) * OB * OB;
+                T* scr = pack + pl.lt;                      // L^T is written last: its space is free until then
+                // L21 = A21 Wo^T, out of place (several column tiles share the rows of A21)
+                rc = gemm_any<T>(0, 1, below, OB, OB, 1.0, A21, lda, sA, Wo, OB, pl.total, 0.0, scr, OB, pl.total, S, 0, st, 0);
+                if (rc != MXF_OK) return rc;
+                rc = gemm_any<T>(0, 1, below, below, OB, -1.0, scr, OB, pl.total, scr, OB, pl.total, 1.0, A22, lda, sA, S, 1, st, 0);
+                if (rc != MXF_OK) return rc;
+                for (int s = 0; s < S; ++s)
+                    cudaMemcpy2DAsync(A21 + (int64_t)s * sA, (size_t)lda * sizeof(T), scr + (int64_t)s * pl.total,
+                                      (size_t)OB * sizeof(T), (size_t)OB * sizeof(T), below, cudaMemcpyDeviceToDevice, st);
+            }
         }
     }
     if (n > 1) {
@@ -442,8 +468,10 @@ static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* i
     }
     int rc = mxf_transpose(dtype_of<T>(), A, lda, sA, pack + pl.lt, pl.ldt, pl.total, S, n, n, st);
     if (rc != MXF_OK) return rc;
-    rc = build_inverse_levels<T>(A, lda, sA, S, n, pack, pl, st);
-    if (rc != MXF_OK) return rc;
+    if (OB == n) {
+        rc = build_inverse_levels<T>(A, lda, sA, S, n, pack, pl, st);
+        if (rc != MXF_OK) return rc;
+    }
     return after_launch(launches);
 }
 
@@ -498,21 +526,24 @@ transpose_blocks_kernel(const T* __restrict__ src, T* __restrict__ dst, int b) {
     for (int r = threadIdx.y; r < 32; r += 8) dp[(int64_t)(bx + r) * b + by + threadIdx.x] = tile[threadIdx.x][r];
 }
 
+// Builds the levels for the diagonal blocks inside rows/cols [row0, row0 + nrows) (default: the whole matrix); row0 and
+// nrows are multiples of pl.top.
 template <typename T>
 static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int n, T* pack, const PackLayout<T>& pl,
-                                cudaStream_t st) {
+                                cudaStream_t st, int row0, int nrows) {
     constexpr int NB = TriBlock<T>::NB;
     if (pl.top == NB) return MXF_OK;
+    if (nrows < 0) nrows = n;
     int launches = 0;
     for (int s = 0; s < S; ++s) {
-        const T* Ls = L + (int64_t)s * sA;
+        const T* Ls = L + (int64_t)s * sA + (int64_t)row0 * lda + row0;
         T* pk = pack + (int64_t)s * pl.total;
         int b = NB;
         for (int j = 0; j + 1 < pl.nlvl; ++j, b *= 2) {
-            const T* src = pk + pl.lvl[j];
-            T* dst = pk + pl.lvl[j + 1];
-            T* t1 = pk + pl.scratch;
-            const int np = n / (2 * b);
+            const T* src = pk + pl.lvl[j] + (int64_t)(row0 / b) * b * b;
+            T* dst = pk + pl.lvl[j + 1] + (int64_t)(row0 / (2 * b)) * 4 * b * b;
+            T* t1 = pk + pl.scratch + (int64_t)(row0 / (2 * b)) * b * b;
+            const int np = nrows / (2 * b);
             // T1_q = L[(2q+1)b.., 2qb..] * W_{2q}
             int rc = gemm_any<T>(0, 0, b, b, b, 1.0, Ls + (int64_t)b * lda, lda, (int64_t)2 * b * lda + 2 * b, src, b,
                                  (int64_t)2 * b * b, 0.0, t1, b, (int64_t)b * b, np, 0, st, 0);
@@ -525,9 +556,10 @@ static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int 
             launch_pdl(inv_level_assemble_kernel<T>, g, dim3(256), (size_t)0, st, src, dst, b);
             ++launches;
         }
-        dim3 gt(pl.top / 32, pl.top / 32, n / pl.top);
-        launch_pdl(transpose_blocks_kernel<T>, gt, dim3(32, 8), (size_t)0, st, (const T*)(pk + pl.lvl[pl.nlvl - 1]), pk + pl.topT,
-                   pl.top);
+        dim3 gt(pl.top / 32, pl.top / 32, nrows / pl.top);
+        const int64_t toff = (int64_t)(row0 / pl.top) * pl.top * pl.top;
+        launch_pdl(transpose_blocks_kernel<T>, gt, dim3(32, 8), (size_t)0, st, (const T*)(pk + pl.lvl[pl.nlvl - 1] + toff),
+                   pk + pl.topT + toff, pl.top);
         ++launches;
     }
     return after_launch(launches);

@@ -326,8 +326,11 @@ struct TaCfg {
     static_assert(BN + STAGES * 64 <= 512, "tensor memory budget");
 };
 
+constexpr int TA_THREADS = 320;            // producer warp, MMA warp, 8 converter / epilogue warps
+constexpr int TA_CONV_THREADS = 256;
+
 template <int BN, bool B_MN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TA_THREADS, 1)
 gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   float* __restrict__ C, int64_t ldc, int64_t sC, int m, int n, int k, float alpha, float beta,
                   int tri, int batchA, int batchB) {
@@ -355,7 +358,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_ready(s), TC_CONV_THREADS);
+            mbar_init(bar_ready(s), TA_CONV_THREADS);
             mbar_init(bar_empty(s), 1);
         }
         mbar_init(bar_tmem, 1);
@@ -420,8 +423,11 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             umma_commit(bar_tmem);
         }
     } else {
-        const int t = threadIdx.x - 64;          // 0..127
+        // 8 converter warps: the first four also split the A tile (one row per thread, TMEM quarter = warp % 4),
+        // all eight share the B tile
+        const int t = threadIdx.x - 64;          // 0..255
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const bool a_warp = warp < 6;
         const int row = q * 32 + lane;           // row of the A tile this thread splits
         constexpr int VECB = Cfg::B_BYTES / 16;
         for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
@@ -430,7 +436,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(bar_full(s), ph);
             uint8_t* stage = base_ptr + s * Cfg::STAGE_BYTES;
             // A: this thread's 128-byte row (16-byte chunk c of row r sits at chunk c ^ (r & 7): 128B swizzle)
-            {
+            if (a_warp) {
                 uint32_t hi[32], lo[32];
                 const uint8_t* arow = stage + row * 128;
 #pragma unroll
@@ -450,7 +456,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float4* bh = reinterpret_cast<float4*>(stage + Cfg::A_BYTES);
             float4* bl = reinterpret_cast<float4*>(stage + Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll 4
-            for (int i = t; i < VECB; i += TC_CONV_THREADS) {
+            for (int i = t; i < VECB; i += TA_CONV_THREADS) {
                 const float4 x = bh[i];
                 float4 h, l;
                 h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
@@ -468,8 +474,9 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int orow = m0 + q * 32 + lane;
         float* Cb = C + (int64_t)blockIdx.z * sC;
         const bool vec_ok = ((ldc & 3) == 0) && ((sC & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        // two warps per TMEM quarter: they take alternate 32-column slabs of the accumulator
 #pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int j = a_warp ? 0 : 1; j < BN / 32; j += 2) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
             if (orow < m) {
@@ -581,7 +588,7 @@ static int launch_tc_ta(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C
         attr_set = true;
     }
     dim3 grid(cdiv(n, BN), cdiv(m, TC_BM), S);
-    kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, C, ldc, sC, m, n, k, alpha, beta, tri, batchA, batchB);
+    kern<<<grid, TA_THREADS, Cfg::SMEM, st>>>(tmA, tmB, C, ldc, sC, m, n, k, alpha, beta, tri, batchA, batchB);
     return after_launch();
 }
 

