@@ -31,11 +31,26 @@ reduce_kernel(const T* __restrict__ a, int64_t lda, int64_t sA, const T* __restr
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(rows, r0 + rows_per_block);
     T acc = 0;
+    // 16-byte loads when every row start is aligned (rows are the contiguous chunks chosen by the launcher)
+    const bool vec = (sizeof(T) == 4) && (cols % 4 == 0) && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(as) & 15) == 0) &&
+                     (!TWO || ((ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(bs) & 15) == 0)));
     for (int64_t r = r0; r < r1; ++r) {
         const T* ar = as + r * lda;
         const T* br = TWO ? bs + r * ldb : nullptr;
-        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x)
-            acc += red_term<T, OP>(ar[c], TWO ? br[c] : T(0));
+        if (vec) {
+            T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            for (int64_t c = 4 * (int64_t)threadIdx.x; c < cols; c += 4 * (int64_t)blockDim.x) {
+                const float4 x = *reinterpret_cast<const float4*>(ar + c);
+                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (TWO) y = *reinterpret_cast<const float4*>(br + c);
+                a0 += red_term<T, OP>((T)x.x, (T)y.x); a1 += red_term<T, OP>((T)x.y, (T)y.y);
+                a2 += red_term<T, OP>((T)x.z, (T)y.z); a3 += red_term<T, OP>((T)x.w, (T)y.w);
+            }
+            acc += (a0 + a1) + (a2 + a3);
+        } else {
+            for (int64_t c = threadIdx.x; c < cols; c += blockDim.x)
+                acc += red_term<T, OP>(ar[c], TWO ? br[c] : T(0));
+        }
     }
     T tot = block_sum(acc, red);
     if (threadIdx.x == 0) {
@@ -62,7 +77,7 @@ static int reduce_impl(int op, const T* a, int64_t lda, int64_t sA, const T* b, 
         while (total % chunk != 0 && chunk > 1) chunk >>= 1;
         if (chunk >= 256) { rows = total / chunk; cols = chunk; lda = chunk; ldb = chunk; }
     }
-    int64_t nblk = std::min<int64_t>(std::max<int64_t>(1, rows), (int64_t)2 * kNumSMs);
+    int64_t nblk = std::min<int64_t>(std::max<int64_t>(1, rows), (int64_t)8 * kNumSMs);
     int64_t rpb = (rows + nblk - 1) / nblk;
     if (rpb < 1) rpb = 1;
     nblk = std::max<int64_t>(1, (rows + rpb - 1) / rpb);
@@ -175,6 +190,28 @@ normal_logpdf_sum_kernel(const T* __restrict__ x, int64_t sX, const T* __restric
     const T c0 = T(-0.91893853320467274178);   // -0.5 log(2 pi)
     T acc = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = (sizeof(T) == 4) && (n % 4 == 0) && (sX % 4 == 0) && (sM % 4 == 0) && (sV % 4 == 0) &&
+                     (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0);
+    if (vec) {
+        T a4[4] = {T(0), T(0), T(0), T(0)};
+        for (int64_t i = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * stride) {
+            float4 mv, vv;
+            if (sM == 0) mv = *reinterpret_cast<const float4*>(m + i);
+            if (sV == 0) vv = *reinterpret_cast<const float4*>(v + i);
+            for (int s = 0; s < S; ++s) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + s * sX + i);
+                if (sM != 0) mv = *reinterpret_cast<const float4*>(m + s * sM + i);
+                if (sV != 0) vv = *reinterpret_cast<const float4*>(v + s * sV + i);
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w}, vs[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float d = xs[u] - ms[u];
+                    a4[u] += (T)((float)c0 - 0.5f * logf(vs[u]) - d * d / (2.0f * vs[u]));
+                }
+            }
+        }
+        acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    } else
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         for (int s = 0; s < S; ++s) {
             const T xv = x[s * sX + i], mv = m[s * sM + i], vv = v[s * sV + i];
@@ -243,22 +280,54 @@ normal_reparam_kernel(const T* __restrict__ eps, const T* __restrict__ m, int64_
         }
         return;
     }
-    // four normals per Philox call: thread handles elements 4q .. 4q+3
-    const int64_t quads = (total + 3) / 4;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+    // four normals per Philox call: thread handles elements 4q .. 4q+3 of the flattened (S, n) array
+    auto normals4 = [&](uint64_t q, float (&z)[4]) {
         uint32_t r[4];
-        philox4x32_10((uint64_t)q, offset, seed, r);
-        float z[4];
+        philox4x32_10(q, offset, seed, r);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const float u1 = ((float)r[2 * h] + 1.0f) * 2.3283064365386963e-10f;       // (0,1]
             const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;            // [0,1)
-            const float rad = sqrtf(-2.0f * logf(u1));
+            const float rad = sqrtf(-2.0f * __logf(u1));
             float sn, cs;
-            sincospif(2.0f * u2, &sn, &cs);
+            __sincosf(6.283185307179586f * u2, &sn, &cs);
             z[2 * h] = rad * cs;
             z[2 * h + 1] = rad * sn;
         }
+    };
+    const bool vec = (sizeof(T) == 4) && (n % 4 == 0) && (sM % 4 == 0) && (sV % 4 == 0) &&
+                     (((reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(w) |
+                        reinterpret_cast<uintptr_t>(eps_out)) & 15) == 0);
+    if (vec) {
+        // rows are whole numbers of quads: no division; mean / variance are loaded once when shared by the samples
+        const int64_t nq = n / 4;
+        for (int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; qi < nq; qi += stride) {
+            float4 mv, sd;
+            if (sM == 0) mv = *reinterpret_cast<const float4*>(m + 4 * qi);
+            if (sV == 0) {
+                const float4 vv = *reinterpret_cast<const float4*>(v + 4 * qi);
+                sd = make_float4(sqrtf(vv.x), sqrtf(vv.y), sqrtf(vv.z), sqrtf(vv.w));
+            }
+            for (int s = 0; s < S; ++s) {
+                float z[4];
+                normals4((uint64_t)(s * nq + qi), z);
+                if (sM != 0) mv = *reinterpret_cast<const float4*>(m + s * sM + 4 * qi);
+                if (sV != 0) {
+                    const float4 vv = *reinterpret_cast<const float4*>(v + s * sV + 4 * qi);
+                    sd = make_float4(sqrtf(vv.x), sqrtf(vv.y), sqrtf(vv.z), sqrtf(vv.w));
+                }
+                const float4 o = make_float4(fmaf(z[0], sd.x, mv.x), fmaf(z[1], sd.y, mv.y), fmaf(z[2], sd.z, mv.z),
+                                             fmaf(z[3], sd.w, mv.w));
+                __stcs(reinterpret_cast<float4*>(w + s * n + 4 * qi), o);
+                if (eps_out) __stcs(reinterpret_cast<float4*>(eps_out + s * n + 4 * qi), make_float4(z[0], z[1], z[2], z[3]));
+            }
+        }
+        return;
+    }
+    const int64_t quads = (total + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+        float z[4];
+        normals4((uint64_t)q, z);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int64_t e = 4 * q + t;

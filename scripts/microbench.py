@@ -117,6 +117,44 @@ def bench_trsm(res):
         res.append(r)
 
 
+def bench_normal(res):
+    """MC-ELBO pieces (normal.py:52-92 + factor_graph.py:223) at a stress size (n >= 2^26)."""
+    dev = torch.device('cuda:0')
+    n, S = 1 << 26, 3
+    m = torch.randn((1, n), device=dev)
+    v = torch.rand((1, n), device=dev) + 0.5
+    w = torch.empty((S, n), device=dev)
+    # reparameterised draw with the Philox stream generated in-kernel: read 2n (mean, variance), write S*n
+    med, best = timeit(lambda: _raw.normal_reparam(m, v, S, seed=1, offset=0), iters=8)
+    nbytes = 4 * n * (2 + S)
+    r = dict(kernel='normal_reparam(philox)', n=n, S=S, ms_median=med, alg_bytes=nbytes, gbs=nbytes / med / 1e6,
+             frac_of_measured_hbm=nbytes / med / 1e6 / HBM)
+    print(r, flush=True)
+    res.append(r)
+    x = _raw.normal_reparam(m, v, S, seed=1, offset=0)
+    # fused log-density + sample mean + sum: read S*n (samples) + 2n (mean, variance), write 4 bytes
+    med, best = timeit(lambda: _raw.normal_logpdf_sum(x, m, v), iters=8)
+    nbytes = 4 * n * (2 + S)
+    r = dict(kernel='normal_logpdf_sum', n=n, S=S, ms_median=med, alg_bytes=nbytes, gbs=nbytes / med / 1e6,
+             frac_of_measured_hbm=nbytes / med / 1e6 / HBM)
+    print(r, flush=True)
+    res.append(r)
+    g = torch.ones((1,), device=dev)
+    med, best = timeit(lambda: _raw.normal_logpdf_sum_bwd(x, m, v, g, need=(False, True, True)), iters=8)
+    nbytes = 4 * n * (2 + S + 2)
+    r = dict(kernel='normal_logpdf_sum_bwd', n=n, S=S, ms_median=med, alg_bytes=nbytes, gbs=nbytes / med / 1e6,
+             frac_of_measured_hbm=nbytes / med / 1e6 / HBM)
+    print(r, flush=True)
+    res.append(r)
+    a = torch.randn((1, 8192, 8192), device=dev)
+    med, best = timeit(lambda: _raw.reduce(_raw.RED_SUMSQ, a), iters=8)
+    nbytes = 4 * a.numel()
+    r = dict(kernel='reduce_sumsq', n=a.numel(), ms_median=med, alg_bytes=nbytes, gbs=nbytes / med / 1e6,
+             frac_of_measured_hbm=nbytes / med / 1e6 / HBM)
+    print(r, flush=True)
+    res.append(r)
+
+
 def main():
     which = sys.argv[1:] or ['all']
     res = []
@@ -129,6 +167,8 @@ def main():
         bench_potrf(res)
     if 'trsm' in which or 'all' in which:
         bench_trsm(res)
+    if 'normal' in which or 'all' in which:
+        bench_normal(res)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'microbench_%d.json' % int(time.time())), 'w') as f:
         json.dump(res, f, indent=1)
