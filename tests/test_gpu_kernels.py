@@ -420,3 +420,25 @@ def test_potrf_packed_two_level_large(cuda):
     B = rng.randn(1, n, 64)
     X = _raw.trsm_solve(L, pack, T(B, cuda, torch.float32))
     np.testing.assert_allclose(X.cpu().numpy()[0], np.linalg.solve(want, B[0]), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('ard', [False, True])
+def test_kbuild_bwd_without_column_gradient(cuda, kind, ard):
+    """X2 needs no gradient (the minibatch rows of K(Z, X)): the lengthscale gradient is accumulated directly."""
+    from mxfusion_b200 import _raw
+    from oracle import torch_ref
+    rng = np.random.RandomState(5)
+    S, N, N2, D = 2, 70, 300, 8
+    X = torch.tensor(rng.uniform(-2, 2, (S, N, D)), requires_grad=True)
+    X2 = torch.tensor(rng.uniform(-2, 2, (S, N2, D)))
+    ls = torch.tensor(rng.uniform(0.5, 2.0, (S, D if ard else 1)), requires_grad=True)
+    var = torch.tensor(rng.uniform(0.5, 2.0, (S, 1)), requires_grad=True)
+    G = torch.tensor(rng.randn(S, N, N2))
+    (torch_ref.K(kind, X, ls, var, X2) * G).sum().backward()
+    dX, dX2, dls, dvar = _raw.kbuild_bwd(kind, X.detach().to(cuda), X2.to(cuda), ls.detach().to(cuda),
+                                         var.detach().to(cuda), G.to(cuda), need_dX2=False)
+    assert dX2 is None
+    np.testing.assert_allclose(dX.cpu().numpy(), X.grad.numpy(), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(dls.cpu().numpy(), ls.grad.numpy(), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(dvar.cpu().numpy(), var.grad.numpy(), rtol=1e-7, atol=1e-9)
