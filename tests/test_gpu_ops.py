@@ -112,3 +112,31 @@ def test_ops_refuse_cpu_tensors():
     x = torch.zeros((1, 4, 2))
     with pytest.raises(_lib.MXFusionB200Error):
         ops.kernel_matrix(0, x, None, torch.ones((1, 1)), torch.ones((1, 1)))
+
+
+@pytest.mark.parametrize('name,kind,B,M,Din', [('C2 SVGP M=512 D=8 RBF B=2048', 0, 2048, 512, 8),
+                                               ('C3 SVGP M=1024 D=16 Matern52 B=4096', 3, 4096, 1024, 16),
+                                               ('H  SVGP M=1024 D=8 RBF B=4096', 0, 4096, 1024, 8)])
+def test_fused_svgp_at_baseline_shapes_f32(cuda, name, kind, B, M, Din):
+    """BASELINE.json configs 2, 3 and the headline shape in float32 (the reference's default dtype) against the float64
+    restatement: value within 2e-3 relative, every gradient within 2e-2 of its max-norm (fp32 with a jittered Kuu)."""
+    from mxfusion_b200 import ops
+    rng = np.random.RandomState(7)
+    X = rng.uniform(-3, 3, (1, B, Din))
+    Y = (np.sin(X).sum(-1, keepdims=True) / np.sqrt(Din) + 0.05 * rng.randn(1, B, 1))
+    a = dict(X=X, Y=Y, Z=X[:, rng.permutation(B)[:M]].copy(), noise=np.full((1, 1), 0.05), mu=0.1 * rng.randn(1, M, 1),
+             W=0.05 * rng.randn(1, M, M) / np.sqrt(M), dv=np.full((1, M), 0.5), ls=np.full((1, 1), 1.3), var=np.full((1, 1), 1.1))
+    r = {k: torch.tensor(v, requires_grad=True) for k, v in a.items()}
+    t = {k: torch.tensor(v, dtype=torch.float32, device=cuda, requires_grad=True) for k, v in a.items()}
+    want = torch_ref.svgp_log_pdf(kind, r['X'], r['Y'], r['Z'], r['noise'], r['mu'], r['W'], r['dv'], r['ls'], r['var'],
+                                  jitter=1e-4, log_pdf_scaling=25.0)
+    want.sum().backward()
+    got = ops.svgp_log_pdf(kind, t['X'], t['Y'], t['Z'], t['noise'], t['mu'], t['W'], t['dv'], t['ls'], t['var'],
+                           jitter=1e-4, log_pdf_scaling=25.0)
+    got.sum().backward()
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=2e-3)
+    for k in a:
+        if k in ('X', 'Y'):
+            continue
+        g, w = t[k].grad.double().cpu().numpy(), r[k].grad.numpy()
+        assert np.max(np.abs(g - w)) <= 2e-2 * (1e-3 + np.max(np.abs(w))), (name, k, np.max(np.abs(g - w)), np.max(np.abs(w)))
