@@ -475,3 +475,100 @@ def gp_log_pdf(kind, X, Y, noise_var, lengthscale, variance, jitter=0.0, mean=No
     S = _lead(X, Y, noise_var, lengthscale, variance)
     args = [_expand(t, S).contiguous() for t in (X, Y, noise_var, lengthscale, variance)]
     return _GPLogPdf.apply(kind, float(jitter), *args)
+
+
+# --------------------------------------------------------------------------------------------------
+# variational sparse GP (Titsias collapsed bound): streamed whitened statistics
+# --------------------------------------------------------------------------------------------------
+STATS_CHUNK_ROWS = 32768     # rows of X per streamed block: K(Z, X_c) is M x 32768 (128 MB at M = 1024, f32)
+
+
+class _WhitenedStats(torch.autograd.Function):
+    """Phi = sum_c A_c A_c^T (S,M,M) and b = sum_c A_c Y_c (S,M,P) with A_c = L^-1 K(Z, X_c), streamed over blocks
+    of rows of X so that neither K(Z,X) nor L^-1 K(Z,X) (M x N, 4.1 GB each at N=1e6, M=1024) is ever resident:
+    these are the only places where sparsegp_regression.py:77-100 touches the N axis besides sum(Y^2).
+    The adjoint re-streams X (recomputing K(Z, X_c) is cheaper than keeping it); the factor's adjoint has the closed
+    form  Lbar = -tril(L^-T (G Phi + bbar b^T)),  G = Phibar + Phibar^T."""
+
+    @staticmethod
+    def forward(ctx, kind, chunk, X, Y, Z, ls, var, L):
+        S, N, P = X.shape[0], X.shape[1], Y.shape[2]
+        M = Z.shape[1]
+        pack = R.tri_pack(L)
+        Phi = torch.zeros((S, M, M), dtype=X.dtype, device=X.device)
+        b = torch.zeros((S, M, P), dtype=X.dtype, device=X.device)
+        for c0 in range(0, N, chunk):
+            Xc, Yc = X[:, c0:c0 + chunk], Y[:, c0:c0 + chunk]
+            A = R.trsm_solve(L, pack, R.kbuild_fwd(kind, Z, Xc, ls, var))       # :77, :81 on this block
+            R.gemm(A, A, transB=True, beta=1.0, C=Phi, tri=True)                # :84 syrk(LinvKuf), lower tiles
+            R.gemm(A, Yc.contiguous(), beta=1.0, C=b)                           # :90 gemm2(LinvKuf, Y)
+        Phi = R.copy_ltu(Phi)
+        ctx.kind, ctx.chunk = kind, chunk
+        ctx.save_for_backward(X, Y, Z, ls, var, L, pack, Phi, b)
+        return Phi, b
+
+    @staticmethod
+    def backward(ctx, gPhi, gb):
+        X, Y, Z, ls, var, L, pack, Phi, b = ctx.saved_tensors
+        need = ctx.needs_input_grad      # (kind, chunk, X, Y, Z, ls, var, L)
+        N, chunk = X.shape[1], ctx.chunk
+        G = R.symmetrize(gPhi.contiguous(), 1.0)                                # Phibar + Phibar^T
+        gb = gb.contiguous()
+        dX = torch.empty_like(X) if need[2] else None
+        dY = torch.empty_like(Y) if need[3] else None
+        dZ = dls = dvar = None
+        for c0 in range(0, N, chunk):
+            Xc, Yc = X[:, c0:c0 + chunk], Y[:, c0:c0 + chunk].contiguous()
+            A = R.trsm_solve(L, pack, R.kbuild_fwd(kind=ctx.kind, X=Z, X2=Xc, ls=ls, var=var))
+            Abar = R.gemm(G, A)
+            R.gemm(gb, Yc, transB=True, beta=1.0, C=Abar)
+            Kbar = R.trsm_solve(L, pack, Abar, transpose=True)
+            dZc, dXc, dlsc, dvarc = R.kbuild_bwd(ctx.kind, Z, Xc, ls, var, Kbar, need_dX=True, need_dX2=need[2])
+            dZ = dZc if dZ is None else dZ + dZc
+            dls = dlsc if dls is None else dls + dlsc
+            dvar = dvarc if dvar is None else dvar + dvarc
+            if need[2]:
+                dX[:, c0:c0 + chunk] = dXc
+            if need[3]:
+                dY[:, c0:c0 + chunk] = R.gemm(A, gb, transA=True)
+        dL = None
+        if need[7]:
+            Hm = R.gemm(G, Phi)
+            R.gemm(gb, b, transB=True, beta=1.0, C=Hm)
+            dL = R.tril(R.trsm_solve(L, pack, Hm, transpose=True))
+            dL = -dL
+        return None, None, dX, dY, dZ, dls, dvar, dL
+
+
+def whitened_stats(kind, X, Y, Z, lengthscale, variance, L, chunk=None):
+    S = _lead(X, Y, Z, lengthscale, variance, L)
+    args = [_expand(t, S).contiguous() for t in (X, Y, Z, lengthscale, variance, L)]
+    return _WhitenedStats.apply(kind, int(chunk or STATS_CHUNK_ROWS), *args)
+
+
+def sparsegp_log_pdf(kind, X, Y, Z, noise_var, lengthscale, variance, jitter=0.0, mean=None, chunk=None):
+    """SparseGPRegressionLogPdf.compute (sparsegp_regression.py:42-108) -> (logL (S,), wv, L, LA); wv, L, LA are the
+    posterior quantities cached for prediction (:101-106) and carry no gradient.  The N axis is consumed by the
+    streamed statistics above; everything after them is M x M (two potrf, one solve, reductions).  As in the
+    reference, `log_pdf_scaling` does not enter this bound."""
+    if noise_var.dim() != 2 or noise_var.shape[-1] != 1:
+        raise NotImplementedError("noise_var must have shape (S, 1)")
+    if mean is not None:
+        Y = Y - mean                                                            # :87-89
+    N, D, M = X.shape[-2], Y.shape[-1], Z.shape[-2]
+    Kuu = kernel_matrix(kind, Z, None, lengthscale, variance, diag_const=jitter)    # :72-75
+    L, info = potrf(Kuu, return_info=True)                                      # :80
+    Phi, b = whitened_stats(kind, X, Y, Z, lengthscale, variance, L, chunk=chunk)
+    nv = noise_var.unsqueeze(-1)                                                # (S,1,1)
+    eye = torch.eye(M, dtype=Phi.dtype, device=Phi.device).unsqueeze(0)
+    LA, infoA = potrf(eye + Phi / nv, return_info=True)                         # :83-85
+    c = trsm(LA, b)                                                             # :90
+    n1 = noise_var[:, 0]
+    logL = -D * sumlogdiag(LA)                                                  # :92
+    logL = logL - (torch.sum(torch.square(Y), dim=(-1, -2)) / n1 + (N * D) * (_LOG2PI + torch.log(n1))) / 2   # :93-94
+    logL = logL + torch.sum(torch.square(c), dim=(-1, -2)) / (2 * torch.square(n1))                           # :95-97
+    logL = logL - (D * N) * variance[:, 0] / (2 * n1)                           # :98  (Kdiag = variance)
+    logL = logL + D * torch.sum(torch.diagonal(Phi, dim1=-2, dim2=-1), dim=-1) / (2. * n1)    # :99-100
+    with torch.no_grad():                                                       # :101-106
+        wv = trsm(L, trsm(LA, c, transpose=True), transpose=True) / nv
+    return logL, wv, L.detach(), LA.detach(), (info, infoA)

@@ -114,6 +114,31 @@ def gp_log_pdf(kind, X, Y, noise_var, lengthscale, variance, jitter=0.0):
     return -logdet_l * D - tmp / 2
 
 
+def sparsegp_log_pdf(kind, X, Y, Z, noise_var, lengthscale, variance, jitter=0.0):
+    """sparsegp_regression.py:62-100 (collapsed bound; log_pdf_scaling is not applied by the reference)."""
+    D = Y.shape[-1]
+    M = Z.shape[-2]
+    noise_var_m = noise_var.unsqueeze(-2)
+    eye = torch.eye(M, dtype=Z.dtype).unsqueeze(0)
+    Kuu = K(kind, Z, lengthscale, variance)
+    if jitter > 0.:
+        Kuu = Kuu + eye * jitter
+    Kuf = K(kind, Z, lengthscale, variance, X)
+    Kff_diag = torch.zeros(X.shape[:-1], dtype=X.dtype) + variance
+    L = torch.linalg.cholesky(Kuu)
+    LinvKuf = trsm(L, Kuf)
+    A = eye + torch.matmul(LinvKuf, LinvKuf.transpose(-1, -2)) / noise_var_m
+    LA = torch.linalg.cholesky(A)
+    LAInvLinvKufY = trsm(LA, torch.matmul(LinvKuf, Y))
+    logL = -D * sumlogdiag(LA)
+    logL = logL - torch.sum(torch.square(Y) / noise_var_m + math.log(2. * math.pi) + torch.log(noise_var_m),
+                            dim=(-1, -2)) / 2
+    logL = logL + torch.sum(torch.square(LAInvLinvKufY) / (2 * torch.square(noise_var_m)), dim=(-1, -2))
+    logL = logL - D * torch.sum(Kff_diag / (2 * noise_var), dim=-1)
+    logL = logL + D * torch.sum(torch.square(LinvKuf) / (2. * noise_var_m), dim=(-1, -2))
+    return logL
+
+
 def normal_log_pdf(mean, variance, rv, scaling=1.0):
     """normal.py:67-69."""
     logvar = math.log(2 * math.pi) / -2 + torch.log(variance) / -2

@@ -11,6 +11,8 @@ Scenarios follow the reference's tests and notebooks:
   svgp_mb   MinibatchInferenceLoop trajectory (shuffled rollover batches, rv_scaling, grads / B)
   normal    testing/components/distributions/normal_test.py:35-109 (log_pdf, reparameterised draw with injected eps)
   svi       StochasticVariationalInference on a conjugate toy model with injected posterior samples
+  sparsegp  testing/modules/sparsegpregression_test.py:41-196 fixture (+ Matern, P=1, larger M): bound, gradients,
+            cached wv / L / LA, mean / variance prediction in the four modes
 Each .npz stores the inputs next to the outputs, so tests need nothing but the file.
 """
 import os
@@ -32,7 +34,7 @@ from mxfusion.common import config  # noqa: E402
 from mxfusion.components.variables import PositiveTransformation  # noqa: E402
 from mxfusion.components.distributions import Normal  # noqa: E402
 from mxfusion.components.distributions.gp.kernels import RBF, Matern12, Matern32, Matern52  # noqa: E402
-from mxfusion.modules.gp_modules import GPRegression, SVGPRegression  # noqa: E402
+from mxfusion.modules.gp_modules import GPRegression, SVGPRegression, SparseGPRegression  # noqa: E402
 from mxfusion.inference import (Inference, GradBasedInference, MAP, BatchInferenceLoop, MinibatchInferenceLoop,  # noqa: E402
                                 StochasticVariationalInference, create_Gaussian_meanfield)
 from mxfusion.inference import TransferInference, ModulePredictionAlgorithm  # noqa: E402
@@ -318,6 +320,58 @@ def golden_svi():
          loss=loss.asnumpy(), **{'grad_' + k: v for k, v in g.items()})
 
 
+# ------------------------------------------------------------------------------------------------ sparse GP (Titsias)
+def sparsegp_case(kname, P, seed, N=10, M=3, Din=3, jitter=1e-8, ard=True):
+    np.random.seed(seed)
+    X, Y, Z = np.random.rand(N, Din), np.random.rand(N, P), np.random.rand(M, Din)
+    noise_var, lengthscale, variance = np.random.rand(1), np.random.rand(Din if ard else 1), np.random.rand(1)
+    Xt = np.random.rand(5, Din)
+    m = Model()
+    m.N = Variable()
+    m.X = Variable(shape=(m.N, Din))
+    m.Z = Variable(shape=(M, Din), initial_value=nd(Z))
+    m.noise_var = Variable(transformation=PositiveTransformation(), initial_value=nd(noise_var))
+    kernel = KERNELS[kname](input_dim=Din, ARD=ard, variance=nd(variance), lengthscale=nd(lengthscale), dtype=DT)
+    m.Y = SparseGPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                             shape=(m.N, P), dtype=DT)
+    gp = m.Y.factor
+    gp.sgp_log_pdf.jitter = jitter
+    infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), dtype=DT)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    executor = infr.create_executor()
+    with mx.autograd.record():
+        loss, loss_g = executor(mx.nd.zeros(1), nd(X), nd(Y))
+        loss_g.backward()
+    g = grads_of(infr, dict(Z=m.Z, noise_var=m.noise_var, lengthscale=kernel.lengthscale, variance=kernel.variance))
+    post = gp._extra_graphs[0]
+    r = dict(X=X, Y=Y, Z=Z, noise_var=noise_var, lengthscale=lengthscale, variance=variance, jitter=jitter, Xt=Xt,
+             loss=loss.asnumpy(), wv=infr.params[post.wv].asnumpy(), L=infr.params[post.L].asnumpy(),
+             LA=infr.params[post.LA].asnumpy(), **{'grad_' + k: v for k, v in g.items()})
+    for noise_free in (True, False):
+        for diag in (True, False):
+            gp.sgp_predict.noise_free, gp.sgp_predict.diagonal_variance = noise_free, diag
+            infr2 = TransferInference(ModulePredictionAlgorithm(m, observed=[m.X], target_variables=[m.Y]),
+                                      infr_params=infr.params, dtype=np.float64)
+            res = infr2.run(X=nd(Xt))[0]
+            tag = 'pred_nf%d_diag%d' % (int(noise_free), int(diag))
+            r[tag + '_mean'] = res[0].asnumpy()
+            r[tag + '_var'] = res[1].asnumpy()
+    return r
+
+
+def golden_sparsegp():
+    out = {}
+    cases = [('rbf', 2, 0, {}), ('matern52', 1, 1, {}), ('matern32', 3, 2, dict(N=17, M=5)),
+             ('rbf', 1, 3, dict(N=40, M=8, Din=2, ard=False, jitter=1e-6)), ('matern12', 1, 4, {})]
+    for i, (kname, P, seed, kw) in enumerate(cases):
+        r = sparsegp_case(kname, P, seed, **kw)
+        out['case%d_kernel' % i] = kname
+        for k, v in r.items():
+            out['case%d_%s' % (i, k)] = v
+    out['n_cases'] = len(cases)
+    save('sparsegp_fixture', **out)
+
+
 if __name__ == '__main__':
     golden_kernels()
     golden_svgp()
@@ -327,3 +381,4 @@ if __name__ == '__main__':
     golden_normal()
     golden_svi()
     golden_predict()
+    golden_sparsegp()

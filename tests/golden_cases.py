@@ -181,3 +181,46 @@ def run_predict(mf, g, module, device):
                 res = infr2.run(X=Xt)[0]
             out[(noise_free, diag)] = (res[0].cpu().numpy(), res[1].cpu().numpy())
     return out
+
+
+def run_sparsegp_case(mf, g, i, device, chunk_rows=None):
+    """Rebuilds case i of sparsegp_fixture.npz through the public API; returns (loss, grads wrt the stored
+    parameters, cached (wv, L, LA), {(noise_free, diag): (mean, var)})."""
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.modules.gp_modules import SparseGPRegression
+    from mxfusion_b200.inference import GradBasedInference, MAP, TransferInference, ModulePredictionAlgorithm
+    c = lambda k: g['case%d_%s' % (i, k)]
+    X, Y, Z, Xt = c('X'), c('Y'), c('Z'), c('Xt')
+    N, Din = X.shape
+    M, P = Z.shape[0], Y.shape[1]
+    ard = c('lengthscale').shape[0] == Din and Din > 1
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, Din))
+    m.Z = mf.Variable(shape=(M, Din), initial_value=Z)
+    m.noise_var = mf.Variable(transformation=PositiveTransformation(), initial_value=c('noise_var'))
+    kernel = kernel_class(c('kernel'))(input_dim=Din, ARD=ard, variance=c('variance'), lengthscale=c('lengthscale'))
+    m.Y = SparseGPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                             shape=(m.N, P))
+    gp = m.Y.factor
+    gp.sgp_log_pdf.jitter = float(c('jitter'))
+    gp.sgp_log_pdf.chunk_rows = chunk_rows
+    infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), context=device)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    infr.params.gflat.zero_()
+    loss, loss_g = infr.create_executor()(None, torch.tensor(X, device=device), torch.tensor(Y, device=device))
+    loss_g.backward()
+    grads = dict(Z=param_grad(infr, m.Z), noise_var=param_grad(infr, m.noise_var),
+                 lengthscale=param_grad(infr, kernel.lengthscale), variance=param_grad(infr, kernel.variance))
+    post = gp._extra_graphs[0]
+    cache = tuple(infr.params[v].cpu().numpy() for v in (post.wv, post.L, post.LA))
+    pred = {}
+    for noise_free in (True, False):
+        for diag in (True, False):
+            gp.sgp_predict.noise_free, gp.sgp_predict.diagonal_variance = noise_free, diag
+            infr2 = TransferInference(ModulePredictionAlgorithm(m, observed=[m.X], target_variables=[m.Y]),
+                                      infr_params=infr.params, context=device)
+            with torch.no_grad():
+                res = infr2.run(X=Xt)[0]
+            pred[(noise_free, diag)] = (res[0].cpu().numpy(), res[1].cpu().numpy())
+    return float(loss), grads, cache, pred

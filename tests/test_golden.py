@@ -178,3 +178,63 @@ def test_product_prediction_matches_reference(mf, module):
         t = '%s_nf%d_diag%d' % (module, int(nf), int(dg))
         np.testing.assert_allclose(mu, g[t + '_mean'], rtol=1e-9, atol=1e-12, err_msg=t)
         np.testing.assert_allclose(var.reshape(g[t + '_var'].shape), g[t + '_var'], rtol=1e-8, atol=1e-11, err_msg=t)
+
+
+# ------------------------------------------------------------------------------------------- sparse GP
+def test_oracle_sparsegp_matches_reference():
+    """Bound, cached wv / L / LA and prediction (4 modes) of the reference's own SparseGPRegression run
+    (sparsegpregression_test.py:41-196 fixture is case 0), plus the independent dense formulation."""
+    from oracle import sparsegp as osg
+    g = gc.load('sparsegp_fixture')
+    for i in range(int(g['n_cases'])):
+        c = lambda k: g['case%d_%s' % (i, k)]
+        kind = KIND[str(c('kernel'))]
+        a = [c(k)[None] for k in ('X', 'Y', 'Z', 'noise_var', 'lengthscale', 'variance')]
+        logL, (wv, L, LA) = osg.sparsegp_log_pdf(kind, *a, jitter=float(c('jitter')), return_cache=True)
+        np.testing.assert_allclose(-logL[0], float(c('loss')), rtol=1e-12)
+        ind = osg.sparsegp_bound_independent(kind, c('X'), c('Y'), c('Z'), c('noise_var'), c('lengthscale'),
+                                             c('variance'), float(c('jitter')))
+        np.testing.assert_allclose(-ind, float(c('loss')), rtol=tol(c('kernel'), 1e-9) * 10)
+        np.testing.assert_allclose(wv[0], c('wv'), rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(L[0], c('L'), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(LA[0], c('LA'), rtol=1e-9, atol=1e-11)
+        for nf in (True, False):
+            for dg in (True, False):
+                mu, var = osg.sparsegp_predict(kind, c('Xt')[None], a[2], wv, L, LA, a[3], a[4], a[5],
+                                               noise_free=nf, diagonal_variance=dg)
+                t = 'pred_nf%d_diag%d' % (int(nf), int(dg))
+                np.testing.assert_allclose(mu, c(t + '_mean'), rtol=1e-9, atol=1e-12)
+                np.testing.assert_allclose(var, c(t + '_var'), rtol=1e-8, atol=1e-11)
+        # gradient oracle (torch restatement) against the reference's gradients wrt the stored parameters
+        u = {k: torch.tensor(otr.softplus_inverse(c(k)), requires_grad=True) for k in ('noise_var', 'lengthscale', 'variance')}
+        Z = torch.tensor(c('Z'), requires_grad=True)
+        sp = torch.nn.functional.softplus
+        un = lambda t_: t_.unsqueeze(0)
+        loss = -torch_ref.sparsegp_log_pdf(kind, un(torch.tensor(c('X'))), un(torch.tensor(c('Y'))), un(Z),
+                                           un(sp(u['noise_var'])), un(sp(u['lengthscale'])), un(sp(u['variance'])),
+                                           jitter=float(c('jitter'))).sum()
+        loss.backward()
+        for k, t_ in list(u.items()) + [('Z', Z)]:
+            np.testing.assert_allclose(t_.grad.numpy(), c('grad_' + k), rtol=tol(c('kernel'), 1e-7) * 10,
+                                       atol=tol(c('kernel'), 1e-9) * 10, err_msg='case %d %s' % (i, k))
+
+
+@pytest.mark.parametrize('chunk_rows', [None, 4])
+def test_product_sparsegp_fixture_value_gradients_cache_and_prediction(mf, chunk_rows):
+    """The streamed-statistics formulation (chunk_rows=4 forces several blocks, with a ragged last one) against the
+    reference's materialising one."""
+    g = gc.load('sparsegp_fixture')
+    for i in range(int(g['n_cases'])):
+        loss, grads, (wv, L, LA), pred = gc.run_sparsegp_case(mf, g, i, torch.device('cpu'), chunk_rows=chunk_rows)
+        kn = g['case%d_kernel' % i]
+        np.testing.assert_allclose(loss, float(g['case%d_loss' % i]), rtol=tol(kn, 1e-10))
+        for k, v in grads.items():
+            np.testing.assert_allclose(v, g['case%d_grad_%s' % (i, k)], rtol=tol(kn, 1e-7) * 10, atol=tol(kn, 1e-9) * 10,
+                                       err_msg='case %d %s' % (i, k))
+        np.testing.assert_allclose(wv, g['case%d_wv' % i], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(L, g['case%d_L' % i], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(LA, g['case%d_LA' % i], rtol=1e-8, atol=1e-10)
+        for (nf, dg), (mu, var) in pred.items():
+            t = 'case%d_pred_nf%d_diag%d' % (i, int(nf), int(dg))
+            np.testing.assert_allclose(mu, g[t + '_mean'], rtol=1e-8, atol=1e-10, err_msg=t)
+            np.testing.assert_allclose(var.reshape(g[t + '_var'].shape), g[t + '_var'], rtol=1e-7, atol=1e-10, err_msg=t)
