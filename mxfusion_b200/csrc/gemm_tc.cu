@@ -317,13 +317,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 
 template <int BN>
 struct TaCfg {
+    // Two decoupled shared-memory rings: RAW (TMA landing tiles [A raw | B raw], R deep) and CONV ([B hi | B lo], C
+    // deep; the matching A hi / A lo live in tensor memory, one 64-column slot per CONV stage).  A RAW slot is handed
+    // back to the TMA producer as soon as the converter warps have read it -- not when the MMAs that consume the converted
+    // copy retire -- so the next loads are in flight a whole K step earlier (the in-place layout left the converters
+    // waiting on TMA for a third of their samples, profiles/r1b).
     static constexpr int A_BYTES = TC_BM * TC_BK * 4;               // raw landing tile of A (16 KB)
     static constexpr int B_BYTES = BN * TC_BK * 4;
-    static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;       // [A raw | B hi | B lo]
-    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128) ? 4 : 6;
-    static constexpr int TMEM_A0 = BN;                              // accumulator in columns [0, BN); A stages after it
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
-    static_assert(BN + STAGES * 64 <= 512, "tensor memory budget");
+    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;             // [A raw | B raw]
+    static constexpr int CONV_BYTES = 2 * B_BYTES;                  // [B hi | B lo]
+    static constexpr int R = (BN == 256) ? 2 : 4;
+    static constexpr int C = (BN == 256) ? 2 : (BN == 128) ? 3 : 4;
+    static constexpr int CONV0 = R * RAW_BYTES;
+    static constexpr int BARS0 = CONV0 + C * CONV_BYTES;
+    static constexpr int TMEM_A0 = BN;                              // accumulator in columns [0, BN); A slots after it
+    static constexpr int SMEM = BARS0 + 1024 + 256;
+    static_assert(BN + C * 64 <= 512, "tensor memory budget");
+    static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 constexpr int TA_THREADS = 320;            // producer warp, MMA warp, 8 converter / epilogue warps
@@ -341,14 +351,15 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;
-    auto bar_full = [&](int s) { return bars + 8u * s; };
-    auto bar_ready = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
-    auto bar_empty = [&](int s) { return bars + 8u * (2 * Cfg::STAGES + s); };
-    const uint32_t bar_tmem = bars + 8u * (3 * Cfg::STAGES);
+    const uint32_t bars = base + Cfg::BARS0;
+    auto bar_full = [&](int s) { return bars + 8u * s; };                            // RAW slot landed (TMA tx)
+    auto bar_rawfree = [&](int s) { return bars + 8u * (Cfg::R + s); };              // RAW slot read by all converters
+    auto bar_ready = [&](int s) { return bars + 8u * (2 * Cfg::R + s); };            // CONV slot (+ TMEM A slot) written
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * Cfg::R + Cfg::C + s); };   // CONV slot consumed by the MMAs
+    const uint32_t bar_tmem = bars + 8u * (2 * Cfg::R + 2 * Cfg::C);
     const uint32_t tmem_slot = bar_tmem + 8u;
     volatile uint32_t* tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (3 * Cfg::STAGES) + 8);
+        reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::BARS0 + 8 * (2 * Cfg::R + 2 * Cfg::C) + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_begin = (tri & 4) ? m0 / TC_BK : 0;
@@ -356,8 +367,11 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int kb_end = (k_end + TC_BK - 1) / TC_BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) {
+        for (int s = 0; s < Cfg::R; ++s) {
             mbar_init(bar_full(s), 1);
+            mbar_init(bar_rawfree(s), TA_CONV_THREADS);
+        }
+        for (int s = 0; s < Cfg::C; ++s) {
             mbar_init(bar_ready(s), TA_CONV_THREADS);
             mbar_init(bar_empty(s), 1);
         }
@@ -378,10 +392,10 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
             const int zA = batchA ? (int)blockIdx.z : 0, zB = batchB ? (int)blockIdx.z : 0;
             for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
-                const int s = it % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
-                mbar_wait(bar_empty(s), ph ^ 1u);
-                const uint32_t st = base + s * Cfg::STAGE_BYTES;
+                const int s = it % Cfg::R;
+                const uint32_t ph = (uint32_t)(it / Cfg::R) & 1u;
+                mbar_wait(bar_rawfree(s), ph ^ 1u);
+                const uint32_t st = base + s * Cfg::RAW_BYTES;
                 mbar_expect_tx(bar_full(s), Cfg::A_BYTES + Cfg::B_BYTES);
                 tma_load_3d(st, &tmA, bar_full(s), kb * TC_BK, m0, zA);
                 if (!B_MN) {
@@ -398,11 +412,11 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
-                const int s = it % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
+                const int s = it % Cfg::C;
+                const uint32_t ph = (uint32_t)(it / Cfg::C) & 1u;
                 mbar_wait(bar_ready(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t b_hi = base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+                const uint32_t b_hi = base + Cfg::CONV0 + s * Cfg::CONV_BYTES, b_lo = b_hi + Cfg::B_BYTES;
                 const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::TMEM_A0 + s * 64), a_lo = a_hi + 32u;
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 8; ++kk) {
@@ -431,10 +445,12 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int row = q * 32 + lane;           // row of the A tile this thread splits
         constexpr int VECB = Cfg::B_BYTES / 16;
         for (int kb = kb_begin, it = 0; kb < kb_end; ++kb, ++it) {
-            const int s = it % Cfg::STAGES;
-            const uint32_t ph = (uint32_t)(it / Cfg::STAGES) & 1u;
-            mbar_wait(bar_full(s), ph);
-            uint8_t* stage = base_ptr + s * Cfg::STAGE_BYTES;
+            const int rs = it % Cfg::R, s = it % Cfg::C;
+            mbar_wait(bar_full(rs), (uint32_t)(it / Cfg::R) & 1u);
+            mbar_wait(bar_empty(s), ((uint32_t)(it / Cfg::C) & 1u) ^ 1u);      // CONV slot + TMEM A slot free again
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint8_t* stage = base_ptr + rs * Cfg::RAW_BYTES;
+            uint8_t* conv = base_ptr + Cfg::CONV0 + s * Cfg::CONV_BYTES;
             // A: this thread's 128-byte row (16-byte chunk c of row r sits at chunk c ^ (r & 7): 128B swizzle)
             if (a_warp) {
                 uint32_t hi[32], lo[32];
@@ -452,12 +468,13 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tmem_st32(ta, hi);
                 tmem_st32(ta + 32u, lo);
             }
-            // B: position-preserving split (hi in place, lo to the second buffer)
-            float4* bh = reinterpret_cast<float4*>(stage + Cfg::A_BYTES);
-            float4* bl = reinterpret_cast<float4*>(stage + Cfg::A_BYTES + Cfg::B_BYTES);
+            // B: position-preserving split of the raw tile into the CONV slot (hi | lo)
+            const float4* braw = reinterpret_cast<const float4*>(stage + Cfg::A_BYTES);
+            float4* bh = reinterpret_cast<float4*>(conv);
+            float4* bl = reinterpret_cast<float4*>(conv + Cfg::B_BYTES);
 #pragma unroll 4
             for (int i = t; i < VECB; i += TA_CONV_THREADS) {
-                const float4 x = bh[i];
+                const float4 x = braw[i];
                 float4 h, l;
                 h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
                 l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
@@ -468,6 +485,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(bar_ready(s));
+            mbar_arrive(bar_rawfree(rs));
         }
         mbar_wait(bar_tmem, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
