@@ -229,6 +229,21 @@ int mxf_adam_step(int dtype, void* w, const void* g, void* m, void* v, int64_t n
 int mxf_gather_rows(int dtype, const void* src, int64_t cols, const int64_t* idx, const int64_t* off,
                     int64_t rows, void* out, void* stream);
 
+/* ---- dense-tanh network with sampled weights (FunctionEvaluation.eval over an MXFusionGluonFunction,
+ *      function_evaluation.py:47-99, mxfusion_gluon_function.py:97-111,166-194; BASELINE config 4) ----
+ *   out[s, r, :] = W_L^s tanh( ... tanh(W_1^s x[s|0, r, :] + b_1^s) ... ) + b_L^s     (Dense layout: W (out, in))
+ * replaces the reference's Python loop over the S weight samples (one Gluon forward and one autograd tape each).
+ * n_layers <= 4 dense layers, every width <= 64 (else MXF_ENOTIMPL); widths[0..n_layers] on the host.
+ * W, b, dW, db: HOST arrays of n_layers DEVICE pointers; sW / sb: sample strides in elements (0 = the tensor is shared
+ * by all S samples).  b (and db) may be NULL (no bias).  x: (S|1, B, widths[0]) with sample stride sx (0 = shared).
+ * The adjoint recomputes the forward pass and ADDS into dW / db (caller zeroes them): dW_l^s = sum_r delta_l act_{l-1}^T. */
+int mxf_mlp_tanh_fwd(int dtype, int n_layers, const int* widths, const void* x, int64_t sx,
+                     const void* const* W, const int64_t* sW, const void* const* b, const int64_t* sb,
+                     void* out, int S, int B, void* stream);
+int mxf_mlp_tanh_bwd(int dtype, int n_layers, const int* widths, const void* x, int64_t sx,
+                     const void* const* W, const int64_t* sW, const void* const* b, const int64_t* sb,
+                     const void* gout, void* const* dW, void* const* db, int S, int B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

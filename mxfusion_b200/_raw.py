@@ -389,3 +389,51 @@ def svgp_bwd_assemble(Phi, T, U, mt, v, coef, out=None):
                                       ptr(_c(coef)), ptr(out), out.stride(1), out.stride(0), S, M, P, stream_ptr()),
           'mxf_svgp_bwd_assemble')
     return out
+
+
+def _mlp_pack(x, Ws, bs):
+    import ctypes
+    L = len(Ws)
+    S = max([x.shape[0]] + [w.shape[0] for w in Ws] + [b.shape[0] for b in bs if b is not None])
+    widths = (ctypes.c_int * (L + 1))(*([Ws[0].shape[2]] + [w.shape[1] for w in Ws]))
+    for l in range(L):
+        if Ws[l].shape[2] != widths[l]:
+            raise _lib.MXFusionB200Error("mlp_tanh: layer %d expects %d inputs, got %d" % (l, Ws[l].shape[2], widths[l]))
+    Wp = (ctypes.c_void_p * L)(*[w.data_ptr() for w in Ws])
+    sW = (ctypes.c_int64 * L)(*[_bstride(w, S) for w in Ws])
+    has_b = all(b is not None for b in bs)
+    bp = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bs]) if has_b else None
+    sb = (ctypes.c_int64 * L)(*[_bstride(b, S) for b in bs]) if has_b else None
+    return L, S, widths, Wp, sW, bp, sb
+
+
+def mlp_tanh_fwd(x, Ws, bs):
+    """out (S,B,width_L) of the dense-tanh stack; x (S|1,B,w0), Ws[l] (S|1,out,in), bs[l] (S|1,out) or None."""
+    require_cuda(x, *Ws, *[b for b in bs if b is not None])
+    x = _c(x)
+    Ws = [_c(w) for w in Ws]
+    bs = [None if b is None else _c(b) for b in bs]
+    L, S, widths, Wp, sW, bp, sb = _mlp_pack(x, Ws, bs)
+    B = x.shape[1]
+    out = torch.empty((S, B, widths[L]), dtype=x.dtype, device=x.device)
+    check(lib().mxf_mlp_tanh_fwd(dtype_code(x), L, widths, ptr(x), _bstride(x, S), Wp, sW, bp, sb, ptr(out), S, B,
+                                 stream_ptr()), 'mxf_mlp_tanh_fwd')
+    return out
+
+
+def mlp_tanh_bwd(x, Ws, bs, gout):
+    """Gradients (dWs, dbs) of sum(out * gout), shaped like Ws / bs (a tensor shared by the samples gets the sum)."""
+    import ctypes
+    require_cuda(x, gout, *Ws)
+    x, gout = _c(x), _c(gout)
+    Ws = [_c(w) for w in Ws]
+    bs = [None if b is None else _c(b) for b in bs]
+    L, S, widths, Wp, sW, bp, sb = _mlp_pack(x, Ws, bs)
+    B = x.shape[1]
+    dWs = [torch.zeros_like(w) for w in Ws]
+    dbs = [None if b is None else torch.zeros_like(b) for b in bs]
+    dWp = (ctypes.c_void_p * L)(*[w.data_ptr() for w in dWs])
+    dbp = (ctypes.c_void_p * L)(*[b.data_ptr() for b in dbs]) if bp is not None else None
+    check(lib().mxf_mlp_tanh_bwd(dtype_code(x), L, widths, ptr(x), _bstride(x, S), Wp, sW, bp, sb, ptr(gout), dWp, dbp,
+                                 S, B, stream_ptr()), 'mxf_mlp_tanh_bwd')
+    return dWs, dbs

@@ -478,9 +478,54 @@ def gp_log_pdf(kind, X, Y, noise_var, lengthscale, variance, jitter=0.0, mean=No
 
 
 # --------------------------------------------------------------------------------------------------
+# dense-tanh network with sampled weights (BNN function evaluation)
+# --------------------------------------------------------------------------------------------------
+class _MlpTanh(torch.autograd.Function):
+    """function_evaluation.py:72-96 for a Dense/tanh stack: all S weight samples in one forward launch and one adjoint
+    launch (csrc/mlp.cu).  Inputs: x, then W_1, b_1, ..., W_L, b_L (b_l may be None)."""
+
+    @staticmethod
+    def forward(ctx, n_layers, x, *wb):
+        Ws, bs = list(wb[0::2]), list(wb[1::2])
+        ctx.n_layers = n_layers
+        ctx.has_b = [b is not None for b in bs]
+        ctx.save_for_backward(x, *Ws, *[b for b in bs if b is not None])
+        return R.mlp_tanh_fwd(x, Ws, bs)
+
+    @staticmethod
+    def backward(ctx, gout):
+        L = ctx.n_layers
+        saved = ctx.saved_tensors
+        x, Ws, rest = saved[0], list(saved[1:1 + L]), list(saved[1 + L:])
+        bs = [rest.pop(0) if h else None for h in ctx.has_b]
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("mlp_tanh: gradient with respect to the network input is not implemented")
+        dWs, dbs = R.mlp_tanh_bwd(x, Ws, bs, gout)
+        out = [None, None]
+        for dW, db in zip(dWs, dbs):
+            out += [dW, db]
+        return tuple(out)
+
+
+def mlp_tanh(x, weights, biases):
+    """x (S|1,B,in); weights[l] (S|1,out_l,in_l) (torch.nn.Linear layout); biases[l] (S|1,out_l) or None."""
+    wb = []
+    for W, b in zip(weights, biases):
+        wb += [W, b]
+    return _MlpTanh.apply(len(weights), x, *wb)
+
+
+# --------------------------------------------------------------------------------------------------
 # variational sparse GP (Titsias collapsed bound): streamed whitened statistics
 # --------------------------------------------------------------------------------------------------
-STATS_CHUNK_ROWS = 32768     # rows of X per streamed block: K(Z, X_c) is M x 32768 (128 MB at M = 1024, f32)
+STATS_CHUNK_ROWS = 28672     # rows of X per streamed block (7 x 4096): K(Z, X_c) is M x 28672 (112 MB at M = 1024, f32)
+
+
+def _syrk_splits(M):
+    """K-axis slabs for the M x M syrk of a streamed block so that (lower 128 x 256 tiles) x slabs fills the 148 SMs in
+    one wave."""
+    tiles = sum(i // 2 + 1 for i in range((M + 127) // 128))
+    return max(1, min(8, 148 // tiles))
 
 
 class _WhitenedStats(torch.autograd.Function):
@@ -497,10 +542,20 @@ class _WhitenedStats(torch.autograd.Function):
         pack = R.tri_pack(L)
         Phi = torch.zeros((S, M, M), dtype=X.dtype, device=X.device)
         b = torch.zeros((S, M, P), dtype=X.dtype, device=X.device)
+        G = _syrk_splits(M) if S == 1 else 1
+        parts = torch.zeros((G, M, M), dtype=X.dtype, device=X.device) if G > 1 else None
         for c0 in range(0, N, chunk):
             Xc, Yc = X[:, c0:c0 + chunk], Y[:, c0:c0 + chunk]
             A = R.trsm_solve(L, pack, R.kbuild_fwd(kind, Z, Xc, ls, var))       # :77, :81 on this block
-            R.gemm(A, A, transB=True, beta=1.0, C=Phi, tri=True)                # :84 syrk(LinvKuf), lower tiles
+            Bc = A.shape[2]
+            if G > 1 and Bc % (4 * G) == 0 and A.is_contiguous():
+                # :84 syrk(LinvKuf): M x M x Bc has too few output tiles for 148 SMs -> split the K axis into G slabs
+                # (a batched GEMM over strided views of the same buffer), then add the G partial lower triangles
+                Av = A.as_strided((G, M, Bc // G), (Bc // G, Bc, 1))
+                R.gemm(Av, Av, transB=True, beta=0.0, C=parts, tri=True)
+                Phi += parts.sum(dim=0, keepdim=True)
+            else:
+                R.gemm(A, A, transB=True, beta=1.0, C=Phi, tri=True)            # lower tiles only
             R.gemm(A, Yc.contiguous(), beta=1.0, C=b)                           # :90 gemm2(LinvKuf, Y)
         Phi = R.copy_ltu(Phi)
         ctx.kind, ctx.chunk = kind, chunk

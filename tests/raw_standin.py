@@ -230,3 +230,26 @@ def svgp_bwd_assemble(Phi, T, U, mt, v, coef, out=None):
         out[:, :, :3 * M].copy_(r)
         return out
     return r
+
+
+def _mlp(x, Ws, bs):
+    h = x
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        h = torch.matmul(h, W.transpose(-1, -2))
+        if b is not None:
+            h = h + b.unsqueeze(-2)
+        if l + 1 < len(Ws):
+            h = torch.tanh(h)
+    return h
+
+
+def mlp_tanh_fwd(x, Ws, bs):
+    return _mlp(x, Ws, bs).contiguous()
+
+
+def mlp_tanh_bwd(x, Ws, bs, gout):
+    with torch.enable_grad():
+        Wr = [w.detach().clone().requires_grad_() for w in Ws]
+        br = [None if b is None else b.detach().clone().requires_grad_() for b in bs]
+        (_mlp(x.detach(), Wr, br) * gout).sum().backward()
+    return [w.grad for w in Wr], [None if b is None else b.grad for b in br]

@@ -219,10 +219,10 @@ def test_oracle_sparsegp_matches_reference():
                                        atol=tol(c('kernel'), 1e-9) * 10, err_msg='case %d %s' % (i, k))
 
 
-@pytest.mark.parametrize('chunk_rows', [None, 4])
+@pytest.mark.parametrize('chunk_rows', [None, 4, 32])
 def test_product_sparsegp_fixture_value_gradients_cache_and_prediction(mf, chunk_rows):
-    """The streamed-statistics formulation (chunk_rows=4 forces several blocks, with a ragged last one) against the
-    reference's materialising one."""
+    """The streamed-statistics formulation (chunk_rows=4 forces several blocks, with a ragged last one; 32 takes the
+    split-K syrk path on the N=40 case) against the reference's materialising one."""
     g = gc.load('sparsegp_fixture')
     for i in range(int(g['n_cases'])):
         loss, grads, (wv, L, LA), pred = gc.run_sparsegp_case(mf, g, i, torch.device('cpu'), chunk_rows=chunk_rows)

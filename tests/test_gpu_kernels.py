@@ -442,3 +442,63 @@ def test_kbuild_bwd_without_column_gradient(cuda, kind, ard):
     np.testing.assert_allclose(dX.cpu().numpy(), X.grad.numpy(), rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(dls.cpu().numpy(), ls.grad.numpy(), rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(dvar.cpu().numpy(), var.grad.numpy(), rtol=1e-7, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------- fused dense-tanh network
+MLP_CASES = [
+    # S, Sx, B, widths, bias, shared-first-layer
+    (3, 1, 4096, (1, 50, 50, 1), True, False),       # BASELINE config 4 (bnn_regression.ipynb: H=50, S=3)
+    (1, 1, 100, (3, 7, 2), True, False),
+    (2, 2, 130, (5, 64, 64, 64, 3), True, False),    # 4 dense layers at the width limit, x sampled too
+    (4, 1, 65, (2, 33, 1), False, False),            # no bias, ragged last CTA
+    (3, 1, 200, (4, 16, 2), True, True),             # first layer's weight shared by all samples (stride 0)
+]
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('case', MLP_CASES)
+def test_mlp_tanh_forward_and_adjoint(cuda, prec, case):
+    """csrc/mlp.cu against the per-sample loop of the reference (oracle/mlp.py) and autograd of a float64 torch
+    restatement for the weight / bias gradients."""
+    from mxfusion_b200 import ops
+    from oracle import mlp as omlp
+    S, Sx, B, widths, bias, shared0 = case
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(len(widths) * 100 + B)
+    x = rng.uniform(-1, 1, (Sx, B, widths[0]))
+    Ws = [rng.randn(1 if (shared0 and l == 0) else S, widths[l + 1], widths[l]) / np.sqrt(widths[l]) for l in range(len(widths) - 1)]
+    bs = [rng.randn(1 if (shared0 and l == 0) else S, widths[l + 1]) * 0.3 if bias else None for l in range(len(widths) - 1)]
+    gout = rng.randn(S, B, widths[-1])
+    tW = [T(w, cuda, tdt).requires_grad_() for w in Ws]
+    tb = [None if b is None else T(b, cuda, tdt).requires_grad_() for b in bs]
+    out = ops.mlp_tanh(T(x, cuda, tdt), tW, tb)
+    want = omlp.mlp_tanh(x, Ws, bs)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want, rtol=rtol, atol=atol * 10)
+    (out * T(gout, cuda, tdt)).sum().backward()
+    rW = [torch.tensor(w, requires_grad=True) for w in Ws]
+    rb = [None if b is None else torch.tensor(b, requires_grad=True) for b in bs]
+    h = torch.tensor(x)
+    for l in range(len(Ws)):
+        h = torch.matmul(h, rW[l].transpose(-1, -2))
+        if rb[l] is not None:
+            h = h + rb[l].unsqueeze(-2)
+        if l + 1 < len(Ws):
+            h = torch.tanh(h)
+    (h * torch.tensor(gout)).sum().backward()
+    gt = 1e-9 if prec == 'f64' else 2e-4
+    for l in range(len(Ws)):
+        w = rW[l].grad.numpy()
+        g = tW[l].grad.double().cpu().numpy()
+        assert np.max(np.abs(g - w)) <= gt * (1.0 + np.max(np.abs(w))), ('W', l, np.max(np.abs(g - w)))
+        if bias:
+            w = rb[l].grad.numpy()
+            g = tb[l].grad.double().cpu().numpy()
+            assert np.max(np.abs(g - w)) <= gt * (1.0 + np.max(np.abs(w))), ('b', l, np.max(np.abs(g - w)))
+
+
+def test_mlp_tanh_rejects_wide_layers(cuda):
+    from mxfusion_b200 import _raw, _lib
+    x = torch.zeros((1, 8, 65), device=cuda)
+    W = [torch.zeros((1, 4, 65), device=cuda)]
+    with pytest.raises(_lib.MXFusionB200Error):
+        _raw.mlp_tanh_fwd(x, W, [None])
