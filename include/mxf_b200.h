@@ -209,10 +209,12 @@ int mxf_normal_logpdf_sum_bwd(int dtype, const void* x, int64_t sX, const void* 
                               const void* gout, void* gx, void* gm, void* gv, void* stream);
 /* Reparameterised draw (normal.py:89-92): w[s][i] = eps[s][i]*sqrt(v[i]) + m[i].
  * If eps == NULL a counter-based Philox4x32-10 standard-normal stream keyed by
- * (seed, offset) is generated in-kernel and, if eps_out != NULL, stored for the adjoint. */
+ * (seed, offset) is generated in-kernel and, if eps_out != NULL, stored for the adjoint.
+ * step_counter (device int32[1] or NULL): its value is added to the high word of the Philox counter at run time, so
+ * a launch replayed from a CUDA graph draws fresh noise every optimiser step (pass the counter mxf_adam_step bumps). */
 int mxf_normal_reparam(int dtype, const void* eps, const void* m, int64_t sM, const void* v, int64_t sV,
-                       int S, int64_t n, uint64_t seed, uint64_t offset,
-                       void* w, void* eps_out, void* stream);
+                       int S, int64_t n, uint64_t seed, uint64_t offset, const int* step_counter, void* w,
+                       void* eps_out, void* stream);
 
 /* ---- optimiser (mx.gluon.Trainer('adam').step(batch_size), minibatch_loop.py:71-91) ----
  * One fused update over a flat parameter bucket:

@@ -55,7 +55,7 @@ def _declare(lib):
         'mxf_svgp_bwd_assemble': (i, [i, p, p, p, p, p, p, p, l, l, i, i, i, p]),
         'mxf_normal_logpdf_sum': (i, [i, p, l, p, l, p, l, i, l, d, p, p]),
         'mxf_normal_logpdf_sum_bwd': (i, [i, p, l, p, l, p, l, i, l, d, p, p, p, p, p]),
-        'mxf_normal_reparam': (i, [i, p, p, l, p, l, i, l, u, u, p, p, p]),
+        'mxf_normal_reparam': (i, [i, p, p, l, p, l, i, l, u, u, p, p, p, p]),
         'mxf_adam_step': (i, [i, p, p, p, p, l, d, d, d, d, d, p, p]),
         'mxf_gather_rows': (i, [i, p, l, p, p, l, p, p]),
         'mxf_mlp_tanh_fwd': (i, [i, i, p, p, l, p, p, p, p, p, i, i, p]),

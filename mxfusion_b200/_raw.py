@@ -297,7 +297,7 @@ def normal_logpdf_sum_bwd(x, m, v, gout, scale=1.0, need=(True, True, True)):
             None if gv is None else gv.reshape(vs))
 
 
-def normal_reparam(m, v, S, eps=None, seed=0, offset=0, return_eps=False):
+def normal_reparam(m, v, S, eps=None, seed=0, offset=0, return_eps=False, step_counter=None):
     """w (S, *shape) = eps*sqrt(v)+m; m, v carry a leading axis of 1 or S."""
     require_cuda(m, v, eps)
     shape = m.shape[1:]
@@ -310,7 +310,7 @@ def normal_reparam(m, v, S, eps=None, seed=0, offset=0, return_eps=False):
     elif return_eps:
         eps_out = torch.empty_like(w)
     check(lib().mxf_normal_reparam(dtype_code(m), ptr(eps), ptr(mf), _bstride(mf, S), ptr(vf), _bstride(vf, S),
-                                   S, n, int(seed), int(offset), ptr(w), ptr(eps_out), stream_ptr()),
+                                   S, n, int(seed), int(offset), ptr(step_counter), ptr(w), ptr(eps_out), stream_ptr()),
           'mxf_normal_reparam')
     w = w.reshape((S,) + tuple(shape))
     if return_eps:

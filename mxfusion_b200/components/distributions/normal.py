@@ -44,8 +44,10 @@ class Normal(Distribution):
             if tuple(variance.shape[1:]) != tuple(rv_shape) else variance
         gen = self._rand_gen
         if getattr(gen, 'in_kernel', False):
+            from .random_gen import step_counter
             seed, offset = gen.next_stream()
-            return ops.normal_draw(mean, variance, num_samples, seed=seed, offset=offset)
+            return ops.normal_draw(mean, variance, num_samples, seed=seed, offset=offset,
+                                   step_counter=step_counter(mean.device))
         eps = gen.sample_normal(shape=full, dtype=self.dtype, ctx=self.ctx)
         return ops.normal_draw(mean, variance, num_samples, eps=eps)
 

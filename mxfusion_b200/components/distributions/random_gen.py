@@ -8,6 +8,20 @@ import torch
 
 _COUNTER = itertools.count(1)
 _SEED = [0]
+_STEP_COUNTER = [None]       # device int32[1] bumped once per optimiser step (InferenceParameters.adam_t)
+
+
+def set_step_counter(t):
+    """Registers the optimiser's device step counter: in-kernel draws mix it into their Philox counter at run time,
+    so a draw captured in a CUDA graph (inference/_stepper.py) is different on every replayed step."""
+    _STEP_COUNTER[0] = t
+
+
+def step_counter(device=None):
+    t = _STEP_COUNTER[0]
+    if t is None or (device is not None and t.device != torch.device(device)):
+        return None
+    return t
 
 
 def seed(value):

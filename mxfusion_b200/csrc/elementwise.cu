@@ -269,8 +269,11 @@ __device__ __forceinline__ void philox4x32_10(uint64_t idx, uint64_t offset, uin
 template <typename T>
 __global__ void __launch_bounds__(256)
 normal_reparam_kernel(const T* __restrict__ eps, const T* __restrict__ m, int64_t sM, const T* __restrict__ v,
-                      int64_t sV, int S, int64_t n, uint64_t seed, uint64_t offset, T* __restrict__ w,
-                      T* __restrict__ eps_out) {
+                      int64_t sV, int S, int64_t n, uint64_t seed, uint64_t offset, const int* __restrict__ step_counter,
+                      T* __restrict__ w, T* __restrict__ eps_out) {
+    // A launch captured in a CUDA graph replays with the SAME host-side (seed, offset): the optimiser's device step
+    // counter goes into the high word of the Philox counter so that every replayed step draws fresh noise.
+    if (step_counter) offset += (uint64_t)(uint32_t)(*step_counter) << 32;
     const int64_t total = (int64_t)S * n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     if (eps) {
@@ -487,13 +490,13 @@ extern "C" int mxf_normal_logpdf_sum_bwd(int dtype, const void* x, int64_t sX, c
 }
 
 extern "C" int mxf_normal_reparam(int dtype, const void* eps, const void* m, int64_t sM, const void* v, int64_t sV,
-                                  int S, int64_t n, uint64_t seed, uint64_t offset, void* w, void* eps_out,
-                                  void* stream) {
+                                  int S, int64_t n, uint64_t seed, uint64_t offset, const int* step_counter, void* w,
+                                  void* eps_out, void* stream) {
     if (!m || !v || !w || S <= 0 || n < 0) return MXF_EINVAL;
     if (n == 0) return MXF_OK;
     MXF_DISPATCH_DTYPE(dtype, normal_reparam_kernel<T><<<grid_for((int64_t)S * n), 256, 0, (cudaStream_t)stream>>>(
-                                  (const T*)eps, (const T*)m, sM, (const T*)v, sV, S, n, seed, offset, (T*)w,
-                                  (T*)eps_out));
+                                  (const T*)eps, (const T*)m, sM, (const T*)v, sV, S, n, seed, offset, step_counter,
+                                  (T*)w, (T*)eps_out));
     return after_launch();
 }
 

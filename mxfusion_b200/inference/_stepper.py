@@ -23,6 +23,8 @@ class Stepper(object):
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rescale = float(rescale_grad) / self.world          # all-reduce(SUM) / world = average over ranks
         params.refresh_leaves()
+        from ..components.distributions import random_gen
+        random_gen.set_step_counter(params.adam_t if params.adam_t.is_cuda else None)
         self.static_in = [torch.empty_like(b) for b in example_batch]
         self.loss = None
         self.graph = None

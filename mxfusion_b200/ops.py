@@ -227,8 +227,9 @@ def normal_log_pdf_sum(x, mean, variance, scale=1.0):
 
 class _NormalReparam(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, m, v, S, eps, seed, offset):
-        w, e = R.normal_reparam(m, v, S, eps=eps, seed=seed, offset=offset, return_eps=True)
+    def forward(ctx, m, v, S, eps, seed, offset, step_counter):
+        w, e = R.normal_reparam(m, v, S, eps=eps, seed=seed, offset=offset, return_eps=True,
+                                step_counter=step_counter)
         ctx.save_for_backward(e, v)
         ctx.mS, ctx.vS = m.shape[0], v.shape[0]
         return w
@@ -241,12 +242,14 @@ class _NormalReparam(torch.autograd.Function):
         gv = gw * e * (0.5 / torch.sqrt(v))
         if ctx.vS != gv.shape[0]:
             gv = gv.sum(dim=0, keepdim=True)
-        return gm, gv, None, None, None, None
+        return gm, gv, None, None, None, None, None
 
 
-def normal_draw(mean, variance, num_samples, eps=None, seed=0, offset=0):
-    """Reparameterised draw eps*sqrt(v)+mu (normal.py:89-92); eps injected or Philox-generated in-kernel."""
-    return _NormalReparam.apply(mean, variance, int(num_samples), eps, int(seed), int(offset))
+def normal_draw(mean, variance, num_samples, eps=None, seed=0, offset=0, step_counter=None):
+    """Reparameterised draw eps*sqrt(v)+mu (normal.py:89-92); eps injected or Philox-generated in-kernel.
+    `step_counter` (device int32[1]) is mixed into the Philox counter at run time: a draw replayed from a CUDA graph
+    sees fresh noise every optimiser step."""
+    return _NormalReparam.apply(mean, variance, int(num_samples), eps, int(seed), int(offset), step_counter)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -168,7 +168,7 @@ def normal_logpdf_sum_bwd(x, m, v, gout, scale=1.0, need=(True, True, True)):
     return (xr.grad if need[0] else None, mr.grad if need[1] else None, vr.grad if need[2] else None)
 
 
-def normal_reparam(m, v, S, eps=None, seed=0, offset=0, return_eps=False):
+def normal_reparam(m, v, S, eps=None, seed=0, offset=0, return_eps=False, step_counter=None):
     shape = (S,) + tuple(m.shape[1:])
     if eps is None:
         g = torch.Generator().manual_seed(int(seed) * 1000003 + int(offset))

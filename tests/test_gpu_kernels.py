@@ -502,3 +502,34 @@ def test_mlp_tanh_rejects_wide_layers(cuda):
     W = [torch.zeros((1, 4, 65), device=cuda)]
     with pytest.raises(_lib.MXFusionB200Error):
         _raw.mlp_tanh_fwd(x, W, [None])
+
+
+def test_reparam_draw_is_fresh_on_every_graph_replay(cuda):
+    """The in-kernel Philox stream is keyed by host scalars, which a CUDA graph freezes at capture time; the device step
+    counter (bumped by the fused Adam kernel) is mixed into the counter at run time so that every replayed optimiser
+    step draws new noise, while a replay at the same step reproduces the draw."""
+    from mxfusion_b200 import _raw
+    m = torch.zeros((1, 4096), device=cuda)
+    v = torch.ones((1, 4096), device=cuda)
+    ctr = torch.zeros((1,), dtype=torch.int32, device=cuda)
+    _raw.normal_reparam(m, v, 3, seed=7, offset=5, step_counter=ctr)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        w = _raw.normal_reparam(m, v, 3, seed=7, offset=5, step_counter=ctr)
+    outs = []
+    for step in (0, 1, 1, 2):
+        ctr.fill_(step)
+        g.replay()
+        outs.append(w.clone())
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[3])
+    assert torch.equal(outs[1], outs[2])
+    eager = _raw.normal_reparam(m, v, 3, seed=7, offset=5, step_counter=ctr)
+    assert torch.equal(eager, outs[3])
+    z = torch.cat([o.flatten() for o in outs])
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02
+    # without a counter the stream is the plain (seed, offset) one
+    a = _raw.normal_reparam(m, v, 3, seed=7, offset=5)
+    ctr.zero_()
+    b = _raw.normal_reparam(m, v, 3, seed=7, offset=5, step_counter=ctr)
+    assert torch.equal(a, b)
