@@ -207,6 +207,83 @@ gemm_skinny_n_kernel(int transB, int m, int n, int k, T alpha, const T* __restri
     }
 }
 
+// Long-k variant (k >= 4096, e.g. b += L^-1 K(Z, X_c) Y_c over a streamed block of 28k rows): a CTA owns 4 output rows and
+// all 256 threads stride over k with 16-byte loads, 4 rows x 2 unrolled steps = 8 independent loads in flight per thread,
+// so the pass over A runs at memory speed instead of on one warp's load latency chain.  Requires lda % 4 == 0 and A
+// 16-byte aligned (fp32); B is read through the read-only path (it is re-read by every CTA and stays in L1/L2).
+template <int NCOL>
+__global__ void __launch_bounds__(256)
+gemm_skinny_longk_kernel(int transB, int m, int n, int k, float alpha, const float* __restrict__ A, int64_t lda, int64_t sA,
+                         const float* __restrict__ B, int64_t ldb, int64_t sB, float beta, float* __restrict__ C,
+                         int64_t ldc, int64_t sC) {
+    constexpr int RPC = 4;
+    __shared__ float part[8][RPC][NCOL];
+    const int s = blockIdx.y;
+    A += (int64_t)s * sA; B += (int64_t)s * sB; C += (int64_t)s * sC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * RPC;
+    float acc[RPC][NCOL];
+#pragma unroll
+    for (int r = 0; r < RPC; ++r)
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) acc[r][j] = 0.f;
+    const float* arow[RPC];
+#pragma unroll
+    for (int r = 0; r < RPC; ++r) arow[r] = A + (int64_t)min(i0 + r, m - 1) * lda;
+    const int k4 = k & ~3;
+#pragma unroll 2
+    for (int kk = threadIdx.x * 4; kk < k4; kk += 1024) {
+        float4 a[RPC];
+#pragma unroll
+        for (int r = 0; r < RPC; ++r) a[r] = __ldcs(reinterpret_cast<const float4*>(arow[r] + kk));
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            if (j < n) {
+                float b0, b1, b2, b3;
+                if (transB) {
+                    const float* bp = B + (int64_t)j * ldb + kk;
+                    b0 = __ldg(bp); b1 = __ldg(bp + 1); b2 = __ldg(bp + 2); b3 = __ldg(bp + 3);
+                } else {
+                    const float* bp = B + (int64_t)kk * ldb + j;
+                    b0 = __ldg(bp); b1 = __ldg(bp + ldb); b2 = __ldg(bp + 2 * ldb); b3 = __ldg(bp + 3 * ldb);
+                }
+#pragma unroll
+                for (int r = 0; r < RPC; ++r)
+                    acc[r][j] = fmaf(a[r].x, b0, fmaf(a[r].y, b1, fmaf(a[r].z, b2, fmaf(a[r].w, b3, acc[r][j]))));
+            }
+        }
+    }
+    for (int kk = k4 + threadIdx.x; kk < k; kk += 256) {           // tail (k % 4 elements)
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (j < n) {
+                const float b = transB ? B[(int64_t)j * ldb + kk] : B[(int64_t)kk * ldb + j];
+#pragma unroll
+                for (int r = 0; r < RPC; ++r) acc[r][j] = fmaf(arow[r][kk], b, acc[r][j]);
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < RPC; ++r)
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const float v = warp_sum(acc[r][j]);
+            if (lane == 0) part[warp][r][j] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < RPC * NCOL) {
+        const int r = threadIdx.x / NCOL, j = threadIdx.x - r * NCOL;
+        if (i0 + r < m && j < n) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += part[w][r][j];
+            float* dst = C + (int64_t)(i0 + r) * ldc + j;
+            float v = alpha * t;
+            if (beta != 0.f) v = fmaf(beta, *dst, v);
+            *dst = v;
+        }
+    }
+}
+
 template <typename T, int NCOL>
 __global__ void __launch_bounds__(256)
 gemm_skinny_t_kernel(int transB, int m, int n, int k, T alpha, const T* __restrict__ A, int64_t lda, int64_t sA,
@@ -274,6 +351,15 @@ template <typename T>
 static int gemm_skinny(int transA, int transB, int m, int n, int k, double alpha, const T* A, int64_t lda, int64_t sA,
                        const T* B, int64_t ldb, int64_t sB, double beta, T* C, int64_t ldc, int64_t sC, int S,
                        cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        if (!transA && k >= 4096 && (lda & 3) == 0 && (sA & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+            dim3 grid(cdiv(m, 4), S);
+            if (n <= 1) gemm_skinny_longk_kernel<1><<<grid, 256, 0, st>>>(transB, m, n, k, (float)alpha, A, lda, sA, B, ldb, sB, (float)beta, C, ldc, sC);
+            else if (n <= 4) gemm_skinny_longk_kernel<4><<<grid, 256, 0, st>>>(transB, m, n, k, (float)alpha, A, lda, sA, B, ldb, sB, (float)beta, C, ldc, sC);
+            else gemm_skinny_longk_kernel<8><<<grid, 256, 0, st>>>(transB, m, n, k, (float)alpha, A, lda, sA, B, ldb, sB, (float)beta, C, ldc, sC);
+            return after_launch();
+        }
+    }
     if (!transA) {
         dim3 grid(cdiv(m, 8), S);
         if (n <= 1) gemm_skinny_n_kernel<T, 1><<<grid, 256, 0, st>>>(transB, m, n, k, (T)alpha, A, lda, sA, B, ldb, sB, (T)beta, C, ldc, sC);

@@ -521,7 +521,16 @@ def mlp_tanh(x, weights, biases):
 # --------------------------------------------------------------------------------------------------
 # variational sparse GP (Titsias collapsed bound): streamed whitened statistics
 # --------------------------------------------------------------------------------------------------
-STATS_CHUNK_ROWS = 28672     # rows of X per streamed block (7 x 4096): K(Z, X_c) is M x 28672 (112 MB at M = 1024, f32)
+STATS_CHUNK_ROWS = 28672     # upper bound on the rows of X per streamed block: K(Z, X_c) is M x 28k (~115 MB at M = 1024)
+
+
+def _stats_chunk(M, S):
+    """Rows per streamed block: the block's GEMMs tile its columns 256 wide, 4 row tiles per 512-row solve step, so a
+    column-tile count that is a multiple of 37 makes every GEMM of the block a whole number of waves on 148 SMs
+    (28672 rows = 448 CTAs = 3.03 waves; 28392 rows = 444 CTAs = 3 waves); also divisible into the syrk's K slabs."""
+    G = _syrk_splits(M) if S == 1 else 1
+    tiles = max(37, (STATS_CHUNK_ROWS // 256) // 37 * 37)
+    return (tiles * 256) // (4 * G) * (4 * G)
 
 
 def _syrk_splits(M):
@@ -601,7 +610,7 @@ class _WhitenedStats(torch.autograd.Function):
 def whitened_stats(kind, X, Y, Z, lengthscale, variance, L, chunk=None):
     S = _lead(X, Y, Z, lengthscale, variance, L)
     args = [_expand(t, S).contiguous() for t in (X, Y, Z, lengthscale, variance, L)]
-    return _WhitenedStats.apply(kind, int(chunk or STATS_CHUNK_ROWS), *args)
+    return _WhitenedStats.apply(kind, int(chunk or _stats_chunk(Z.shape[-2], S)), *args)
 
 
 def sparsegp_log_pdf(kind, X, Y, Z, noise_var, lengthscale, variance, jitter=0.0, mean=None, chunk=None):

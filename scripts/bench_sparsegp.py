@@ -79,7 +79,7 @@ def run_cpu(n_sample=32768):
 
 
 out = dict(workload='SparseGPRegression full batch N=%d M=%d D=%d RBF f32, bound + gradient' % (N, M, D),
-           chunk_rows=CHUNK or ops.STATS_CHUNK_ROWS)
+           chunk_rows=CHUNK or ops._stats_chunk(M, 1))
 out.update(run_gpu())
 # algorithmic work of the streamed statistics: K-build N*M, trsm M^2 N, syrk M^2 N (lower half), fwd; bwd ~ 3x
 out['fwd_gflop'] = (2.0 * M * M * N) / 1e9

@@ -533,3 +533,24 @@ def test_reparam_draw_is_fresh_on_every_graph_replay(cuda):
     ctr.zero_()
     b = _raw.normal_reparam(m, v, 3, seed=7, offset=5, step_counter=ctr)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('shape', [(1000, 1, 5000, 5000, False), (1024, 1, 28392, 28392, False), (130, 3, 4099, 4100, False),
+                                   (64, 8, 8192, 8192, True), (5, 4, 4096, 4096, False)])
+def test_gemm_skinny_long_k(cuda, shape):
+    """The long-k matrix-vector kernel (b += L^-1 K(Z, X_c) Y_c of the streamed sparse-GP statistics) against float64,
+    including a k % 4 tail on a padded leading dimension and beta accumulation."""
+    from mxfusion_b200 import _raw
+    m, n, k, lda, tb = shape
+    rng = np.random.RandomState(k + n)
+    Abuf = rng.randn(1, m, lda).astype(np.float32)
+    Bm = (rng.randn(1, n, k) if tb else rng.randn(1, k, n)).astype(np.float32)
+    C0 = rng.randn(1, m, n).astype(np.float32)
+    A_t = torch.as_tensor(Abuf, device=cuda)[:, :, :k]
+    C = torch.as_tensor(C0.copy(), device=cuda)
+    _raw.gemm(A_t, torch.as_tensor(Bm, device=cuda), False, tb, alpha=0.5, beta=1.0, C=C)
+    A64, B64 = Abuf[:, :, :k].astype(np.float64), Bm.astype(np.float64)
+    Bop = np.swapaxes(B64, -1, -2) if tb else B64
+    want = 0.5 * (A64 @ Bop) + C0
+    bound = 2e-6 * (np.abs(A64) @ np.abs(Bop) + np.abs(C0)) + 1e-6
+    assert np.all(np.abs(C.cpu().numpy() - want) <= bound)
