@@ -532,6 +532,269 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent variant of the TMEM-A kernel: one CTA per SM walks a static list of 128 x 128 output tiles; the FP32
+// accumulator is double-buffered in tensor memory (2 x 128 columns) and a dedicated group of four epilogue warps drains
+// tile j (tcgen05.ld -> alpha / beta -> global) while the TMA producer, the converter warps and the MMA thread are
+// already running the K loop of tile j + 1.  The one-tile-per-CTA kernels above pay barrier / TMEM set-up, the pipeline
+// fill and the whole epilogue once per tile with nothing overlapped -- with K = 512 (potrf / trsm updates) that is as long
+// as the K loop itself (profiles/r1b: 35 % tensor-pipe activity at K = 512 against 69 % at K = 4096).
+// Converter warps work in two groups of four that take alternate K steps, so each group has two MMA periods
+// (2 x 768 cycles at BN = 128) for the load -> split -> tcgen05.st / st.shared -> fence chain of its step.
+// ------------------------------------------------------------------------------------------------
+struct PeCfg {
+    static constexpr int BN = 128;
+    static constexpr int A_BYTES = TC_BM * TC_BK * 4;               // 16 KB
+    static constexpr int B_BYTES = BN * TC_BK * 4;                  // 16 KB
+    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
+    static constexpr int CONV_BYTES = 2 * B_BYTES;
+    static constexpr int R = 4;
+    static constexpr int C = 3;
+    static constexpr int CONV0 = R * RAW_BYTES;
+    static constexpr int BARS0 = CONV0 + C * CONV_BYTES;
+    static constexpr int TMEM_A0 = 2 * BN;                          // accumulators in columns [0, 256); A slots after
+    static constexpr int SMEM = BARS0 + 1024 + 256;
+    static constexpr int THREADS = 448;                             // producer, MMA, 8 converter, 4 epilogue warps
+    static constexpr int GROUP_THREADS = 128;                       // one converter group
+    static_assert(2 * BN + C * 64 <= 512, "tensor memory budget");
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <bool B_MN>
+__global__ void __launch_bounds__(PeCfg::THREADS, 1)
+gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  float* __restrict__ C, int64_t ldc, int64_t sC, int m, int n, int k, float alpha, float beta,
+                  int tri, int batchA, int batchB, int tiles_m, int tiles_n, int S) {
+    using Cfg = PeCfg;
+    constexpr int BN = Cfg::BN;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + Cfg::BARS0;
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_rawfree = [&](int s) { return bars + 8u * (Cfg::R + s); };
+    auto bar_ready = [&](int s) { return bars + 8u * (2 * Cfg::R + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * Cfg::R + Cfg::C + s); };
+    auto bar_accfull = [&](int s) { return bars + 8u * (2 * Cfg::R + 2 * Cfg::C + s); };
+    auto bar_accfree = [&](int s) { return bars + 8u * (2 * Cfg::R + 2 * Cfg::C + 2 + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * Cfg::R + 2 * Cfg::C + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::BARS0 + 8 * (2 * Cfg::R + 2 * Cfg::C + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::R; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_rawfree(s), Cfg::GROUP_THREADS);
+        }
+        for (int s = 0; s < Cfg::C; ++s) {
+            mbar_init(bar_ready(s), Cfg::GROUP_THREADS);
+            mbar_init(bar_empty(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_accfull(s), 1);
+            mbar_init(bar_accfree(s), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int tiles_per_batch = tiles_m * tiles_n;
+    const int total_tiles = tiles_per_batch * S;
+    // every role walks the same tile list; `tile_of` decodes tile t and returns false for tiles that are skipped
+    auto tile_of = [&](int t, int& z, int& m0, int& n0, int& kb_begin, int& kb_end) -> bool {
+        z = t / tiles_per_batch;
+        const int r = t - z * tiles_per_batch;
+        const int tm = r / tiles_n, tn = r - tm * tiles_n;
+        m0 = tm * TC_BM;
+        n0 = tn * BN;
+        if ((tri & 1) && n0 > m0 + TC_BM - 1) return false;
+        kb_begin = (tri & 4) ? m0 / TC_BK : 0;
+        const int k_end = (tri & 2) ? min(k, m0 + TC_BM) : k;
+        kb_end = (k_end + TC_BK - 1) / TC_BK;
+        return kb_end > kb_begin;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int z, m0, n0, kb0, kb1;
+                if (!tile_of(t, z, m0, n0, kb0, kb1)) continue;
+                const int zA = batchA ? z : 0, zB = batchB ? z : 0;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % Cfg::R;
+                    mbar_wait(bar_rawfree(s), ((uint32_t)(it / Cfg::R) & 1u) ^ 1u);
+                    const uint32_t st = base + s * Cfg::RAW_BYTES;
+                    mbar_expect_tx(bar_full(s), Cfg::A_BYTES + Cfg::B_BYTES);
+                    tma_load_3d(st, &tmA, bar_full(s), kb * TC_BK, m0, zA);
+                    if (!B_MN) {
+                        tma_load_3d(st + Cfg::A_BYTES, &tmB, bar_full(s), kb * TC_BK, n0, zB);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BN / 32; ++c)
+                            tma_load_3d(st + Cfg::A_BYTES + c * (TC_BK * 128), &tmB, bar_full(s), n0 + c * 32, kb * TC_BK, zB);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int it = 0, j = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int z, m0, n0, kb0, kb1;
+                if (!tile_of(t, z, m0, n0, kb0, kb1)) continue;
+                const int as = j & 1;
+                mbar_wait(bar_accfree(as), ((uint32_t)(j >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % Cfg::C;
+                    mbar_wait(bar_ready(s), (uint32_t)(it / Cfg::C) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t b_hi = base + Cfg::CONV0 + s * Cfg::CONV_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+                    const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::TMEM_A0 + s * 64), a_lo = a_hi + 32u;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        uint64_t dbh, dbl;
+                        if (!B_MN) {
+                            dbh = smem_desc(b_hi + kk * 32, 16, 1024);
+                            dbl = smem_desc(b_lo + kk * 32, 16, 1024);
+                        } else {
+                            dbh = smem_desc(b_hi + kk * 1024, TC_BK * 128, 512, 1);
+                            dbl = smem_desc(b_lo + kk * 1024, TC_BK * 128, 512, 1);
+                        }
+                        umma_tf32_ts(tmem_d, a_lo + kk * 8, dbh, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+                        umma_tf32_ts(tmem_d, a_hi + kk * 8, dbl, idesc, 1);
+                        umma_tf32_ts(tmem_d, a_hi + kk * 8, dbh, idesc, 1);
+                    }
+                    umma_commit(bar_empty(s));
+                }
+                umma_commit(bar_accfull(as));
+                ++j;
+            }
+        }
+    } else if (warp < 10) {
+        // ------------------------------------------------------------------ converters: two groups, alternate K steps
+        const int grp = (warp - 2) >> 2;                       // 0: warps 2..5, 1: warps 6..9
+        const int tg = threadIdx.x - 64 - grp * Cfg::GROUP_THREADS;   // 0..127 within the group
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                         // row of the A tile this thread splits
+        constexpr int VECB = Cfg::B_BYTES / 16;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int z, m0, n0, kb0, kb1;
+            if (!tile_of(t, z, m0, n0, kb0, kb1)) continue;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                if ((it & 1) != grp) continue;
+                const int rs = it % Cfg::R, s = it % Cfg::C;
+                mbar_wait(bar_full(rs), (uint32_t)(it / Cfg::R) & 1u);
+                mbar_wait(bar_empty(s), ((uint32_t)(it / Cfg::C) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint8_t* stage = base_ptr + rs * Cfg::RAW_BYTES;
+                uint8_t* conv = base_ptr + Cfg::CONV0 + s * Cfg::CONV_BYTES;
+                {
+                    uint32_t hi[32], lo[32];
+                    const uint8_t* arow = stage + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+                        const float h0 = to_tf32(x.x), h1 = to_tf32(x.y), h2 = to_tf32(x.z), h3 = to_tf32(x.w);
+                        hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+                        hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+                        lo[4 * c] = __float_as_uint(to_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(to_tf32(x.y - h1));
+                        lo[4 * c + 2] = __float_as_uint(to_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(to_tf32(x.w - h3));
+                    }
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::TMEM_A0 + s * 64);
+                    tmem_st32(ta, hi);
+                    tmem_st32(ta + 32u, lo);
+                }
+                const float4* braw = reinterpret_cast<const float4*>(stage + Cfg::A_BYTES);
+                float4* bh = reinterpret_cast<float4*>(conv);
+                float4* bl = reinterpret_cast<float4*>(conv + Cfg::B_BYTES);
+#pragma unroll 4
+                for (int i = tg; i < VECB; i += Cfg::GROUP_THREADS) {
+                    const float4 x = braw[i];
+                    float4 h, l;
+                    h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+                    l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+                    bh[i] = h;
+                    bl[i] = l;
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(bar_ready(s));
+                mbar_arrive(bar_rawfree(rs));
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps (10..13)
+        const int q = warp & 3;
+        const bool vec_ok = ((ldc & 3) == 0) && ((sC & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        int j = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int z, m0, n0, kb0, kb1;
+            if (!tile_of(t, z, m0, n0, kb0, kb1)) continue;
+            const int as = j & 1;
+            mbar_wait(bar_accfull(as), (uint32_t)(j >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int orow = m0 + q * 32 + lane;
+            float* Cb = C + (int64_t)z * sC;
+#pragma unroll 1
+            for (int jj = 0; jj < BN / 32; ++jj) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + jj * 32), v);
+                if (orow < m) {
+                    float* crow = Cb + (int64_t)orow * ldc;
+                    const int c0 = n0 + jj * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        const int c = c0 + e;
+                        if (c >= n) break;
+                        float o0 = alpha * __uint_as_float(v[e]), o1 = alpha * __uint_as_float(v[e + 1]);
+                        float o2 = alpha * __uint_as_float(v[e + 2]), o3 = alpha * __uint_as_float(v[e + 3]);
+                        if (vec_ok && c + 3 < n) {
+                            float4* dst = reinterpret_cast<float4*>(crow + c);
+                            if (beta != 0.f) {
+                                const float4 old = *dst;
+                                o0 = fmaf(beta, old.x, o0); o1 = fmaf(beta, old.y, o1);
+                                o2 = fmaf(beta, old.z, o2); o3 = fmaf(beta, old.w, o3);
+                            }
+                            *dst = make_float4(o0, o1, o2, o3);
+                        } else {
+                            const float o[4] = {o0, o1, o2, o3};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (c + u < n) crow[c + u] = (beta != 0.f) ? fmaf(beta, crow[c + u], o[u]) : o[u];
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_accfree(as));
+            ++j;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -610,6 +873,29 @@ static int launch_tc_ta(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C
     return after_launch();
 }
 
+template <bool B_MN>
+static int launch_tc_pe(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int64_t ldc, int64_t sC, int m, int n,
+                        int k, float alpha, float beta, int S, int tri, int batchA, int batchB, cudaStream_t st) {
+    auto kern = gemm_tc_pe_kernel<B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PeCfg::SMEM) != cudaSuccess)
+            return (int)cudaGetLastError();
+        attr_set = true;
+    }
+    const int tiles_m = cdiv(m, TC_BM), tiles_n = cdiv(n, PeCfg::BN);
+    const int64_t total = (int64_t)tiles_m * tiles_n * S;
+    const int grid = (int)std::min<int64_t>(total, kNumSMs);
+    kern<<<grid, PeCfg::THREADS, PeCfg::SMEM, st>>>(tmA, tmB, C, ldc, sC, m, n, k, alpha, beta, tri, batchA, batchB, tiles_m,
+                                                    tiles_n, S);
+    return after_launch();
+}
+
+static int pe_mode() {      // 0 = off, 1 = on for problems with more than one wave of 128 x 128 tiles (default)
+    static int v = [] { const char* e = getenv("MXF_GEMM_PE"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
 static int ta_mode() {      // 0 = off, 1 = on for long K loops (default)
     static int v = [] { const char* e = getenv("MXF_GEMM_TA"); return e ? atoi(e) : 1; }();
     return v;
@@ -642,6 +928,19 @@ int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const
             return MXF_ENOTIMPL;
     }
     const float al = (float)alpha, be = (float)beta;
+    // persistent kernel (128-wide tiles, epilogue overlapped with the next tile's K loop): pays when a CTA gets several
+    // tiles and the K loop is short enough for the per-tile overheads to matter
+    static const int pe_kmax = [] { const char* e = getenv("MXF_GEMM_PE_KMAX"); return e ? atoi(e) : 2048; }();
+    if (pe_mode() && !wide && k >= 256 && k <= pe_kmax && n >= 128 &&
+        (int64_t)cdiv(n, 128) * cdiv(m, TC_BM) * S >= 2 * kNumSMs) {
+        CUtensorMap tmBp;
+        bool ok;
+        if (!b_mn) ok = make_map(&tmBp, B, n, k, ldb, sB, batchB ? S : 1, TC_BK, PeCfg::BN);
+        else ok = make_map(&tmBp, B, k, n, ldb, sB, batchB ? S : 1, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (ok)
+            return b_mn ? launch_tc_pe<true>(tmA, tmBp, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)
+                        : launch_tc_pe<false>(tmA, tmBp, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st);
+    }
     if (ta_mode() && k >= 256) {
         if (bn256)
             return b_mn ? launch_tc_ta<256, true>(tmA, tmB, C, ldc, sC, m, n, k, al, be, S, tri, batchA, batchB, st)

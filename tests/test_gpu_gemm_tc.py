@@ -22,6 +22,15 @@ CASES = [
     (100, 200, 72, False, 2, False, -1.0, 1.0),
     (1000, 64, 128, False, 1, False, 1.0, 1.0),
     (64, 64, 4096, True, 1, False, 1.0, 0.0),
+    # persistent kernel (>= 2 waves of 128 x 128 tiles, 256 <= k <= 2048): NT / NN, beta, ragged edges with an odd number
+    # of K steps (the two converter groups swap roles from tile to tile), batch, lower tiles only
+    (2048, 2560, 512, True, 1, False, 1.0, 0.0),
+    (2048, 2560, 512, False, 1, False, -1.0, 1.0),
+    (2000, 2500, 288, True, 1, False, 0.5, 0.3),
+    (2000, 2500, 288, False, 1, False, 0.5, 0.3),
+    (1024, 2560, 256, False, 2, False, 1.0, 0.0),
+    (3072, 3072, 512, True, 1, True, -1.0, 1.0),
+    (512, 28392, 512, False, 1, False, -1.0, 1.0),
 ]
 
 
