@@ -891,7 +891,7 @@ static int launch_tc_pe(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C
     return after_launch();
 }
 
-static int pe_mode() {      // 0 = off, 1 = on for problems with more than one wave of 128 x 128 tiles (default)
+static int pe_mode() {      // 0 = off, 1 = on for problems with more than one wave of 128 x 128 tiles and 256 <= K <= 2048 (default)
     static int v = [] { const char* e = getenv("MXF_GEMM_PE"); return e ? atoi(e) : 1; }();
     return v;
 }
@@ -931,8 +931,9 @@ int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const
     // persistent kernel (128-wide tiles, epilogue overlapped with the next tile's K loop): pays when a CTA gets several
     // tiles and the K loop is short enough for the per-tile overheads to matter
     static const int pe_kmax = [] { const char* e = getenv("MXF_GEMM_PE_KMAX"); return e ? atoi(e) : 2048; }();
+    static const int pe_min_tiles = [] { const char* e = getenv("MXF_GEMM_PE_MIN_TILES"); return e ? atoi(e) : kNumSMs + 12; }();
     if (pe_mode() && !wide && k >= 256 && k <= pe_kmax && n >= 128 &&
-        (int64_t)cdiv(n, 128) * cdiv(m, TC_BM) * S >= 2 * kNumSMs) {
+        (int64_t)cdiv(n, 128) * cdiv(m, TC_BM) * S >= pe_min_tiles) {
         CUtensorMap tmBp;
         bool ok;
         if (!b_mn) ok = make_map(&tmBp, B, n, k, ldb, sB, batchB ? S : 1, TC_BK, PeCfg::BN);

@@ -155,6 +155,24 @@ def bench_normal(res):
     res.append(r)
 
 
+def bench_gemmshapes(res):
+    """The GEMM shapes of the blocked potrf / trsm / streamed statistics (set MXF_GEMM_PE=0/1 to compare kernels)."""
+    dev = torch.device('cuda:0')
+    shapes = [(512, 28392, 512, False, False), (1024, 28392, 1024, False, False), (7680, 7680, 512, True, True),
+              (4096, 4096, 512, True, True), (2048, 2048, 512, True, True), (7680, 512, 512, True, False),
+              (1024, 4096, 1024, False, False), (4096, 4096, 1024, True, False), (4096, 4096, 2048, True, False)]
+    for (m, n, k, tb, tri) in shapes:
+        A = torch.randn((1, m, k), device=dev)
+        B = torch.randn((1, n, k) if tb else (1, k, n), device=dev)
+        C = torch.zeros((1, m, n), device=dev)
+        med, best = timeit(lambda: _raw.gemm(A, B, False, tb, alpha=-1.0, beta=1.0, C=C, tri=tri))
+        fl = 2.0 * m * n * k * (0.5 if tri else 1.0)
+        r = dict(kernel='gemm_f32', pe=os.environ.get('MXF_GEMM_PE', '1'), m=m, n=n, k=k, transB=tb, tri=tri, ms_median=med,
+                 tflops=fl / med / 1e9)
+        print(r, flush=True)
+        res.append(r)
+
+
 def main():
     which = sys.argv[1:] or ['all']
     res = []
@@ -163,6 +181,8 @@ def main():
         bench_kbuild(res)
     if 'gemm' in which or 'all' in which:
         bench_gemm(res)
+    if 'gemmshapes' in which:
+        bench_gemmshapes(res)
     if 'potrf' in which or 'all' in which:
         bench_potrf(res)
     if 'trsm' in which or 'all' in which:
@@ -176,3 +196,4 @@ def main():
 
 if __name__ == '__main__':
     main()
+
