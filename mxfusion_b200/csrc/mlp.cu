@@ -8,11 +8,12 @@
 // for all samples and rows, and one launch computes all weight / bias gradients (BASELINE config 4: 1-50-50-1,
 // S = 3, B = 4096).  Widths <= 64, <= 4 dense layers; torch.nn.Linear layout W (out, in), y = W x + b.
 //
-// Mapping: a CTA owns ROWS rows of ONE sample; thread r owns row r.  The sample's weights sit in shared memory (read as
-// warp-uniform broadcasts, 16 bytes at a time), activations in shared memory as [unit][row] with an odd row stride
-// (conflict-free both for "thread = row" and for the "thread = 8 x 8 tile of dW" reduction).
+// Mapping: a CTA owns ROWS rows of ONE sample and runs 4 x ROWS threads: thread (p, r) owns row r and every fourth group
+// of 4 output units (p is warp-uniform).  The sample's weights sit in shared memory (read as warp-uniform broadcasts,
+// 16 bytes at a time), activations in shared memory as [unit][row] with an odd row stride (conflict-free both for
+// "thread = row" and for the "thread = 4 x 4 tile of dW" reduction).
 // The adjoint recomputes the forward pass (cheaper than storing S x B x width activations in HBM), back-propagates per
-// row, reduces  dW_l = delta_l act_{l-1}^T  over the CTA's rows in registers (8 x 8 tiles) and adds the CTA's partial sums
+// row, reduces  dW_l = delta_l act_{l-1}^T  over the CTA's rows in registers (4 x 4 tiles) and adds the CTA's partial sums
 // to HBM with atomics (buffers zeroed by the caller; a weight shared by all samples has stride 0 and simply receives
 // the contributions of every sample).
 #include "common.cuh"
@@ -21,7 +22,8 @@ namespace mxf {
 
 constexpr int MLP_MAXW = 64;
 constexpr int MLP_MAXL = 4;
-template <typename T> struct MlpRows { static constexpr int value = 64; };     // rows (= threads) per CTA
+constexpr int MLP_SPLIT = 4;               // threads per row (each takes every fourth group of 4 output units)
+template <typename T> struct MlpRows { static constexpr int value = 64; };     // rows per CTA (threads = 4 x rows)
 template <> struct MlpRows<double> { static constexpr int value = 32; };       // f64: half, to fit shared memory
 constexpr int MLP_LDW = MLP_MAXW;          // row stride of the staged weight matrices
 
@@ -59,8 +61,8 @@ __device__ __forceinline__ void stage_layer(const MlpArgs<T>& a, int l, int s, T
 // One dense layer for this thread's row: dst[j][r] = act(bias[j] + sum_k Wt[k][j] src[k][r]).
 template <typename T, bool TANH, int MLP_RS>
 __device__ __forceinline__ void dense_row(const T* __restrict__ Wt, const T* __restrict__ bs, const T* __restrict__ src,
-                                          T* __restrict__ dst, int in, int out, int r) {
-    for (int j0 = 0; j0 < out; j0 += 4) {
+                                          T* __restrict__ dst, int in, int out, int r, int p) {
+    for (int j0 = 4 * p; j0 < out; j0 += 4 * MLP_SPLIT) {
         T acc[4] = {bs[j0], bs[j0 + 1], bs[j0 + 2], bs[j0 + 3]};
         for (int k = 0; k < in; ++k) {
             const T x = src[k * MLP_RS + r];
@@ -75,7 +77,7 @@ __device__ __forceinline__ void dense_row(const T* __restrict__ Wt, const T* __r
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MlpRows<T>::value)
+__global__ void __launch_bounds__(MLP_SPLIT * MlpRows<T>::value)
 mlp_tanh_fwd_kernel(MlpArgs<T> a, const T* __restrict__ x, int64_t sx, T* __restrict__ out, int B) {
     constexpr int MLP_ROWS = MlpRows<T>::value, MLP_RS = MLP_ROWS + 1;   // odd row stride of the [unit][row] arrays
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -83,30 +85,31 @@ mlp_tanh_fwd_kernel(MlpArgs<T> a, const T* __restrict__ x, int64_t sx, T* __rest
     T* bs = Wt + MLP_MAXW * MLP_LDW;                        // [MAXW]
     T* act0 = bs + MLP_MAXW;                                // [MAXW][RS]
     T* act1 = act0 + MLP_MAXW * MLP_RS;
-    const int s = blockIdx.y, r = threadIdx.x, row = blockIdx.x * MLP_ROWS + r;
+    const int s = blockIdx.y, r = threadIdx.x % MLP_ROWS, p = threadIdx.x / MLP_ROWS, row = blockIdx.x * MLP_ROWS + r;
     const bool live = row < B;
     const int w0 = a.width[0];
     const T* xr = x + (int64_t)s * sx + (int64_t)row * w0;
-    for (int k = 0; k < w0; ++k) act0[k * MLP_RS + r] = live ? xr[k] : T(0);
+    for (int k = p; k < w0; k += MLP_SPLIT) act0[k * MLP_RS + r] = live ? xr[k] : T(0);
     T* src = act0;
     T* dst = act1;
     for (int l = 0; l < a.n_layers; ++l) {
         __syncthreads();
         stage_layer<T>(a, l, s, Wt, nullptr, bs);
         __syncthreads();
-        if (l + 1 < a.n_layers) dense_row<T, true, MLP_RS>(Wt, bs, src, dst, a.width[l], a.width[l + 1], r);
-        else dense_row<T, false, MLP_RS>(Wt, bs, src, dst, a.width[l], a.width[l + 1], r);
+        if (l + 1 < a.n_layers) dense_row<T, true, MLP_RS>(Wt, bs, src, dst, a.width[l], a.width[l + 1], r, p);
+        else dense_row<T, false, MLP_RS>(Wt, bs, src, dst, a.width[l], a.width[l + 1], r, p);
         T* t = src; src = dst; dst = t;
     }
+    __syncthreads();
     const int wo = a.width[a.n_layers];
     if (live) {
         T* o = out + ((int64_t)s * B + row) * wo;
-        for (int j = 0; j < wo; ++j) o[j] = src[j * MLP_RS + r];
+        for (int j = p; j < wo; j += MLP_SPLIT) o[j] = src[j * MLP_RS + r];
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MlpRows<T>::value)
+__global__ void __launch_bounds__(MLP_SPLIT * MlpRows<T>::value)
 mlp_tanh_bwd_kernel(MlpArgs<T> a, const T* __restrict__ x, int64_t sx, const T* __restrict__ gout, int B) {
     constexpr int MLP_ROWS = MlpRows<T>::value, MLP_RS = MLP_ROWS + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -116,19 +119,19 @@ mlp_tanh_bwd_kernel(MlpArgs<T> a, const T* __restrict__ x, int64_t sx, const T* 
     T* act = bs + MLP_MAXW;                                 // [MAXL][MAXW][RS]: act[l] = input of layer l
     T* d0 = act + MLP_MAXL * MLP_MAXW * MLP_RS;             // [MAXW][RS]  delta ping
     T* d1 = d0 + MLP_MAXW * MLP_RS;                         // [MAXW][RS]  delta pong
-    const int s = blockIdx.y, r = threadIdx.x, row = blockIdx.x * MLP_ROWS + r;
+    const int s = blockIdx.y, r = threadIdx.x % MLP_ROWS, p = threadIdx.x / MLP_ROWS, row = blockIdx.x * MLP_ROWS + r;
     const bool live = row < B;
     const int L = a.n_layers;
     // ---- forward recomputation, keeping every layer's input -------------------------------------------------
     const int w0 = a.width[0];
     const T* xr = x + (int64_t)s * sx + (int64_t)row * w0;
-    for (int k = 0; k < w0; ++k) act[k * MLP_RS + r] = live ? xr[k] : T(0);
+    for (int k = p; k < w0; k += MLP_SPLIT) act[k * MLP_RS + r] = live ? xr[k] : T(0);
     for (int l = 0; l + 1 < L; ++l) {
         __syncthreads();
         stage_layer<T>(a, l, s, Wt, nullptr, bs);
         __syncthreads();
         dense_row<T, true, MLP_RS>(Wt, bs, act + l * MLP_MAXW * MLP_RS, act + (l + 1) * MLP_MAXW * MLP_RS, a.width[l],
-                           a.width[l + 1], r);
+                                   a.width[l + 1], r, p);
     }
     // ---- delta of the output layer = upstream gradient -------------------------------------------------------
     const int wo = a.width[L];
@@ -136,41 +139,43 @@ mlp_tanh_bwd_kernel(MlpArgs<T> a, const T* __restrict__ x, int64_t sx, const T* 
     T* dnext = d1;
     {
         const T* g = gout + ((int64_t)s * B + row) * wo;
-        for (int j = 0; j < MLP_MAXW; ++j) dcur[j * MLP_RS + r] = (live && j < wo) ? g[j] : T(0);
+        for (int j = p; j < MLP_MAXW; j += MLP_SPLIT) dcur[j * MLP_RS + r] = (live && j < wo) ? g[j] : T(0);
     }
     for (int l = L - 1; l >= 0; --l) {
         const int in = a.width[l], out = a.width[l + 1];
         const T* ain = act + l * MLP_MAXW * MLP_RS;
         __syncthreads();                                    // dcur complete (all rows), previous Wj no longer read
         if (l > 0) stage_layer<T>(a, l, s, Wt, Wj, bs);
-        // dW_l[j][k] += sum_r dcur[j][r] ain[k][r]  (8 x 8 tile per thread), db_l[j] += sum_r dcur[j][r]
+        // dW_l[j][k] += sum_r dcur[j][r] ain[k][r]  (4 x 4 tile per thread), db_l[j] += sum_r dcur[j][r]
         {
-            const int k0 = 8 * (r & 7);
-            for (int j0 = 8 * (r >> 3); j0 < out && k0 < in; j0 += MLP_ROWS) {
-                T acc[8][8];
+            const int tid = threadIdx.x;
+            const int k0 = 4 * (tid & 15);
+            for (int j0 = 4 * (tid >> 4); j0 < out && k0 < in; j0 += MLP_SPLIT * MLP_ROWS / 4) {
+                T acc[4][4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int u = 0; u < 4; ++u)
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) acc[u][v] = T(0);
+                    for (int v = 0; v < 4; ++v) acc[u][v] = T(0);
+#pragma unroll 4
                 for (int q = 0; q < MLP_ROWS; ++q) {
-                    T dj[8], ak[8];
+                    T dj[4], ak[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) dj[u] = dcur[(j0 + u) * MLP_RS + q];
+                    for (int u = 0; u < 4; ++u) dj[u] = dcur[(j0 + u) * MLP_RS + q];
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) ak[v] = ain[(k0 + v) * MLP_RS + q];
+                    for (int v = 0; v < 4; ++v) ak[v] = ain[(k0 + v) * MLP_RS + q];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
+                    for (int u = 0; u < 4; ++u)
 #pragma unroll
-                        for (int v = 0; v < 8; ++v) acc[u][v] = fma(dj[u], ak[v], acc[u][v]);
+                        for (int v = 0; v < 4; ++v) acc[u][v] = fma(dj[u], ak[v], acc[u][v]);
                 }
                 T* dW = a.dW[l] + (int64_t)s * a.sW[l];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int u = 0; u < 4; ++u)
 #pragma unroll
-                    for (int v = 0; v < 8; ++v)
+                    for (int v = 0; v < 4; ++v)
                         if (j0 + u < out && k0 + v < in) atomicAdd(dW + (int64_t)(j0 + u) * in + k0 + v, acc[u][v]);
             }
-            for (int j = r; a.db[l] && j < out; j += MLP_ROWS) {
+            for (int j = tid; a.db[l] && j < out; j += MLP_SPLIT * MLP_ROWS) {
                 T sum = T(0);
                 for (int q = 0; q < MLP_ROWS; ++q) sum += dcur[j * MLP_RS + q];
                 atomicAdd(a.db[l] + (int64_t)s * a.sb[l] + j, sum);
@@ -179,7 +184,7 @@ mlp_tanh_bwd_kernel(MlpArgs<T> a, const T* __restrict__ x, int64_t sx, const T* 
         if (l == 0) break;
         __syncthreads();                                    // Wj staged
         // delta of the layer below: dnext[k][r] = (sum_j W[j][k] dcur[j][r]) (1 - ain[k][r]^2)
-        for (int k0 = 0; k0 < in; k0 += 4) {
+        for (int k0 = 4 * p; k0 < in; k0 += 4 * MLP_SPLIT) {
             T acc[4] = {T(0), T(0), T(0), T(0)};
             for (int j = 0; j < out; ++j) {
                 const T d = dcur[j * MLP_RS + r];
@@ -193,7 +198,7 @@ mlp_tanh_bwd_kernel(MlpArgs<T> a, const T* __restrict__ x, int64_t sx, const T* 
                 dnext[(k0 + u) * MLP_RS + r] = (k0 + u < in) ? acc[u] * (T(1) - h * h) : T(0);
             }
         }
-        for (int k = (in + 3) & ~3; k < MLP_MAXW; ++k) dnext[k * MLP_RS + r] = T(0);
+        for (int k = ((in + 3) & ~3) + p; k < MLP_MAXW; k += MLP_SPLIT) dnext[k * MLP_RS + r] = T(0);
         T* t = dcur; dcur = dnext; dnext = t;
     }
 }
@@ -232,7 +237,7 @@ static int mlp_fwd_impl(int n_layers, const int* widths, const void* x, int64_t 
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     dim3 grid(cdiv(B, MLP_ROWS), S);
-    k<<<grid, MLP_ROWS, smem, st>>>(a, static_cast<const T*>(x), sx, static_cast<T*>(out), B);
+    k<<<grid, MLP_SPLIT * MLP_ROWS, smem, st>>>(a, static_cast<const T*>(x), sx, static_cast<T*>(out), B);
     return after_launch();
 }
 
@@ -251,7 +256,7 @@ static int mlp_bwd_impl(int n_layers, const int* widths, const void* x, int64_t 
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     dim3 grid(cdiv(B, MLP_ROWS), S);
-    k<<<grid, MLP_ROWS, smem, st>>>(a, static_cast<const T*>(x), sx, static_cast<const T*>(gout), B);
+    k<<<grid, MLP_SPLIT * MLP_ROWS, smem, st>>>(a, static_cast<const T*>(x), sx, static_cast<const T*>(gout), B);
     return after_launch();
 }
 
