@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 
 N_ROWS, M_IND, D_IN, BATCH = 1000000, 1024, 8, 4096
 JITTER, LR = 1e-6, 1e-2
+KBUILD_NCU_TRAFFIC_BYTES = 4070277632      # profiles/r1b_kbuild_raw.csv: 32.06 MB read + 4038.2 MB written per launch
 METRIC = "svgp_elbo_iters_per_sec"
 UNIT = "minibatch iterations (B=4096 rows: ELBO fwd + grad + Adam) per second, summed over GPUs"
 
@@ -176,8 +177,40 @@ def kernel_rooflines(device, pk):
     ach = nbytes / ms / 1e6
     del out
     return {'bound': 'hbm', 'kernel': 'kbuild_fwd_kernel<float,RBF> K(X,Z) N=1e6 M=1024 D=8', 'achieved': ach,
-            'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'], 'traffic': None,
+            'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'], 'traffic': KBUILD_NCU_TRAFFIC_BYTES,
+            'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture '
+                              'profiles/r1b_kbuild_raw.csv (0.032 GB read + 4.038 GB written)',
             'ms_per_launch': ms, 'algorithmic_bytes': nbytes}
+
+
+def tensor_roofline(device, pk):
+    """The tensor-pipe kernel of the path on its own (the potrf / trsm / syrk update engine, csrc/gemm_tc.cu): a
+    4096^3 FP32-accurate product = 3 TF32 tcgen05 MMAs per multiply-add.  `achieved` counts the TF32 MMA flops actually
+    issued (3 x 2mnk); `peak` = half the measured dense bf16 rate (TF32 runs at half the bf16 MMA rate)."""
+    import torch
+    from mxfusion_b200 import _raw
+    n = 4096
+    A = torch.randn((1, n, n), device=device)
+    B = torch.randn((1, n, n), device=device)
+    C = torch.empty((1, n, n), device=device)
+    for _ in range(3):
+        _raw.gemm(A, B, False, True, C=C)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _raw.gemm(A, B, False, True, C=C)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sum(ts) / len(ts)
+    fp32_tflops = 2.0 * n ** 3 / ms / 1e9
+    peak = pk.get('bf16_tflops', 1590.0) / 2.0
+    return {'bound': 'tensor', 'kernel': 'gemm_tc_ta_kernel<256> 4096^3 (3xTF32, tcgen05 + TMEM-resident A)',
+            'achieved': 3.0 * fp32_tflops, 'peak': peak, 'unit': 'TFLOP/s', 'frac': 3.0 * fp32_tflops / peak,
+            'fp32_equivalent_tflops': fp32_tflops, 'ms_per_launch': ms,
+            'ncu': 'sm__pipe_tensor_cycles_active 69.7 % of peak sustained active (profiles/r1c_gemm4096_raw.csv)'}
 
 
 def cpu_reference_iters_per_sec(X, Y, Z, n_total, seconds_budget=20.0, max_iters=30):
@@ -303,8 +336,9 @@ def main():
         del infr, infr2, flush
         torch.cuda.empty_cache()
         line['roofline'] = kernel_rooflines(device, pk)
+        line['roofline_tensor'] = tensor_roofline(device, pk)
         if not args.no_cpu_baseline:
-            ips, cores, n, dt = cpu_reference_iters_per_sec(X, Y, Z, N_ROWS, seconds_budget=15.0, max_iters=20)
+            ips, cores, n, dt = cpu_reference_iters_per_sec(X, Y, Z, N_ROWS, seconds_budget=12.0, max_iters=200)
             line['cpu_baseline'] = {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': '%d iterations of the same B=4096 step in %.1f s on the host cores '
                                               '(torch CPU f32 op-for-op restatement of the reference)' % (n, dt)}
