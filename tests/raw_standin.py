@@ -54,10 +54,11 @@ def gemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None, tri=Fals
     prod = alpha * torch.matmul(a, b)
     if C is None:
         return torch.tril(prod).contiguous() if tri else prod.contiguous()
+    acc = prod if beta == 0.0 else prod + beta * C      # like the kernels, beta == 0 never reads C (it may be uninitialised)
     if tri:
-        C.copy_(torch.triu(C, 1) + torch.tril(prod + beta * C))
+        C.copy_(torch.where(torch.ones_like(C, dtype=torch.bool).tril(), acc, C))
     else:
-        C.copy_(prod + beta * C)
+        C.copy_(acc)
     return C
 
 
