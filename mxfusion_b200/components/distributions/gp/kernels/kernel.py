@@ -87,13 +87,25 @@ class Kernel(MXFusionFunction):
         return rep
 
     def add(self, other, name='add'):
-        raise ModelSpecificationError("kernel addition is outside the hot-path scope of this build (SURVEY 8f-4)")
+        """kernel.py:149-160."""
+        if not isinstance(other, Kernel):
+            raise ModelSpecificationError("Only a Gaussian Process Kernel can be added to a Gaussian Process Kernel.")
+        from .add_kernel import AddKernel
+        return AddKernel([self, other], name=name, ctx=self.ctx, dtype=self.dtype)
+
+    def __add__(self, other):
+        return self.add(other)
 
     def multiply(self, other, name='mul'):
-        raise ModelSpecificationError("kernel multiplication is outside the hot-path scope of this build (SURVEY 8f-4)")
+        """kernel.py:168-181."""
+        if not isinstance(other, Kernel):
+            raise ModelSpecificationError(
+                "Only a Gaussian Process Kernel can be multiplied with a Gaussian Process Kernel.")
+        from .multiply_kernel import MultiplyKernel
+        return MultiplyKernel([self, other], name=name, ctx=self.ctx, dtype=self.dtype)
 
-    __add__ = add
-    __mul__ = multiply
+    def __mul__(self, other):
+        return self.multiply(other)
 
 
 class NativeKernel(Kernel):
@@ -104,3 +116,71 @@ class NativeKernel(Kernel):
     @property
     def parameter_names(self):
         return [self.name + '_' + n for n in self._parameter_names]
+
+
+def rename_duplicate_names(names):
+    """['a', 'b', 'a', 'a'] -> [(2, 'a0'), (3, 'a1')] (mxfusion/util/util.py:65-99)."""
+    import re
+    all_names = set(names)
+    if len(all_names) == len(names):
+        return []
+    cur_names, renames = set(), []
+    prog = re.compile(r'^(.*)(\d+)$')
+    for i, n in enumerate(names):
+        if n in cur_names:
+            res = prog.match(n)
+            if res is None or len(res.groups()) == 0:
+                prefix, count = n, 0
+            else:
+                prefix, count = res.groups()[0], int(res.groups()[1]) + 1
+            while prefix + str(count) in all_names:
+                count += 1
+            renames.append((i, prefix + str(count)))
+            all_names.add(prefix + str(count))
+        else:
+            cur_names.add(n)
+    return renames
+
+
+class CombinationKernel(Kernel):
+    """Covariance computed by combining the covariance matrices of sub-kernels (kernel.py:309-373).  Parameter names
+    nest: `<combination>_<sub-kernel>_<parameter>`."""
+
+    def __init__(self, sub_kernels, name, dtype=None, ctx=None):
+        input_dim = max([k.input_dim for k in sub_kernels])
+        for i, n in rename_duplicate_names([k.name for k in sub_kernels]):
+            sub_kernels[i].name = n
+        super(CombinationKernel, self).__init__(input_dim=input_dim, name=name, dtype=dtype, ctx=ctx)
+        self.__dict__['sub_kernels'] = sub_kernels
+        for k in sub_kernels:
+            self.__dict__[k.name] = k
+
+    @property
+    def local_parameters(self):
+        out = set()
+        for k in self.sub_kernels:
+            out |= set(k.local_parameters)
+        return out
+
+    @property
+    def parameters(self):
+        p = {}
+        for k in self.sub_kernels:
+            p.update(k.parameters)
+        return {self.name + '_' + k: v for k, v in p.items()}
+
+    @property
+    def parameter_names(self):
+        names = []
+        for k in self.sub_kernels:
+            names.extend([self.name + '_' + n for n in k.parameter_names])
+        return names
+
+    def replicate_self(self, attribute_map=None):
+        rep = copy(self)
+        rep.__dict__['_parameter_names'] = []
+        rep.__dict__['sub_kernels'] = [k.replicate_self(attribute_map) for k in self.sub_kernels]
+        for k in rep.sub_kernels:
+            rep.__dict__[k.name] = k
+        rep.active_dims = copy(self.active_dims)
+        return rep

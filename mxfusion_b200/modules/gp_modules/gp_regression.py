@@ -26,8 +26,17 @@ class GPRegressionLogPdf(VariationalInference):
         Y = variables[self.model.Y]
         noise_var = variables[self.model.noise_var]
         kern = self.model.kernel
-        kp = kern._strip(kern.fetch_parameters(variables))
         mean = variables[self.model.mean] if self.model.has_mean else None
+        if getattr(kern, 'KIND', None) is None:          # Add / Multiply / Linear / static kernels
+            from . import _generic
+            logL, L, LinvY = _generic.gp_log_pdf(F, kern, kern.fetch_parameters(variables), X, Y, noise_var,
+                                                 self.jitter, mean=mean)
+            with torch.no_grad():
+                self.set_parameter(variables, self.posterior.X, X[0])
+                self.set_parameter(variables, self.posterior.L, L[0])
+                self.set_parameter(variables, self.posterior.LinvY, LinvY[0])
+            return logL
+        kp = kern._strip(kern.fetch_parameters(variables))
         Xk = X
         if kern.active_dims is not None:
             from ...components.distributions.gp.kernels.kernel import slice_axis

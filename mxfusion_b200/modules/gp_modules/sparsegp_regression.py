@@ -37,8 +37,17 @@ class SparseGPRegressionLogPdf(VariationalInference):
         Z = variables[self.model.inducing_inputs]
         noise_var = variables[self.model.noise_var]
         kern = self.model.kernel
-        kp = kern._strip(kern.fetch_parameters(variables))
         mean = variables[self.model.mean] if self.model.has_mean else None
+        if getattr(kern, 'KIND', None) is None:          # Add / Multiply / Linear / static kernels: materialising path
+            from . import _generic
+            logL, wv, L, LA = _generic.sparsegp_log_pdf(F, kern, kern.fetch_parameters(variables), X, Y, Z, noise_var,
+                                                        self.jitter, mean=mean)
+            with torch.no_grad():
+                self.set_parameter(variables, self.posterior.wv, wv[0])
+                self.set_parameter(variables, self.posterior.L, L[0])
+                self.set_parameter(variables, self.posterior.LA, LA[0])
+            return logL
+        kp = kern._strip(kern.fetch_parameters(variables))
         X, Z = _active(F, kern, X, Z)
         logL, wv, L, LA, _ = ops.sparsegp_log_pdf(kern.KIND, X, Y, Z, noise_var, kp['lengthscale'], kp['variance'],
                                                   jitter=self.jitter, mean=mean, chunk=self.chunk_rows)

@@ -38,8 +38,12 @@ class SVGPRegressionLogPdf(VariationalInference):
         S_W = variables[self.posterior.qU_cov_W]
         S_diag = variables[self.posterior.qU_cov_diag]
         kern = self.model.kernel
-        kp = kern._strip(kern.fetch_parameters(variables))
         mean = variables[self.model.mean] if self.model.has_mean else None
+        if getattr(kern, 'KIND', None) is None:          # Add / Multiply / Linear / static kernels: primitive-by-primitive
+            from . import _generic
+            return _generic.svgp_log_pdf(F, kern, kern.fetch_parameters(variables), X, Y, Z, noise_var, mu, S_W,
+                                         S_diag, self.jitter, self.log_pdf_scaling, mean=mean)
+        kp = kern._strip(kern.fetch_parameters(variables))
         X, Z = _active(F, kern, X, Z)
         return ops.svgp_log_pdf(kern.KIND, X, Y, Z, noise_var, mu, S_W, S_diag, kp['lengthscale'], kp['variance'],
                                 jitter=self.jitter, log_pdf_scaling=self.log_pdf_scaling, mean=mean)
@@ -65,10 +69,15 @@ class SVGPRegressionMeanVariancePrediction(SamplingAlgorithm):
         S_diag = variables[self.graphs[1].qU_cov_diag]
         kern = self.model.kernel
         kern_params = kern.fetch_parameters(variables)
-        kp = kern._strip(kern_params)
+        kp = kern._strip(kern_params) if getattr(kern, 'KIND', None) is not None else None
         S = ops.syrk(S_W) + ops.make_diagonal(S_diag)
-        (Zs,) = _active(F, kern, Z)
-        Kuu = ops.kernel_matrix(kern.KIND, Zs, None, kp['lengthscale'], kp['variance'], diag_const=self.jitter)
+        if getattr(kern, 'KIND', None) is None:
+            Kuu = kern.K(F, Z, **kern_params)
+            if self.jitter > 0.:
+                Kuu = Kuu + torch.eye(Z.shape[-2], dtype=Z.dtype, device=Z.device).unsqueeze(0) * self.jitter
+        else:
+            (Zs,) = _active(F, kern, Z)
+            Kuu = ops.kernel_matrix(kern.KIND, Zs, None, kp['lengthscale'], kp['variance'], diag_const=self.jitter)
         L = ops.potrf(Kuu)
         Ls = ops.potrf(S)
         LinvLs = ops.trsm(L, Ls)

@@ -11,6 +11,8 @@ Scenarios follow the reference's tests and notebooks:
   svgp_mb   MinibatchInferenceLoop trajectory (shuffled rollover batches, rv_scaling, grads / B)
   normal    testing/components/distributions/normal_test.py:35-109 (log_pdf, reparameterised draw with injected eps)
   svi       StochasticVariationalInference on a conjugate toy model with injected posterior samples
+  combo     kernel algebra (kernel_test.py:163-300: Linear / Bias / White / Add / Multiply) and the three GP modules with
+            combination kernels: values and gradients
   sparsegp  testing/modules/sparsegpregression_test.py:41-196 fixture (+ Matern, P=1, larger M): bound, gradients,
             cached wv / L / LA, mean / variance prediction in the four modes
 Each .npz stores the inputs next to the outputs, so tests need nothing but the file.
@@ -33,7 +35,7 @@ from mxfusion import Model, Variable  # noqa: E402
 from mxfusion.common import config  # noqa: E402
 from mxfusion.components.variables import PositiveTransformation  # noqa: E402
 from mxfusion.components.distributions import Normal  # noqa: E402
-from mxfusion.components.distributions.gp.kernels import RBF, Matern12, Matern32, Matern52  # noqa: E402
+from mxfusion.components.distributions.gp.kernels import RBF, Matern12, Matern32, Matern52, Linear, Bias, White  # noqa: E402
 from mxfusion.modules.gp_modules import GPRegression, SVGPRegression, SparseGPRegression  # noqa: E402
 from mxfusion.inference import (Inference, GradBasedInference, MAP, BatchInferenceLoop, MinibatchInferenceLoop,  # noqa: E402
                                 StochasticVariationalInference, create_Gaussian_meanfield)
@@ -372,6 +374,117 @@ def golden_sparsegp():
     save('sparsegp_fixture', **out)
 
 
+# ------------------------------------------------------------------------------------------------ kernel algebra
+def combo_kernel(spec, Din):
+    """spec -> a reference kernel object.  Initial values are filled in by the caller through infr.params / K kwargs."""
+    if spec == 'linear':
+        return Linear(input_dim=Din, ARD=False, dtype=DT)
+    if spec == 'linear_ard':
+        return Linear(input_dim=Din, ARD=True, dtype=DT)
+    if spec == 'bias':
+        return Bias(input_dim=Din, dtype=DT)
+    if spec == 'white':
+        return White(input_dim=Din, dtype=DT)
+    if spec == 'rbf+linear_ard':
+        return RBF(input_dim=Din, ARD=True, dtype=DT) + Linear(input_dim=Din, ARD=True, dtype=DT)
+    if spec == 'rbf*matern32':
+        return RBF(input_dim=Din, ARD=False, dtype=DT) * Matern32(input_dim=Din, ARD=True, dtype=DT)
+    if spec == 'rbf+rbf+bias':
+        return RBF(input_dim=Din, dtype=DT) + RBF(input_dim=Din, ARD=True, dtype=DT) + Bias(input_dim=Din, dtype=DT)
+    if spec == '(matern52+white)*linear':
+        return (Matern52(input_dim=Din, dtype=DT) + White(input_dim=Din, dtype=DT)) * Linear(input_dim=Din, dtype=DT)
+    raise ValueError(spec)
+
+
+COMBO_SPECS = ['linear', 'linear_ard', 'bias', 'white', 'rbf+linear_ard', 'rbf*matern32', 'rbf+rbf+bias',
+               '(matern52+white)*linear']
+
+
+def golden_combo_kernels():
+    rng = np.random.RandomState(7)
+    out = {'specs': np.array(COMBO_SPECS)}
+    Din, N, N2 = 3, 6, 4
+    for i, spec in enumerate(COMBO_SPECS):
+        for S in (1, 2):
+            k = combo_kernel(spec, Din)
+            X, X2 = rng.rand(S, N, Din), rng.rand(S, N2, Din)
+            names = sorted(k.parameters.keys())
+            vals = {n: rng.rand(S, *k.parameters[n].shape) + 0.3 for n in names}
+            params = {n: nd(v) for n, v in vals.items()}
+            tag = 'k%d_S%d' % (i, S)
+            out[tag + '_X'], out[tag + '_X2'] = X, X2
+            out[tag + '_names'] = np.array(names)
+            for n in names:
+                out[tag + '_p_' + n] = vals[n]
+            out[tag + '_K'] = k.K(mx.nd, nd(X), **params).asnumpy()
+            out[tag + '_K2'] = k.K(mx.nd, nd(X), nd(X2), **params).asnumpy()
+            out[tag + '_Kdiag'] = k.Kdiag(mx.nd, nd(X), **params).asnumpy()
+    save('combo_kernels', **out)
+
+
+def combo_module_case(module, spec, seed, N=12, M=4, Din=3, P=2):
+    np.random.seed(seed)
+    X, Y, Z = np.random.rand(N, Din), np.random.rand(N, P), np.random.rand(M, Din)
+    noise_var = np.random.rand(1) + 0.1
+    m = Model()
+    m.N = Variable()
+    m.X = Variable(shape=(m.N, Din))
+    m.noise_var = Variable(transformation=PositiveTransformation(), initial_value=nd(noise_var))
+    kernel = combo_kernel(spec, Din)
+    if module == 'gp':
+        m.Y = GPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, shape=(m.N, P), dtype=DT)
+    else:
+        m.Z = Variable(shape=(M, Din), initial_value=nd(Z))
+        cls = SVGPRegression if module == 'svgp' else SparseGPRegression
+        m.Y = cls.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z, shape=(m.N, P),
+                                  dtype=DT)
+        (m.Y.factor.svgp_log_pdf if module == 'svgp' else m.Y.factor.sgp_log_pdf).jitter = 1e-6
+    gp = m.Y.factor
+    infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), dtype=DT)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    r = dict(X=X, Y=Y, Z=Z, noise_var=noise_var)
+    names = sorted(kernel.parameters.keys())
+    r['names'] = np.array(names)
+    for n in names:
+        v = np.random.rand(*kernel.parameters[n].shape) + 0.3
+        infr.params[kernel.parameters[n]] = nd(v)
+        r['p_' + n] = v
+    if module == 'svgp':
+        post = gp._extra_graphs[0]
+        for nm in ('qU_mean', 'qU_cov_W', 'qU_cov_diag'):
+            v = np.random.rand(*getattr(post, nm).shape)
+            infr.params[getattr(post, nm)] = nd(v)
+            r[nm] = v
+    executor = infr.create_executor()
+    with mx.autograd.record():
+        loss, loss_g = executor(mx.nd.zeros(1), nd(X), nd(Y))
+        loss_g.backward()
+    gvars = {'noise_var': m.noise_var}
+    if module != 'gp':
+        gvars['Z'] = m.Z
+    if module == 'svgp':
+        gvars.update(qU_mean=post.qU_mean, qU_cov_W=post.qU_cov_W, qU_cov_diag=post.qU_cov_diag)
+    for n in names:
+        gvars['p_' + n] = kernel.parameters[n]
+    g = grads_of(infr, gvars)
+    r['loss'] = loss.asnumpy()
+    r.update({'grad_' + k: v for k, v in g.items()})
+    return r
+
+
+def golden_combo_modules():
+    out = {}
+    cases = [('svgp', 'rbf+linear_ard', 0), ('svgp', 'rbf*matern32', 1), ('gp', '(matern52+white)*linear', 2),
+             ('gp', 'rbf+rbf+bias', 3), ('sparsegp', 'rbf+linear_ard', 4), ('sparsegp', 'linear', 5)]
+    for i, (module, spec, seed) in enumerate(cases):
+        r = combo_module_case(module, spec, seed)
+        out['case%d_module' % i], out['case%d_spec' % i] = module, spec
+        for k, v in r.items():
+            out['case%d_%s' % (i, k)] = v
+    out['n_cases'] = len(cases)
+    save('combo_modules', **out)
+
+
 if __name__ == '__main__':
     golden_kernels()
     golden_svgp()
@@ -382,3 +495,5 @@ if __name__ == '__main__':
     golden_svi()
     golden_predict()
     golden_sparsegp()
+    golden_combo_kernels()
+    golden_combo_modules()

@@ -224,3 +224,87 @@ def run_sparsegp_case(mf, g, i, device, chunk_rows=None):
                 res = infr2.run(X=Xt)[0]
             pred[(noise_free, diag)] = (res[0].cpu().numpy(), res[1].cpu().numpy())
     return float(loss), grads, cache, pred
+
+
+# ------------------------------------------------------------------------------------------------ kernel algebra (8f-4)
+def combo_kernel(spec, Din):
+    """Same constructions as tests/golden/make_golden.py::combo_kernel, with this package's classes."""
+    from mxfusion_b200.components.distributions.gp.kernels import RBF, Matern32, Matern52, Linear, Bias, White
+    if spec == 'linear':
+        return Linear(input_dim=Din, ARD=False)
+    if spec == 'linear_ard':
+        return Linear(input_dim=Din, ARD=True)
+    if spec == 'bias':
+        return Bias(input_dim=Din)
+    if spec == 'white':
+        return White(input_dim=Din)
+    if spec == 'rbf+linear_ard':
+        return RBF(input_dim=Din, ARD=True) + Linear(input_dim=Din, ARD=True)
+    if spec == 'rbf*matern32':
+        return RBF(input_dim=Din, ARD=False) * Matern32(input_dim=Din, ARD=True)
+    if spec == 'rbf+rbf+bias':
+        return RBF(input_dim=Din) + RBF(input_dim=Din, ARD=True) + Bias(input_dim=Din)
+    if spec == '(matern52+white)*linear':
+        return (Matern52(input_dim=Din) + White(input_dim=Din)) * Linear(input_dim=Din)
+    raise ValueError(spec)
+
+
+def run_combo_kernels(g, device):
+    """Yields (tag, got, want) for K(X), K(X, X2), Kdiag of every kernel spec / sample count in combo_kernels.npz."""
+    from mxfusion_b200 import F
+    for i, spec in enumerate([str(s) for s in g['specs']]):
+        for S in (1, 2):
+            tag = 'k%d_S%d' % (i, S)
+            X, X2 = g[tag + '_X'], g[tag + '_X2']
+            k = combo_kernel(spec, X.shape[-1])
+            names = [str(n) for n in g[tag + '_names']]
+            assert sorted(k.parameters.keys()) == names, (spec, sorted(k.parameters.keys()), names)
+            T = lambda a: torch.tensor(a, device=device)
+            params = {n: T(g[tag + '_p_' + n]) for n in names}
+            yield tag + ' ' + spec + ' K', k.K(F, T(X), **params).cpu().numpy(), g[tag + '_K']
+            yield tag + ' ' + spec + ' K2', k.K(F, T(X), T(X2), **params).cpu().numpy(), g[tag + '_K2']
+            yield tag + ' ' + spec + ' Kdiag', k.Kdiag(F, T(X), **params).cpu().numpy(), g[tag + '_Kdiag']
+
+
+def run_combo_module_case(mf, g, i, device):
+    """Rebuilds case i of combo_modules.npz (a GP module over a combination kernel); returns (loss, grads)."""
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.modules.gp_modules import GPRegression, SVGPRegression, SparseGPRegression
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    c = lambda k: g['case%d_%s' % (i, k)]
+    module, spec = str(c('module')), str(c('spec'))
+    X, Y, Z = c('X'), c('Y'), c('Z')
+    N, Din = X.shape
+    M, P = Z.shape[0], Y.shape[1]
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, Din))
+    m.noise_var = mf.Variable(transformation=PositiveTransformation(), initial_value=c('noise_var'))
+    kernel = combo_kernel(spec, Din)
+    if module == 'gp':
+        m.Y = GPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, shape=(m.N, P))
+    else:
+        m.Z = mf.Variable(shape=(M, Din), initial_value=Z)
+        cls = SVGPRegression if module == 'svgp' else SparseGPRegression
+        m.Y = cls.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z, shape=(m.N, P))
+        (m.Y.factor.svgp_log_pdf if module == 'svgp' else m.Y.factor.sgp_log_pdf).jitter = 1e-6
+    gp = m.Y.factor
+    infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), context=device)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    names = [str(n) for n in c('names')]
+    for n in names:
+        infr.params[kernel.parameters[n]] = c('p_' + n)
+    gvars = {'noise_var': m.noise_var}
+    if module != 'gp':
+        gvars['Z'] = m.Z
+    if module == 'svgp':
+        post = gp._extra_graphs[0]
+        for nm in ('qU_mean', 'qU_cov_W', 'qU_cov_diag'):
+            infr.params[getattr(post, nm)] = c(nm)
+            gvars[nm] = getattr(post, nm)
+    for n in names:
+        gvars['p_' + n] = kernel.parameters[n]
+    infr.params.gflat.zero_()
+    loss, loss_g = infr.create_executor()(None, torch.tensor(X, device=device), torch.tensor(Y, device=device))
+    loss_g.backward()
+    return float(loss), {k: param_grad(infr, v) for k, v in gvars.items()}

@@ -238,3 +238,25 @@ def test_product_sparsegp_fixture_value_gradients_cache_and_prediction(mf, chunk
             t = 'case%d_pred_nf%d_diag%d' % (i, int(nf), int(dg))
             np.testing.assert_allclose(mu, g[t + '_mean'], rtol=1e-8, atol=1e-10, err_msg=t)
             np.testing.assert_allclose(var.reshape(g[t + '_var'].shape), g[t + '_var'], rtol=1e-7, atol=1e-10, err_msg=t)
+
+
+# ------------------------------------------------------------------------------------------- kernel algebra
+def test_product_kernel_algebra_matches_reference(mf):
+    """Linear / Bias / White / Add / Multiply (incl. nested, duplicate names, sample axis) against the reference's own
+    kernel classes run on the stand-in; parameter naming (`add_rbf0_lengthscale`, ...) must match too."""
+    g = gc.load('combo_kernels')
+    n = 0
+    for tag, got, want in gc.run_combo_kernels(g, torch.device('cpu')):
+        np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13, err_msg=tag)
+        n += 1
+    assert n == 8 * 2 * 3
+
+
+def test_product_modules_with_combination_kernels(mf):
+    """SVGP / exact GP / sparse GP over Add and Multiply kernels (primitive-by-primitive path): value and gradients."""
+    g = gc.load('combo_modules')
+    for i in range(int(g['n_cases'])):
+        loss, grads = gc.run_combo_module_case(mf, g, i, torch.device('cpu'))
+        np.testing.assert_allclose(loss, float(g['case%d_loss' % i]), rtol=1e-10, err_msg='case %d' % i)
+        for k, v in grads.items():
+            np.testing.assert_allclose(v, g['case%d_grad_%s' % (i, k)], rtol=1e-6, atol=1e-8, err_msg='case %d %s' % (i, k))
