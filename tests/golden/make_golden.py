@@ -11,6 +11,8 @@ Scenarios follow the reference's tests and notebooks:
   svgp_mb   MinibatchInferenceLoop trajectory (shuffled rollover batches, rv_scaling, grads / B)
   normal    testing/components/distributions/normal_test.py:35-109 (log_pdf, reparameterised draw with injected eps)
   svi       StochasticVariationalInference on a conjugate toy model with injected posterior samples
+  gpdist    GaussianProcess / ConditionalGaussianProcess distributions (testing/components/distributions/gp/gp_test.py,
+            cond_gp_test.py): log-pdf and draws with injected standard normals, with a sample axis, P = 1 and 3
   combo     kernel algebra (kernel_test.py:163-300: Linear / Bias / White / Add / Multiply) and the three GP modules with
             combination kernels: values and gradients
   sparsegp  testing/modules/sparsegpregression_test.py:41-196 fixture (+ Matern, P=1, larger M): bound, gradients,
@@ -35,6 +37,8 @@ from mxfusion import Model, Variable  # noqa: E402
 from mxfusion.common import config  # noqa: E402
 from mxfusion.components.variables import PositiveTransformation  # noqa: E402
 from mxfusion.components.distributions import Normal  # noqa: E402
+from mxfusion.components.distributions.gp.gp import GaussianProcess  # noqa: E402
+from mxfusion.components.distributions.gp.cond_gp import ConditionalGaussianProcess  # noqa: E402
 from mxfusion.components.distributions.gp.kernels import RBF, Matern12, Matern32, Matern52, Linear, Bias, White  # noqa: E402
 from mxfusion.modules.gp_modules import GPRegression, SVGPRegression, SparseGPRegression  # noqa: E402
 from mxfusion.inference import (Inference, GradBasedInference, MAP, BatchInferenceLoop, MinibatchInferenceLoop,  # noqa: E402
@@ -485,6 +489,52 @@ def golden_combo_modules():
     save('combo_modules', **out)
 
 
+# ------------------------------------------------------------------------------------------------ GP distributions
+def golden_gp_distributions():
+    rng = np.random.RandomState(11)
+    out = {}
+    i = 0
+    for kname in ('rbf', 'matern52'):
+        for S in (1, 3):
+            for P in (1, 3):
+                N, Nc, Din, ns = 7, 5, 2, 4
+                X, Xc = rng.rand(S, N, Din), rng.rand(S, Nc, Din)
+                Y, Yc = rng.randn(S, N, P), rng.randn(S, Nc, P)
+                ls, var = rng.rand(S, Din) + 0.5, rng.rand(S, 1) + 0.5
+                die = rng.randn(ns, N, P)
+                kern = KERNELS[kname](input_dim=Din, ARD=True, dtype=DT)
+                kp = {kern.name + '_lengthscale': nd(ls), kern.name + '_variance': nd(var)}
+                X_var, Xc_var, Yc_var = Variable(shape=(N, Din)), Variable(shape=(Nc, Din)), Variable(shape=(Nc, P))
+                tag = 'c%d' % i
+                out[tag + '_kernel'] = kname
+                for k, v in dict(X=X, Xc=Xc, Y=Y, Yc=Yc, ls=ls, var=var, die=die).items():
+                    out[tag + '_' + k] = v
+                # prior GP
+                gp = GaussianProcess.define_variable(X=X_var, kernel=kern, shape=(N, P), dtype=DT,
+                                                     rand_gen=MockMXNetRandomGenerator(nd(die.flatten()))).factor
+                variables = {gp.X.uuid: nd(X), gp.random_variable.uuid: nd(Y)}
+                variables.update({getattr(gp, n).uuid: v for n, v in kp.items()})
+                out[tag + '_gp_log_pdf'] = gp.log_pdf(F=mx.nd, variables=variables).asnumpy()
+                variables1 = {gp.X.uuid: nd(X[:1])}
+                variables1.update({getattr(gp, n).uuid: nd(v.asnumpy()[:1]) for n, v in kp.items()})
+                out[tag + '_gp_draw'] = gp.draw_samples(F=mx.nd, variables=variables1, num_samples=ns).asnumpy()
+                # conditional GP
+                kern2 = KERNELS[kname](input_dim=Din, ARD=True, dtype=DT)
+                cgp = ConditionalGaussianProcess.define_variable(
+                    X=X_var, X_cond=Xc_var, Y_cond=Yc_var, kernel=kern2, shape=(N, P), dtype=DT,
+                    rand_gen=MockMXNetRandomGenerator(nd(die.flatten()))).factor
+                variables = {cgp.X.uuid: nd(X), cgp.X_cond.uuid: nd(Xc), cgp.Y_cond.uuid: nd(Yc),
+                             cgp.random_variable.uuid: nd(Y)}
+                variables.update({getattr(cgp, n).uuid: v for n, v in kp.items()})
+                out[tag + '_cgp_log_pdf'] = cgp.log_pdf(F=mx.nd, variables=variables).asnumpy()
+                variables1 = {cgp.X.uuid: nd(X[:1]), cgp.X_cond.uuid: nd(Xc[:1]), cgp.Y_cond.uuid: nd(Yc[:1])}
+                variables1.update({getattr(cgp, n).uuid: nd(v.asnumpy()[:1]) for n, v in kp.items()})
+                out[tag + '_cgp_draw'] = cgp.draw_samples(F=mx.nd, variables=variables1, num_samples=ns).asnumpy()
+                i += 1
+    out['n_cases'] = i
+    save('gp_distributions', **out)
+
+
 if __name__ == '__main__':
     golden_kernels()
     golden_svgp()
@@ -495,5 +545,6 @@ if __name__ == '__main__':
     golden_svi()
     golden_predict()
     golden_sparsegp()
+    golden_gp_distributions()
     golden_combo_kernels()
     golden_combo_modules()

@@ -308,3 +308,39 @@ def run_combo_module_case(mf, g, i, device):
     loss, loss_g = infr.create_executor()(None, torch.tensor(X, device=device), torch.tensor(Y, device=device))
     loss_g.backward()
     return float(loss), {k: param_grad(infr, v) for k, v in gvars.items()}
+
+
+# ------------------------------------------------------------------------------------------------ GP distributions (8f-3)
+def run_gp_distributions(g, device):
+    """Yields (tag, got, want) for log-pdf and injected-noise draws of GaussianProcess / ConditionalGaussianProcess."""
+    from mxfusion_b200 import F, Variable
+    from mxfusion_b200.components.distributions import GaussianProcess, ConditionalGaussianProcess, \
+        MockMXNetRandomGenerator
+    T = lambda a: torch.tensor(a, device=device)
+    for i in range(int(g['n_cases'])):
+        c = lambda k: g['c%d_%s' % (i, k)]
+        X, Xc, Y, Yc, ls, var, die = (c(k) for k in ('X', 'Xc', 'Y', 'Yc', 'ls', 'var', 'die'))
+        N, Din = X.shape[1:]
+        Nc, P, ns = Xc.shape[1], Y.shape[2], die.shape[0]
+        cls = kernel_class(c('kernel'))
+        X_var, Xc_var, Yc_var = Variable(shape=(N, Din)), Variable(shape=(Nc, Din)), Variable(shape=(Nc, P))
+        kern = cls(input_dim=Din, ARD=True)
+        gp = GaussianProcess.define_variable(X=X_var, kernel=kern, shape=(N, P),
+                                             rand_gen=MockMXNetRandomGenerator(T(die.flatten()))).factor
+        kp = {kern.name + '_lengthscale': ls, kern.name + '_variance': var}
+        variables = {gp.X.uuid: T(X), gp.random_variable.uuid: T(Y)}
+        variables.update({getattr(gp, n).uuid: T(v) for n, v in kp.items()})
+        yield 'c%d gp log_pdf' % i, gp.log_pdf(F=F, variables=variables).cpu().numpy(), c('gp_log_pdf')
+        variables1 = {gp.X.uuid: T(X[:1])}
+        variables1.update({getattr(gp, n).uuid: T(v[:1]) for n, v in kp.items()})
+        yield 'c%d gp draw' % i, gp.draw_samples(F=F, variables=variables1, num_samples=ns).cpu().numpy(), c('gp_draw')
+        kern2 = cls(input_dim=Din, ARD=True)
+        cgp = ConditionalGaussianProcess.define_variable(X=X_var, X_cond=Xc_var, Y_cond=Yc_var, kernel=kern2,
+                                                         shape=(N, P),
+                                                         rand_gen=MockMXNetRandomGenerator(T(die.flatten()))).factor
+        variables = {cgp.X.uuid: T(X), cgp.X_cond.uuid: T(Xc), cgp.Y_cond.uuid: T(Yc), cgp.random_variable.uuid: T(Y)}
+        variables.update({getattr(cgp, n).uuid: T(v) for n, v in kp.items()})
+        yield 'c%d cgp log_pdf' % i, cgp.log_pdf(F=F, variables=variables).cpu().numpy(), c('cgp_log_pdf')
+        variables1 = {cgp.X.uuid: T(X[:1]), cgp.X_cond.uuid: T(Xc[:1]), cgp.Y_cond.uuid: T(Yc[:1])}
+        variables1.update({getattr(cgp, n).uuid: T(v[:1]) for n, v in kp.items()})
+        yield 'c%d cgp draw' % i, cgp.draw_samples(F=F, variables=variables1, num_samples=ns).cpu().numpy(), c('cgp_draw')

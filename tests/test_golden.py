@@ -260,3 +260,21 @@ def test_product_modules_with_combination_kernels(mf):
         np.testing.assert_allclose(loss, float(g['case%d_loss' % i]), rtol=1e-10, err_msg='case %d' % i)
         for k, v in grads.items():
             np.testing.assert_allclose(v, g['case%d_grad_%s' % (i, k)], rtol=1e-6, atol=1e-8, err_msg='case %d %s' % (i, k))
+
+
+# ------------------------------------------------------------------------------------------- GP distributions
+def test_product_gp_distributions_match_reference(mf):
+    """GaussianProcess / ConditionalGaussianProcess log-pdf and injected-noise draws (sample axis, P = 1 and 3; the
+    conditional log-pdf keeps the reference's sum-over-outputs-before-squaring, cond_gp.py:170) and an independent
+    check of the prior log-pdf against scipy's multivariate normal."""
+    import scipy.stats
+    g = gc.load('gp_distributions')
+    n = 0
+    for tag, got, want in gc.run_gp_distributions(g, torch.device('cpu')):
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11, err_msg=tag)
+        n += 1
+    assert n == 4 * int(g['n_cases'])
+    # scipy anchor (gp_test.py:43-75): case 0 is RBF, S = 1, P = 1
+    K = ok.K(0, g['c0_X'], g['c0_ls'], g['c0_var'])[0]
+    want = scipy.stats.multivariate_normal.logpdf(g['c0_Y'][0, :, 0], mean=None, cov=K)
+    np.testing.assert_allclose(g['c0_gp_log_pdf'][0], want, rtol=1e-9)

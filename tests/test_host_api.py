@@ -159,3 +159,29 @@ def test_meanfield_svi_bnn_like_model_trains(mf):
     infr.run(max_iter=150, learning_rate=1e-2, y=y, x=x)
     l1, _ = infr.create_executor()(None, torch.tensor(y), torch.tensor(x))
     assert float(l1) < float(l0)
+
+
+def test_forward_sampling_draws_from_a_gp_prior(mf):
+    """ForwardSamplingAlgorithm over a model whose output has a GaussianProcess prior (forward_sampling.py:24-56,
+    gp.py:123-153): with injected standard normals the draw is chol(K) @ die."""
+    from mxfusion_b200.components.distributions import GaussianProcess, MockMXNetRandomGenerator
+    from mxfusion_b200.components.distributions.gp.kernels import RBF
+    from mxfusion_b200.inference import Inference, ForwardSamplingAlgorithm
+    from oracle import kernels as ok
+    rng = np.random.RandomState(3)
+    N, ns = 9, 5
+    X = rng.rand(N, 2)
+    die = rng.randn(ns, N, 1)
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, 2))
+    kern = RBF(input_dim=2, variance=1.3, lengthscale=0.7)
+    m.Y = GaussianProcess.define_variable(X=m.X, kernel=kern, shape=(m.N, 1),
+                                          rand_gen=MockMXNetRandomGenerator(torch.tensor(die.flatten())))
+    infr = Inference(ForwardSamplingAlgorithm(m, observed=[m.X], num_samples=ns, target_variables=[m.Y]))
+    infr.initialize(X=X.shape)
+    with torch.no_grad():
+        got = infr.run(X=X)[0].numpy()
+    K = ok.K(0, X[None], np.array([[0.7]]), np.array([[1.3]]))[0]
+    want = np.linalg.cholesky(K) @ die
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)
