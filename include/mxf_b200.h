@@ -193,6 +193,22 @@ int mxf_softplus_bwd(int dtype, const void* x, const void* gy, void* gx, int64_t
 int mxf_svgp_bwd_assemble(int dtype, const void* Phi, const void* T, const void* U, const void* mt, const void* v,
                           const void* coef, void* out, int64_t ldo, int64_t sO, int S, int M, int P, void* stream);
 
+/* Scalar head / tail of the SVGP bound (svgp_regression.py:94-108) on the per-sample reductions, one launch each way
+ * instead of ~20 scalar operators: with nv = noise[s], kv = kvar[s], beta = 1/nv,
+ *   Q     = -sumr2/2 - P B kv/2 - P (trPhiT - trPhi)/2
+ *   logL  = scale (beta Q - B P (log 2pi + log nv)/2) + P (M/2 + sldLs - sldL) - P trT/2 - mm/2
+ * (sumr2 = sum (Y - A^T mt)^2, trPhi = tr(A A^T), trT = tr(C C^T), trPhiT = tr(Phi T), mm = sum mt^2, sldL / sldLs =
+ * sumlogdiag of the two factors).  Outputs logL, beta, Q (S each).  The adjoint head writes coef (S x 6, the layout
+ * mxf_svgp_bwd_assemble reads), gsb = g scale beta, -gsb, d logL / d noise_var, the Kff_diag part of d / d variance, and the
+ * per-sample constants -g and -1 that the remaining axpby launches take as device coefficients. */
+int mxf_svgp_bound_fwd(int dtype, int S, int P, int B, int M, double scale, const void* sumr2, const void* trPhi,
+                       const void* trT, const void* trPhiT, const void* mm, const void* sldL, const void* sldLs,
+                       const void* noise, int64_t sNoise, const void* kvar, int64_t sKvar, void* logL, void* beta,
+                       void* Q, void* stream);
+int mxf_svgp_coef_bwd(int dtype, int S, int P, int B, double scale, const void* g, const void* beta, const void* Q,
+                      void* coef, void* gsb, void* neg_gsb, void* dnoise, void* dkvar_diag, void* neg_g, void* minus_one,
+                      void* stream);
+
 /* ---- Normal distribution: MC-ELBO pieces (normal.py:52-92, factor_graph.py:223) ----
  * Fused log-density + sample-mean + sum:
  *   out[0] = scale * (1/S) * sum_{s,i} [ -0.5 log 2pi - 0.5 log v - (x-m)^2 / (2 v) ]

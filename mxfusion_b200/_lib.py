@@ -53,6 +53,8 @@ def _declare(lib):
         'mxf_softplus_fwd': (i, [i, p, d, p, l, p]),
         'mxf_softplus_bwd': (i, [i, p, p, p, l, p]),
         'mxf_svgp_bwd_assemble': (i, [i, p, p, p, p, p, p, p, l, l, i, i, i, p]),
+        'mxf_svgp_bound_fwd': (i, [i, i, i, i, i, d, p, p, p, p, p, p, p, p, l, p, l, p, p, p, p]),
+        'mxf_svgp_coef_bwd': (i, [i, i, i, i, d, p, p, p, p, p, p, p, p, p, p, p]),
         'mxf_normal_logpdf_sum': (i, [i, p, l, p, l, p, l, i, l, d, p, p]),
         'mxf_normal_logpdf_sum_bwd': (i, [i, p, l, p, l, p, l, i, l, d, p, p, p, p, p]),
         'mxf_normal_reparam': (i, [i, p, p, l, p, l, i, l, u, u, p, p, p, p]),

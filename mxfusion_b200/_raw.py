@@ -437,3 +437,27 @@ def mlp_tanh_bwd(x, Ws, bs, gout):
     check(lib().mxf_mlp_tanh_bwd(dtype_code(x), L, widths, ptr(x), _bstride(x, S), Wp, sW, bp, sb, ptr(gout), dWp, dbp,
                                  S, B, stream_ptr()), 'mxf_mlp_tanh_bwd')
     return dWs, dbs
+
+
+def svgp_bound_fwd(P, B, M, scale, sumr2, trPhi, trT, trPhiT, mm, sldL, sldLs, noise, kvar):
+    """(logL, beta, Q), each (S,), from the per-sample reductions; noise / kvar are (S|1, 1)."""
+    require_cuda(sumr2, trPhi, trT, trPhiT, mm, sldL, sldLs, noise, kvar)
+    S = sumr2.shape[0]
+    out = torch.empty((3, S), dtype=sumr2.dtype, device=sumr2.device)
+    check(lib().mxf_svgp_bound_fwd(dtype_code(sumr2), S, int(P), int(B), int(M), float(scale), ptr(_c(sumr2)),
+                                   ptr(_c(trPhi)), ptr(_c(trT)), ptr(_c(trPhiT)), ptr(_c(mm)), ptr(_c(sldL)),
+                                   ptr(_c(sldLs)), ptr(noise), _bstride(noise, S), ptr(kvar), _bstride(kvar, S),
+                                   ptr(out[0]), ptr(out[1]), ptr(out[2]), stream_ptr()), 'mxf_svgp_bound_fwd')
+    return out[0], out[1], out[2]
+
+
+def svgp_coef_bwd(P, B, scale, g, beta, Q):
+    """(coef (S,6), gsb, -gsb, dnoise, dkvar_diag, -g, -1) for the adjoint of the SVGP bound."""
+    require_cuda(g, beta, Q)
+    S = g.shape[0]
+    coef = torch.empty((S, 6), dtype=g.dtype, device=g.device)
+    out = torch.empty((6, S), dtype=g.dtype, device=g.device)
+    check(lib().mxf_svgp_coef_bwd(dtype_code(g), S, int(P), int(B), float(scale), ptr(_c(g)), ptr(_c(beta)), ptr(_c(Q)),
+                                  ptr(coef), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), ptr(out[4]),
+                                  ptr(out[5]), stream_ptr()), 'mxf_svgp_coef_bwd')
+    return coef, out[0], out[1], out[2], out[3], out[4], out[5]

@@ -15,7 +15,10 @@ def add_sample_dimension_to_arrays(F, arrays, out=None):
 
 
 def expectation(F, array):
-    """Mean over the sample axis (runtime_variable.py:53-60)."""
+    """Mean over the sample axis (runtime_variable.py:53-60).  With a single sample the mean is the array itself: a view,
+    not a kernel launch (the reference launches `F.mean` regardless; every 2 us launch counts in a 1.4 ms step)."""
+    if array.shape[0] == 1:
+        return array[0]
     return torch.mean(array, dim=0)
 
 

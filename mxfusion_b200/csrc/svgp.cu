@@ -89,6 +89,56 @@ svgp_bwd_assemble_kernel(const T* __restrict__ Phi, const T* __restrict__ Tm, co
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Scalar head / tail of the SVGP bound (svgp_regression.py:94-108): everything that happens on the ~10 reduced
+// scalars of a sample.  The reference issues ~20 scalar NDArray operators here (and autograd twice as many on the way
+// back); as separate launches they are a 100 us chain of 2 us kernels in a 1.4 ms step.  One thread per sample.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void svgp_bound_fwd_kernel(int S, T P, T B, T M, T scale, const T* __restrict__ sumr2,
+                                      const T* __restrict__ trPhi, const T* __restrict__ trT,
+                                      const T* __restrict__ trPhiT, const T* __restrict__ mm,
+                                      const T* __restrict__ sldL, const T* __restrict__ sldLs,
+                                      const T* __restrict__ noise, int64_t sNoise, const T* __restrict__ kvar,
+                                      int64_t sKvar, T* __restrict__ logL, T* __restrict__ beta_out, T* __restrict__ Q_out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const T nv = noise[s * sNoise], kv = kvar[s * sKvar];
+    const T beta = T(1) / nv;
+    const T Q = T(-0.5) * sumr2[s] - (T(0.5) * P * B) * kv - (T(0.5) * P) * (trPhiT[s] - trPhi[s]);
+    const T data = beta * Q - (T(0.5) * B * P) * (T(1.8378770664093453) + Num<T>::log_(nv));       // :98-107
+    const T neg_kl = P * (T(0.5) * M + sldLs[s] - sldL[s]) - (T(0.5) * P) * trT[s] - T(0.5) * mm[s];   // :94-96
+    logL[s] = scale * data + neg_kl;                                                                  // :108
+    beta_out[s] = beta;
+    Q_out[s] = Q;
+}
+
+// coef[s][0..5] = {gP/2, g s P beta/2, g/2, g s beta/2, g s P beta, g s beta} (see mxf_svgp_bwd_assemble), plus
+// gsb = g s beta, its negative, the noise-variance gradient and the Kff_diag part of the kernel-variance gradient.
+template <typename T>
+__global__ void svgp_coef_bwd_kernel(int S, T P, T B, T scale, const T* __restrict__ g, const T* __restrict__ beta,
+                                     const T* __restrict__ Q, T* __restrict__ coef, T* __restrict__ gsb_out,
+                                     T* __restrict__ neg_gsb_out, T* __restrict__ dnoise, T* __restrict__ dkvar_diag,
+                                     T* __restrict__ neg_g_out, T* __restrict__ minus_one_out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const T gg = g[s], b = beta[s];
+    const T gsb = gg * (scale * b);
+    coef[6 * s + 0] = gg * (T(0.5) * P);
+    coef[6 * s + 1] = gsb * (T(0.5) * P);
+    coef[6 * s + 2] = T(0.5) * gg;
+    coef[6 * s + 3] = T(0.5) * gsb;
+    coef[6 * s + 4] = gsb * P;
+    coef[6 * s + 5] = gsb;
+    gsb_out[s] = gsb;
+    neg_gsb_out[s] = -gsb;
+    dnoise[s] = gg * scale * (-b * b * Q[s] - (T(0.5) * B * P) * b);
+    dkvar_diag[s] = -gsb * (T(0.5) * P * B);                          // Kff_diag term (:100)
+    neg_g_out[s] = -gg;
+    minus_one_out[s] = T(-1);
+}
+
 static inline int grid1d(int64_t n) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)8 * kNumSMs));
 }
@@ -134,5 +184,31 @@ extern "C" int mxf_svgp_bwd_assemble(int dtype, const void* Phi, const void* T_,
     MXF_DISPATCH_DTYPE(dtype, svgp_bwd_assemble_kernel<T><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
                                   (const T*)Phi, (const T*)T_, (const T*)U, (const T*)mt, (const T*)v,
                                   (const T*)coef, (T*)out, ldo, sO, M, P));
+    return after_launch();
+}
+
+extern "C" int mxf_svgp_bound_fwd(int dtype, int S, int P, int B, int M, double scale, const void* sumr2,
+                                  const void* trPhi, const void* trT, const void* trPhiT, const void* mm,
+                                  const void* sldL, const void* sldLs, const void* noise, int64_t sNoise,
+                                  const void* kvar, int64_t sKvar, void* logL, void* beta, void* Q, void* stream) {
+    if (!sumr2 || !trPhi || !trT || !trPhiT || !mm || !sldL || !sldLs || !noise || !kvar || !logL || !beta || !Q || S < 0)
+        return MXF_EINVAL;
+    if (S == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, svgp_bound_fwd_kernel<T><<<cdiv(S, 128), 128, 0, (cudaStream_t)stream>>>(
+                                  S, (T)P, (T)B, (T)M, (T)scale, (const T*)sumr2, (const T*)trPhi, (const T*)trT,
+                                  (const T*)trPhiT, (const T*)mm, (const T*)sldL, (const T*)sldLs, (const T*)noise,
+                                  sNoise, (const T*)kvar, sKvar, (T*)logL, (T*)beta, (T*)Q));
+    return after_launch();
+}
+
+extern "C" int mxf_svgp_coef_bwd(int dtype, int S, int P, int B, double scale, const void* g, const void* beta,
+                                 const void* Q, void* coef, void* gsb, void* neg_gsb, void* dnoise, void* dkvar_diag,
+                                 void* neg_g, void* minus_one, void* stream) {
+    if (!g || !beta || !Q || !coef || !gsb || !neg_gsb || !dnoise || !dkvar_diag || !neg_g || !minus_one || S < 0)
+        return MXF_EINVAL;
+    if (S == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, svgp_coef_bwd_kernel<T><<<cdiv(S, 128), 128, 0, (cudaStream_t)stream>>>(
+                                  S, (T)P, (T)B, (T)scale, (const T*)g, (const T*)beta, (const T*)Q, (T*)coef, (T*)gsb,
+                                  (T*)neg_gsb, (T*)dnoise, (T*)dkvar_diag, (T*)neg_g, (T*)minus_one));
     return after_launch();
 }

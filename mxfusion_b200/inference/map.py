@@ -23,4 +23,5 @@ class MAP(VariationalInference):
             if v.type == VariableType.RANDVAR and v not in self._observed:
                 variables[v.uuid] = variables[self.posterior[v].factor.location.uuid]
         logL = self.model.log_pdf(F=F, variables=variables)
-        return -logL, -logL
+        loss = -logL
+        return loss, loss

@@ -139,15 +139,17 @@ class FactorGraph(object):
                     variables[var.uuid] = v
             elif isinstance(f, Distribution):
                 if targets is None or f.random_variable.uuid in targets:
-                    logL = logL + f.log_pdf_sum(F=F, variables=variables)
+                    term = f.log_pdf_sum(F=F, variables=variables)
+                    logL = term if (isinstance(logL, float) and logL == 0.) else logL + term
             elif isinstance(f, Module):
                 if targets is None:
                     module_targets = [v.uuid for _, v in f.outputs if v.uuid in variables]
                 else:
                     module_targets = [v.uuid for _, v in f.outputs if v.uuid in targets]
                 if len(module_targets) > 0:
-                    logL = logL + torch.sum(expectation(F, f.log_pdf(F=F, variables=variables,
-                                                                     targets=module_targets)))
+                    e = expectation(F, f.log_pdf(F=F, variables=variables, targets=module_targets))
+                    term = e.reshape(()) if e.numel() == 1 else torch.sum(e)     # F.sum of one element: a view
+                    logL = term if (isinstance(logL, float) and logL == 0.) else logL + term
             else:
                 raise ModelSpecificationError("There is an object in the factor graph that isn't a factor.")
         return logL

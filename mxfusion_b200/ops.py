@@ -305,7 +305,14 @@ class _SVGPLogPdf(torch.autograd.Function):
             RH[:, :, B + M + P:].zero_()
         RH = R.trsm_solve(L, pk, RH)                            # :85-87  A = L^-1 Kuf, C = L^-1 Ls, mt = L^-1 mu
         A, C, mt = RH[:, :, :B], RH[:, :, B:B + M], RH[:, :, B + M:B + M + P]
-        Phi = R.copy_ltu(R.gemm(A, A, transB=True, tri=True))
+        G = _split_k(M, B) if S == 1 else 1
+        if G > 1:
+            # Phi = A A^T is M x M x B: 36-72 output tiles on 148 SMs with a 4096-deep K loop each -> split K into G slabs
+            # (batched GEMM over strided views of the same buffer) and add the partial lower triangles
+            Av = A.as_strided((G, M, B // G), (B // G, RH.stride(1), 1))
+            Phi = R.copy_ltu(R.gemm(Av, Av, transB=True, tri=True).sum(dim=0, keepdim=True))
+        else:
+            Phi = R.copy_ltu(R.gemm(A, A, transB=True, tri=True))
         T = R.copy_ltu(R.gemm(C, C, transB=True, tri=True))
         G1 = R.gemm(A, mt, transA=True)                         # :89  (S,B,P)
         sumr2 = R.reduce(R.RED_SUMSQDIFF, Y, G1)
@@ -314,12 +321,10 @@ class _SVGPLogPdf(torch.autograd.Function):
         trPhiT = R.reduce(R.RED_DOT, Phi, T)
         mm = R.reduce(R.RED_SUMSQ, mt)
         sldL, sldLs = R.sumlogdiag(L), R.sumlogdiag(Ls)
-        nv, kv = noise[:, 0], kvar[:, 0]
-        beta = 1.0 / nv
-        Q = -0.5 * sumr2 - (0.5 * P * B) * kv - (0.5 * P) * (trPhiT - trPhi)
-        data = beta * Q - (0.5 * B * P) * (_LOG2PI + torch.log(nv))          # :98-107
-        neg_kl = P * (0.5 * M + sldLs - sldL) - (0.5 * P) * trT - 0.5 * mm   # :94-96 (`KL_u` is minus the KL)
-        logL = scale * data + neg_kl                                         # :108
+        # :94-108 on the reduced scalars in one launch (`KL_u` of the reference is minus the KL):
+        #   Q = -sumr2/2 - P B kv/2 - P (tr(Phi T) - tr Phi)/2,  data = beta Q - B P (log 2pi + log nv)/2,
+        #   logL = scale data + P (M/2 + sld(Ls) - sld(L)) - P tr(T)/2 - |mt|^2/2
+        logL, beta, Q = R.svgp_bound_fwd(P, B, M, scale, sumr2, trPhi, trT, trPhiT, mm, sldL, sldLs, noise, kvar)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)                    # join: S^-1 is ready for the adjoint
         ctx.kind, ctx.scale, ctx.dims = kind, scale, (S, B, P, M)
@@ -336,9 +341,7 @@ class _SVGPLogPdf(torch.autograd.Function):
         A, mt = RH[:, :, :B], RH[:, :, B + M:B + M + P].contiguous()
         sc = ctx.scale
         need = ctx.needs_input_grad      # (kind, jitter, scale, X, Y, Z, noise, mu, W, dvec, ls, kvar)
-        g = g.contiguous()
-        gsb = g * (sc * beta)
-        coef = torch.stack([g * (0.5 * P), gsb * (0.5 * P), 0.5 * g, 0.5 * gsb, gsb * P, gsb], dim=1).contiguous()
+        coef, gsb, neg_gsb, dnoise_s, dkvar_diag, neg_g, minus1 = R.svgp_coef_bwd(P, B, sc, g.contiguous(), beta, Q)
         U = R.gemm(Phi, T)
         v = R.gemm(A, Y)
         R.gemm(Phi, mt, alpha=-1.0, beta=1.0, C=v)              # v = A (Y - A^T mt)
@@ -370,7 +373,7 @@ class _SVGPLogPdf(torch.autograd.Function):
         F2 = torch.empty((S, M, 2 * M + PP), dtype=dt, device=dev)
         R.transpose(E4[:, :, :M], out=F2[:, :, :M])
         R.transpose(E4[:, :, M:2 * M], out=F2[:, :, M:2 * M])
-        F2[:, :, 2 * M:2 * M + P].copy_(R.axpby_dev(gsb, v, -g, mt))
+        F2[:, :, 2 * M:2 * M + P].copy_(R.axpby_dev(gsb, v, neg_g, mt))
         if PP > P:
             F2[:, :, 2 * M + P:].zero_()
         F2 = R.trsm_solve(L, pk, F2, transpose=True)
@@ -380,17 +383,16 @@ class _SVGPLogPdf(torch.autograd.Function):
         if side is None:
             dZ1, dX, dls1, dvar1 = kuf_branch()
         # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 (S^-1 from the forward pass); W adjoint 2 Sbar W ; diag adjoint diag(Sbar)
-        minus1 = torch.full((S,), -1.0, dtype=dt, device=dev)
         Sbar = R.axpby_dev(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M].contiguous())
         dW = R.gemm(Sbar, W, alpha=2.0)
         dd = R.get_diag(Sbar)
-        dnoise = (g * sc * (-beta * beta * Q - (0.5 * B * P) * beta)).unsqueeze(1)
-        dY = R.axpby_dev(-gsb, Y, gsb, G1) if need[4] else None             # -g s beta (Y - A^T mt)
+        dnoise = dnoise_s.unsqueeze(1)
+        dY = R.axpby_dev(neg_gsb, Y, gsb, G1) if need[4] else None          # -g s beta (Y - A^T mt)
         if side is not None:
             cur.wait_stream(side)                                            # join the Kuf branch
         dZ = dZ1 + dZ2
         dls = dls1 + dls2
-        dkvar = dvar1 + dvar2 - (gsb * (0.5 * P * B)).unsqueeze(1)          # Kff_diag term (:100)
+        dkvar = dvar1 + dvar2 + dkvar_diag.unsqueeze(1)                     # Kff_diag term (:100)
         return None, None, None, dX, dY, dZ, dnoise, dmu, dW, dd, dls, dkvar
 
 
@@ -531,6 +533,15 @@ def _stats_chunk(M, S):
     G = _syrk_splits(M) if S == 1 else 1
     tiles = max(37, (STATS_CHUNK_ROWS // 256) // 37 * 37)
     return (tiles * 256) // (4 * G) * (4 * G)
+
+
+def _split_k(M, K):
+    """K slabs for an M x M x K product with lower tiles only: the largest count <= _syrk_splits(M) that divides K into
+    slabs whose length is a multiple of 4 elements (16-byte TMA rows)."""
+    for G in range(_syrk_splits(M), 1, -1):
+        if K % (4 * G) == 0:
+            return G
+    return 1
 
 
 def _syrk_splits(M):

@@ -254,3 +254,20 @@ def mlp_tanh_bwd(x, Ws, bs, gout):
         br = [None if b is None else b.detach().clone().requires_grad_() for b in bs]
         (_mlp(x.detach(), Wr, br) * gout).sum().backward()
     return [w.grad for w in Wr], [None if b is None else b.grad for b in br]
+
+
+def svgp_bound_fwd(P, B, M, scale, sumr2, trPhi, trT, trPhiT, mm, sldL, sldLs, noise, kvar):
+    nv, kv = noise[:, 0], kvar[:, 0]
+    beta = 1.0 / nv
+    Q = -0.5 * sumr2 - (0.5 * P * B) * kv - (0.5 * P) * (trPhiT - trPhi)
+    data = beta * Q - (0.5 * B * P) * (math.log(2.0 * math.pi) + torch.log(nv))
+    neg_kl = P * (0.5 * M + sldLs - sldL) - (0.5 * P) * trT - 0.5 * mm
+    S = sumr2.shape[0]
+    return (scale * data + neg_kl).expand(S).contiguous(), beta.expand(S).contiguous(), Q.expand(S).contiguous()
+
+
+def svgp_coef_bwd(P, B, scale, g, beta, Q):
+    gsb = g * (scale * beta)
+    coef = torch.stack([g * (0.5 * P), gsb * (0.5 * P), 0.5 * g, 0.5 * gsb, gsb * P, gsb], dim=1).contiguous()
+    return (coef, gsb, -gsb, g * scale * (-beta * beta * Q - (0.5 * B * P) * beta), -gsb * (0.5 * P * B), -g,
+            torch.full_like(g, -1.0))
