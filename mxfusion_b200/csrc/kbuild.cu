@@ -560,6 +560,153 @@ kbuild_bwd_tile_kernel(const T* __restrict__ X, const T* __restrict__ X2, const 
     if (tid == 0) atomicAdd(&ACC[(int64_t)s * (ls_len + 1) + ls_len], tot);
 }
 
+// Register-blocked variant for D <= 16 (DP = D rounded up to 4 / 8 / 16): the thread's scaled column vector lives in
+// registers, the scaled row vectors (zero-padded to DP) are read as 16-byte warp-uniform broadcasts, |a'|^2 is staged
+// once per row, and -- when the column operand needs no gradient (COLS = false: the K(Z, X) adjoint of the SVGP / sparse-GP
+// step, X being data) -- the column sums never leave registers: the lengthscale gradient's column part
+// sum_j b'_jd^2 CS_j is formed directly and its row part comes from RS / RB in the finalise kernel.  ncu on the first
+// kernel (1024 x 4096 x 8): 22 M warp instructions, issue-bound at 20 % occupancy; this one executes about a third.
+template <typename T, int KIND, int TR, bool COLS, int DP>
+__global__ void __launch_bounds__(KBB_THREADS)
+kbuild_bwd_tile2_kernel(const T* __restrict__ X, const T* __restrict__ X2, const T* __restrict__ ls,
+                        int ls_len, const T* __restrict__ var, const T* __restrict__ G, int64_t ldg,
+                        T* __restrict__ RS, T* __restrict__ RB, T* __restrict__ CS, T* __restrict__ CB,
+                        T* __restrict__ ACC, int N, int N2, int D, int64_t sX, int64_t sX2,
+                        int64_t sLs, int64_t sVar, int64_t sG) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* a_s = reinterpret_cast<T*>(smem_raw);        // [TR][DP]  a' rows, zero-padded
+    T* bT_s = a_s + TR * DP;                        // [DP][KBB_TN] b' columns (transposed)
+    T* h_s = bT_s + DP * KBB_TN;                    // [TR][KBB_TN+1]
+    T* na_s = h_s + TR * (KBB_TN + 1);              // [TR]  |a'|^2
+    T* red = na_s + TR;                             // [32 * (DP + 1)]
+    constexpr int HS = KBB_TN + 1;
+
+    const int s = blockIdx.z;
+    const T* Xs = X + (int64_t)s * sX;
+    const T* X2s = X2 + (int64_t)s * sX2;
+    const T* lss = ls + (int64_t)s * sLs;
+    const T v = var[(int64_t)s * sVar];
+    const T* Gs = G + (int64_t)s * sG;
+    const int i0 = blockIdx.y * TR, j0 = blockIdx.x * KBB_TN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int e = tid; e < TR * DP; e += KBB_THREADS) {
+        const int r = e / DP, d = e - r * DP;
+        const int i = i0 + r;
+        a_s[e] = (i < N && d < D) ? Xs[(int64_t)i * D + d] / lss[ls_len == 1 ? 0 : d] : T(0);
+    }
+    for (int e = tid; e < KBB_TN * DP; e += KBB_THREADS) {
+        const int c = e / DP, d = e - c * DP;
+        const int j = j0 + c;
+        bT_s[d * KBB_TN + c] = (j < N2 && d < D) ? X2s[(int64_t)j * D + d] / lss[ls_len == 1 ? 0 : d] : T(0);
+    }
+    __syncthreads();
+    for (int r = tid; r < TR; r += KBB_THREADS) {
+        T na = 0;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) na = fma(a_s[r * DP + d], a_s[r * DP + d], na);
+        na_s[r] = na;
+    }
+    // phase H: thread per column, its b' vector in registers
+    const int j = j0 + tid;
+    T b[DP];
+    T nb = 0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { b[d] = bT_s[d * KBB_TN + tid]; nb = fma(b[d], b[d], nb); }
+    __syncthreads();
+    T gk = 0, cs = 0;
+    for (int rb = 0; rb < TR; rb += 8) {
+        T g8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + rb + u;
+            g8[u] = (i < N && j < N2) ? Gs[(int64_t)i * ldg + j] : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = rb + u;
+            T dot = 0;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) dot = fma(a_s[r * DP + d], b[d], dot);
+            const T r2 = na_s[r] + nb - T(2) * dot;
+            T kv;
+            const T dk = kern_dr2<T, KIND>(r2, v, &kv);
+            const T h = g8[u] * dk;             // g8 is 0 outside the matrix, so h and the sums below are too
+            gk = fma(g8[u], kv, gk);
+            cs += h;
+            h_s[r * HS + tid] = h;
+        }
+    }
+    __syncthreads();
+
+    if (COLS) {
+        // phase A: column sums (thread per column)
+        if (j < N2) {
+            atomicAdd(&CS[(int64_t)s * N2 + j], cs);
+            T cb[DP];
+#pragma unroll
+            for (int d = 0; d < DP; ++d) cb[d] = T(0);
+            for (int r = 0; r < TR; ++r) {
+                const T h = h_s[r * HS + tid];
+#pragma unroll
+                for (int d = 0; d < DP; ++d) cb[d] = fma(h, a_s[r * DP + d], cb[d]);
+            }
+#pragma unroll
+            for (int d = 0; d < DP; ++d)
+                if (d < D) atomicAdd(&CB[((int64_t)s * N2 + j) * D + d], cb[d]);
+        }
+    } else {
+        // column part of the lengthscale gradient, -(2 / l_d) sum_j b'_jd^2 CS_j: warp sums, then one atomic per d per CTA
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            const T t = warp_sum(cs * b[d] * b[d]);
+            if (lane == 0) red[warp * DP + d] = t;
+        }
+        __syncthreads();
+        if (tid < D) {
+            T t = 0;
+            for (int w = 0; w < KBB_THREADS / 32; ++w) t += red[w * DP + tid];
+            const T l = lss[ls_len == 1 ? 0 : tid];
+            atomicAdd(&ACC[(int64_t)s * (ls_len + 1) + (ls_len == 1 ? 0 : tid)], t * (T(-2) / l));
+        }
+        __syncthreads();
+    }
+    // phase B: row sums.  A warp owns TR / 4 rows; its lanes stride over the columns, then a warp reduction per quantity.
+    {
+        constexpr int RPW = TR / (KBB_THREADS / 32);
+        T bb[KBB_TN / 32][DP];
+#pragma unroll
+        for (int q = 0; q < KBB_TN / 32; ++q)
+#pragma unroll
+            for (int d = 0; d < DP; ++d) bb[q][d] = bT_s[d * KBB_TN + lane + 32 * q];
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp * RPW + rr, i = i0 + r;
+            T rs = 0, rbv[DP];
+#pragma unroll
+            for (int d = 0; d < DP; ++d) rbv[d] = T(0);
+#pragma unroll
+            for (int q = 0; q < KBB_TN / 32; ++q) {
+                const T h = h_s[r * HS + lane + 32 * q];
+                rs += h;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) rbv[d] = fma(h, bb[q][d], rbv[d]);
+            }
+            rs = warp_sum(rs);
+#pragma unroll
+            for (int d = 0; d < DP; ++d) rbv[d] = warp_sum(rbv[d]);
+            if (i < N) {
+                if (lane == 0) atomicAdd(&RS[(int64_t)s * N + i], rs);
+#pragma unroll
+                for (int d = 0; d < DP; ++d)
+                    if (lane == d && d < D) atomicAdd(&RB[((int64_t)s * N + i) * D + d], rbv[d]);
+            }
+        }
+    }
+    // dvar partial
+    const T tot = block_sum(gk, red);
+    if (tid == 0) atomicAdd(&ACC[(int64_t)s * (ls_len + 1) + ls_len], tot);
+}
+
 // Finalise: rows (which = 0) or columns (which = 1).  One thread per (row, d).
 template <typename T>
 __global__ void kbuild_bwd_final_kernel(const T* __restrict__ Xp, const T* __restrict__ ls, int ls_len,
@@ -640,31 +787,46 @@ static int launch_bwd(const T* X, const T* X2, const T* ls, int ls_len, const T*
     const int64_t nz = (int64_t)(ACC - ws) + (int64_t)S * (ls_len + 1);
     zero_kernel<T><<<std::min<int64_t>(cdiv(nz, 256), 4 * kNumSMs), 256, 0, st>>>(ws, nz);
 
-    const size_t smem = sizeof(T) * ((size_t)TR * D + (size_t)D * KBB_TN + (size_t)TR * (KBB_TN + 1) + 32);
-    if (smem > 200 * 1024) return MXF_ENOTIMPL;
-    // the column side needs sums only if X2 (or, for K(X,X), the same X through its second role) gets a gradient
-    // measured on B200: the direct d/dl variant (COLS = false) is slower than the column sums it avoids (94 vs 55 us at
-    // 1024 x 4096 x 8), so the column sums are always formed
-    const bool cols = true;
+    // the column side needs its sums in memory only if X2 (or, for K(X,X), the same X through its second role) gets a
+    // gradient
+    const bool cols = sym || dX2 != nullptr;
     dim3 grid(cdiv(N2, KBB_TN), cdiv(N, TR), S);
-    if (cols) {
-        auto k = kbuild_bwd_tile_kernel<T, KIND, TR, true>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, KBB_THREADS, smem, st>>>(X, X2e, ls, ls_len, var, G, ldg, RS, RB, CS, CB, ACC, N, N2, D, sX, sX2e,
-                                           sLs, sVar, sG);
+    if (D <= 16) {
+#define MXF_KBB2_LAUNCH(COLSV, DPV)                                                                                   \
+    do {                                                                                                              \
+        auto k = kbuild_bwd_tile2_kernel<T, KIND, TR, COLSV, DPV>;                                                    \
+        const size_t smem2 = sizeof(T) * ((size_t)TR * DPV + (size_t)DPV * KBB_TN + (size_t)TR * (KBB_TN + 1) + TR +   \
+                                          32 * (DPV + 1));                                                            \
+        if (smem2 > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);      \
+        k<<<grid, KBB_THREADS, smem2, st>>>(X, X2e, ls, ls_len, var, G, ldg, RS, RB, CS, CB, ACC, N, N2, D, sX, sX2e,  \
+                                            sLs, sVar, sG);                                                           \
+    } while (0)
+        if (D <= 4) { if (cols) MXF_KBB2_LAUNCH(true, 4); else MXF_KBB2_LAUNCH(false, 4); }
+        else if (D <= 8) { if (cols) MXF_KBB2_LAUNCH(true, 8); else MXF_KBB2_LAUNCH(false, 8); }
+        else { if (cols) MXF_KBB2_LAUNCH(true, 16); else MXF_KBB2_LAUNCH(false, 16); }
+#undef MXF_KBB2_LAUNCH
     } else {
-        auto k = kbuild_bwd_tile_kernel<T, KIND, TR, false>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, KBB_THREADS, smem, st>>>(X, X2e, ls, ls_len, var, G, ldg, RS, RB, CS, CB, ACC, N, N2, D, sX, sX2e,
-                                           sLs, sVar, sG);
+        const size_t smem = sizeof(T) * ((size_t)TR * D + (size_t)D * KBB_TN + (size_t)TR * (KBB_TN + 1) + 32);
+        if (smem > 200 * 1024) return MXF_ENOTIMPL;
+        if (cols) {
+            auto k = kbuild_bwd_tile_kernel<T, KIND, TR, true>;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k<<<grid, KBB_THREADS, smem, st>>>(X, X2e, ls, ls_len, var, G, ldg, RS, RB, CS, CB, ACC, N, N2, D, sX, sX2e,
+                                               sLs, sVar, sG);
+        } else {
+            auto k = kbuild_bwd_tile_kernel<T, KIND, TR, false>;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k<<<grid, KBB_THREADS, smem, st>>>(X, X2e, ls, ls_len, var, G, ldg, RS, RB, CS, CB, ACC, N, N2, D, sX, sX2e,
+                                               sLs, sVar, sG);
+        }
     }
+    // lengthscale gradient: the old COLS = false kernel (D > 16) accumulates all of it directly; the register-blocked one
+    // only its column part, the row part comes from RS / RB below
+    const bool direct_dl = !cols && D > 16;
     // rows -> dX (and dl row terms); columns -> dX2 (or accumulated into dX when symmetric)
-    if (dX) {
+    if (dX || !direct_dl) {
         dim3 g(cdiv((int64_t)N * D, 256), S);
-        kbuild_bwd_final_kernel<T><<<g, 256, 0, st>>>(X, ls, ls_len, RS, RB, dX, 0, ACC, N, D, sX, sLs, 1, cols ? 0 : 1);
-    } else if (cols) {
-        dim3 g(cdiv((int64_t)N * D, 256), S);
-        kbuild_bwd_final_kernel<T><<<g, 256, 0, st>>>(X, ls, ls_len, RS, RB, dX, 0, ACC, N, D, sX, sLs, 1, 0);
+        kbuild_bwd_final_kernel<T><<<g, 256, 0, st>>>(X, ls, ls_len, RS, RB, dX, 0, ACC, N, D, sX, sLs, 1, direct_dl ? 1 : 0);
     }
     if (cols) {
         dim3 g(cdiv((int64_t)N2 * D, 256), S);

@@ -30,5 +30,14 @@ elif what == 'gemm':
     for tb in (True, False):
         for _ in range(2):
             R.gemm(A, B, False, tb)
+elif what == 'kbwd':
+    M, B, D = 1024, 4096, 8
+    g = torch.Generator(device='cpu').manual_seed(0)
+    Z = (torch.rand((1, M, D), generator=g) * 6 - 3).to(dev)
+    X = (torch.rand((1, B, D), generator=g) * 6 - 3).to(dev)
+    G = torch.randn((1, M, B), generator=g).to(dev)
+    ls = torch.ones((1, 1), device=dev); var = torch.ones((1, 1), device=dev)
+    for _ in range(3):
+        R.kbuild_bwd(R.RBF, Z, X, ls, var, G, need_dX=True, need_dX2=False)
 torch.cuda.synchronize()
 print('done', what)
