@@ -241,6 +241,18 @@ int mxf_adam_step(int dtype, void* w, const void* g, void* m, void* v, int64_t n
                   double lr, double beta1, double beta2, double eps, double rescale,
                   int* step_count, void* stream);
 
+/* ---- flat parameter bucket: multi-tensor transform and gradient gather (inference_alg.py:79-80 applies
+ *      `var_trans[k].transform` per constrained parameter on every forward; gluon Trainer / autograd accumulate one
+ *      gradient per parameter) ----
+ * Segment t of the flat buffers is [off[t], off[t] + n[t]); kind[t] = 0 identity, 1 softplus (+ offset[t]).
+ * mxf_params_transform: tflat[seg] = transform(flat[seg]) for every segment, one launch (per 24 segments).
+ * mxf_params_pack_grads: gflat[seg] = grads[t] * d transform / d raw (grads[t]: HOST array of DEVICE pointers to the
+ * gradient w.r.t. the transformed value; NULL = no gradient, the segment is zero-filled); overwrites gflat. */
+int mxf_params_transform(int dtype, int count, const int64_t* off, const int64_t* n, const int* kind,
+                         const double* offset, const void* flat, void* tflat, void* stream);
+int mxf_params_pack_grads(int dtype, int count, const void* const* grads, const int64_t* off, const int64_t* n,
+                          const int* kind, const void* flat, void* gflat, void* stream);
+
 /* ---- minibatch gather (gluon DataLoader batchify, minibatch_loop.py:68-70,78) ----
  * out[r][:] = src[idx[off + r]][:] for r < rows; idx is int64 on device; bit-exact copy.
  * `off` is read from device memory (int64[1]) so the gather can be replayed inside a CUDA graph. */

@@ -60,6 +60,8 @@ def _declare(lib):
         'mxf_normal_reparam': (i, [i, p, p, l, p, l, i, l, u, u, p, p, p, p]),
         'mxf_adam_step': (i, [i, p, p, p, p, l, d, d, d, d, d, p, p]),
         'mxf_gather_rows': (i, [i, p, l, p, p, l, p, p]),
+        'mxf_params_transform': (i, [i, i, p, p, p, p, p, p, p]),
+        'mxf_params_pack_grads': (i, [i, i, p, p, p, p, p, p, p]),
         'mxf_mlp_tanh_fwd': (i, [i, i, p, p, l, p, p, p, p, p, i, i, p]),
         'mxf_mlp_tanh_bwd': (i, [i, i, p, p, l, p, p, p, p, p, p, p, i, i, p]),
     }

@@ -461,3 +461,25 @@ def svgp_coef_bwd(P, B, scale, g, beta, Q):
                                   ptr(coef), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), ptr(out[4]),
                                   ptr(out[5]), stream_ptr()), 'mxf_svgp_coef_bwd')
     return coef, out[0], out[1], out[2], out[3], out[4], out[5]
+
+
+def params_transform(flat, tflat, offs, sizes, kinds, offsets):
+    """tflat[seg] = transform(flat[seg]) for every (offset, size, kind, softplus offset) segment: one launch."""
+    import ctypes
+    require_cuda(flat, tflat)
+    n = len(offs)
+    check(lib().mxf_params_transform(dtype_code(flat), n, (ctypes.c_int64 * n)(*offs), (ctypes.c_int64 * n)(*sizes),
+                                     (ctypes.c_int * n)(*kinds), (ctypes.c_double * n)(*offsets), ptr(flat), ptr(tflat),
+                                     stream_ptr()), 'mxf_params_transform')
+
+
+def params_pack_grads(flat, gflat, grads, offs, sizes, kinds):
+    """gflat[seg] = grads[t] * d transform / d raw (None: zeros) for every segment: one launch."""
+    import ctypes
+    require_cuda(flat, gflat, *[g for g in grads if g is not None])
+    n = len(offs)
+    gs = [None if g is None else _c(g) for g in grads]
+    gp = (ctypes.c_void_p * n)(*[None if g is None else g.data_ptr() for g in gs])
+    check(lib().mxf_params_pack_grads(dtype_code(flat), n, gp, (ctypes.c_int64 * n)(*offs), (ctypes.c_int64 * n)(*sizes),
+                                      (ctypes.c_int * n)(*kinds), ptr(flat), ptr(gflat), stream_ptr()),
+          'mxf_params_pack_grads')

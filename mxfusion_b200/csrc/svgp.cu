@@ -139,6 +139,62 @@ __global__ void svgp_coef_bwd_kernel(int S, T P, T B, T scale, const T* __restri
     minus_one_out[s] = T(-1);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Multi-tensor parameter plumbing over the flat parameter bucket (inference_parameters.py / inference_alg.py:79-80 /
+// gluon Trainer): the reference transforms every constrained parameter with its own softrelu launch on the way in and
+// autograd accumulates one gradient per parameter on the way out (plus the softplus adjoints).  Here one launch
+// transforms all constrained segments of the flat buffer, and one launch gathers every parameter's gradient into the
+// flat gradient bucket, applying the softplus chain rule where the segment is constrained.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MT_MAX = 24;
+template <typename T>
+struct MtTable {
+    const T* src[MT_MAX];       // gradient w.r.t. the (transformed) value, or nullptr (no gradient: zeros)
+    int64_t off[MT_MAX];        // segment offset in the flat buffers
+    int64_t n[MT_MAX];          // segment length
+    T offset[MT_MAX];           // softplus offset
+    int kind[MT_MAX];           // 0: identity, 1: softplus
+    int count;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) mt_transform_kernel(MtTable<T> tb, const T* __restrict__ flat, T* __restrict__ tflat) {
+    const int t = blockIdx.y;
+    if (t >= tb.count) return;
+    const T* x = flat + tb.off[t];
+    T* y = tflat + tb.off[t];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tb.n[t]; i += stride) {
+        const T v = x[i];
+        if (tb.kind[t] == 1) {
+            const T av = v < T(0) ? -v : v;
+            y[i] = (v > T(0) ? v : T(0)) + log1p(exp(-av)) + tb.offset[t];
+        } else {
+            y[i] = v;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) mt_pack_grads_kernel(MtTable<T> tb, const T* __restrict__ flat, T* __restrict__ gflat) {
+    const int t = blockIdx.y;
+    if (t >= tb.count) return;
+    const T* x = flat + tb.off[t];
+    const T* g = tb.src[t];
+    T* out = gflat + tb.off[t];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tb.n[t]; i += stride) {
+        T gv = g ? g[i] : T(0);
+        if (g && tb.kind[t] == 1) {
+            const T v = x[i];
+            const T e = exp(v < T(0) ? v : -v);
+            gv *= v >= T(0) ? T(1) / (T(1) + e) : e / (T(1) + e);
+        }
+        out[i] = gv;
+    }
+}
+
 static inline int grid1d(int64_t n) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)8 * kNumSMs));
 }
@@ -211,4 +267,50 @@ extern "C" int mxf_svgp_coef_bwd(int dtype, int S, int P, int B, double scale, c
                                   S, (T)P, (T)B, (T)scale, (const T*)g, (const T*)beta, (const T*)Q, (T*)coef, (T*)gsb,
                                   (T*)neg_gsb, (T*)dnoise, (T*)dkvar_diag, (T*)neg_g, (T*)minus_one));
     return after_launch();
+}
+
+template <typename T>
+static int mt_launch(int which, int count, const void* const* src, const int64_t* off, const int64_t* n, const int* kind,
+                     const double* offset, const void* flat, void* out, cudaStream_t st) {
+    for (int base = 0; base < count; base += MT_MAX) {
+        MtTable<T> tb;
+        tb.count = std::min(MT_MAX, count - base);
+        int64_t nmax = 1;
+        for (int i = 0; i < MT_MAX; ++i) {
+            const bool on = i < tb.count;
+            tb.src[i] = (on && src) ? static_cast<const T*>(src[base + i]) : nullptr;
+            tb.off[i] = on ? off[base + i] : 0;
+            tb.n[i] = on ? n[base + i] : 0;
+            tb.kind[i] = on ? kind[base + i] : 0;
+            tb.offset[i] = (on && offset) ? (T)offset[base + i] : T(0);
+            if (on) {
+                if (tb.n[i] < 0 || tb.off[i] < 0 || (tb.kind[i] != 0 && tb.kind[i] != 1)) return MXF_EINVAL;
+                nmax = std::max(nmax, tb.n[i]);
+            }
+        }
+        dim3 grid((unsigned)std::min<int64_t>(cdiv(nmax, 256), 2 * kNumSMs), tb.count);
+        if (which == 0)
+            mt_transform_kernel<T><<<grid, 256, 0, st>>>(tb, static_cast<const T*>(flat), static_cast<T*>(out));
+        else
+            mt_pack_grads_kernel<T><<<grid, 256, 0, st>>>(tb, static_cast<const T*>(flat), static_cast<T*>(out));
+        int rc = after_launch();
+        if (rc != MXF_OK) return rc;
+    }
+    return MXF_OK;
+}
+
+extern "C" int mxf_params_transform(int dtype, int count, const int64_t* off, const int64_t* n, const int* kind,
+                                    const double* offset, const void* flat, void* tflat, void* stream) {
+    if (count < 0 || (count > 0 && (!off || !n || !kind || !flat || !tflat))) return MXF_EINVAL;
+    if (count == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, return mt_launch<T>(0, count, nullptr, off, n, kind, offset, flat, tflat,
+                                                  (cudaStream_t)stream));
+}
+
+extern "C" int mxf_params_pack_grads(int dtype, int count, const void* const* grads, const int64_t* off,
+                                     const int64_t* n, const int* kind, const void* flat, void* gflat, void* stream) {
+    if (count < 0 || (count > 0 && (!grads || !off || !n || !kind || !flat || !gflat))) return MXF_EINVAL;
+    if (count == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, return mt_launch<T>(1, count, grads, off, n, kind, nullptr, flat, gflat,
+                                                  (cudaStream_t)stream));
 }

@@ -23,6 +23,13 @@ class Stepper(object):
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rescale = float(rescale_grad) / self.world          # all-reduce(SUM) / world = average over ranks
         params.refresh_leaves()
+        # one-launch parameter transform on the way in, one-launch gradient gather (with the softplus chain rule) on the
+        # way out; needs the executor's transformation table (ObjectiveBlock)
+        self.fused = hasattr(infr_executor, '_var_trans') and hasattr(ops.R, 'params_pack_grads') and \
+            len(getattr(infr_executor, '_var_ties', {})) == 0
+        if self.fused:
+            params.setup_fused_transforms(infr_executor._var_trans)
+            infr_executor.pretransformed = params._fused_uuids
         from ..components.distributions import random_gen
         random_gen.set_step_counter(params.adam_t if params.adam_t.is_cuda else None)
         self.static_in = [torch.empty_like(b) for b in example_batch]
@@ -37,6 +44,13 @@ class Stepper(object):
         self.launches_per_step = None    # library kernels launched by one forward+backward (counted on an eager step)
 
     def _fwd_bwd(self):
+        if self.fused:
+            self.params.transform_all_()
+            self.params.clear_leaf_grads()
+            loss, loss_for_gradient = self.executor(None, *self.static_in)
+            loss_for_gradient.backward()
+            self.params.pack_grads_()
+            return loss.detach().reshape(())
         self.params.gflat.zero_()
         loss, loss_for_gradient = self.executor(None, *self.static_in)
         loss_for_gradient.backward()

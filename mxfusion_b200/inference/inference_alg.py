@@ -35,13 +35,19 @@ class ObjectiveBlock(object):
     def __call__(self, x, *args):
         """`x` is the reference's dummy first argument (``mx.nd.zeros(1)``); ignored."""
         from .. import F
-        kw = {name: p.tensor for name, p in self._infr_params.param_dict.items() if name not in self._excluded}
+        fused = getattr(self, 'pretransformed', None)       # set by the training step: uuids whose transformed value
+        params = self._infr_params                           # is already in `tflat` (one launch for all of them)
+        if fused is not None:
+            kw = {name: (params.leaf(name) if name in params._params else p.tensor)
+                  for name, p in params.param_dict.items() if name not in self._excluded}
+        else:
+            kw = {name: p.tensor for name, p in params.param_dict.items() if name not in self._excluded}
         for to_uuid, from_uuid in self._var_ties.items():
             kw[to_uuid] = kw[from_uuid]
         data = {k: v for k, v in zip(self._data_def, args)}
         variables = add_sample_dimension_to_arrays(F, data)
         for k, t in self._var_trans.items():
-            if k in kw:
+            if k in kw and not (fused is not None and k in fused):
                 kw[k] = t.transform(kw[k], F=F)
         add_sample_dimension_to_arrays(F, kw, out=variables)
         add_sample_dimension_to_arrays(F, self._constants, out=variables)

@@ -180,6 +180,50 @@ class InferenceParameters(object):
             p.tensor = view.data.requires_grad_(True)
             p.tensor.grad = self.gflat[p.offset:p.offset + n].view(p.shape)
 
+    # fused transforms / gradient gather (training loops) ---------------------------------------------------
+    def setup_fused_transforms(self, var_trans):
+        """Prepare the one-launch parameter plumbing of the training step: `transform_all_()` writes softplus(flat) for
+        every Softplus-constrained parameter into `tflat` (the executor then reads those values through the leaves
+        `tleaf`, skipping the per-parameter transform launches of inference_alg.py:79-80), and `pack_grads_()` gathers
+        all leaf gradients into `gflat` with the softplus chain rule applied (instead of one accumulation launch per
+        parameter plus one softplus adjoint per constrained parameter)."""
+        from ..components.variables.var_trans import Softplus
+        self.tflat = torch.zeros_like(self.flat)
+        self._segments = []
+        for uuid, p in self._params.items():
+            n = p.tensor.numel()
+            t = var_trans.get(uuid)
+            fused = isinstance(t, Softplus)
+            p.tleaf = None
+            if fused:
+                p.tleaf = self.tflat[p.offset:p.offset + n].view(p.shape).data.requires_grad_(True)
+            self._segments.append((uuid, p, p.offset, n, 1 if fused else 0, float(t._offset) if fused else 0.0))
+        self._fused_uuids = set(u for u, _, _, _, k, _ in self._segments if k == 1)
+
+    def leaf(self, uuid):
+        p = self._params[uuid]
+        return p.tleaf if getattr(p, 'tleaf', None) is not None else p.tensor
+
+    def transform_all_(self):
+        seg = [s for s in self._segments if s[4] == 1]
+        if seg:
+            from .. import ops
+            ops.R.params_transform(self.flat, self.tflat, [s[2] for s in seg], [s[3] for s in seg], [1] * len(seg),
+                                   [s[5] for s in seg])
+
+    def clear_leaf_grads(self):
+        for _, p, _, _, _, _ in self._segments:
+            p.tensor.grad = None
+            if p.tleaf is not None:
+                p.tleaf.grad = None
+
+    def pack_grads_(self):
+        from .. import ops
+        seg = self._segments
+        grads = [(p.tleaf if k == 1 else p.tensor).grad for _, p, _, _, k, _ in seg]
+        ops.R.params_pack_grads(self.flat, self.gflat, grads, [s[2] for s in seg], [s[3] for s in seg],
+                                [s[4] for s in seg])
+
     def fix_all(self):
         for p in self._params.values():
             p.grad_req = 'null'

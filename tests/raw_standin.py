@@ -271,3 +271,18 @@ def svgp_coef_bwd(P, B, scale, g, beta, Q):
     coef = torch.stack([g * (0.5 * P), gsb * (0.5 * P), 0.5 * g, 0.5 * gsb, gsb * P, gsb], dim=1).contiguous()
     return (coef, gsb, -gsb, g * scale * (-beta * beta * Q - (0.5 * B * P) * beta), -gsb * (0.5 * P * B), -g,
             torch.full_like(g, -1.0))
+
+
+def params_transform(flat, tflat, offs, sizes, kinds, offsets):
+    for o, n, k, c in zip(offs, sizes, kinds, offsets):
+        x = flat[o:o + n]
+        tflat[o:o + n] = torch.nn.functional.softplus(x) + c if k == 1 else x
+
+
+def params_pack_grads(flat, gflat, grads, offs, sizes, kinds):
+    for g, o, n, k in zip(grads, offs, sizes, kinds):
+        if g is None:
+            gflat[o:o + n] = 0
+        else:
+            gv = g.reshape(-1)
+            gflat[o:o + n] = gv * torch.sigmoid(flat[o:o + n]) if k == 1 else gv
