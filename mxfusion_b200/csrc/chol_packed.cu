@@ -35,7 +35,7 @@ template <> struct TriBlock<double> { static constexpr int NB = 64; };
 inline int tri_inv_max() {
     static int v = [] {
         const char* e = getenv("MXF_TRI_INV");
-        int x = e ? atoi(e) : 512;
+        int x = e ? atoi(e) : 1024;
         return x < 64 ? 64 : x;
     }();
     return v;
