@@ -609,10 +609,23 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int tiles_per_batch = tiles_m * tiles_n;
     const int total_tiles = tiles_per_batch * S;
     // every role walks the same tile list; `tile_of` decodes tile t and returns false for tiles that are skipped
+    // Tile schedule: position p of the list (rows of tiles ordered by DEcreasing K-loop length when A is triangular: with
+    // tri & 2 the K loop of row block tm has tm + 1 blocks) is dealt to the CTAs in snake order (round i runs forwards for
+    // even i, backwards for odd i), which balances the per-CTA sums of K steps to within one tile (plain round-robin on
+    // 8 x 41 tiles of a 1024 solve leaves the slowest CTA with 14 units against a mean of 10).
+    const int rounds = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto tile_at = [&](int i) -> int {
+        const int b = (i & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+        const int p = i * (int)gridDim.x + b;
+        return p < total_tiles ? p : -1;
+    };
     auto tile_of = [&](int t, int& z, int& m0, int& n0, int& kb_begin, int& kb_end) -> bool {
+        if (t < 0) return false;
         z = t / tiles_per_batch;
         const int r = t - z * tiles_per_batch;
-        const int tm = r / tiles_n, tn = r - tm * tiles_n;
+        int tm = r / tiles_n;
+        const int tn = r - tm * tiles_n;
+        if ((tri & 2) && !(tri & 4)) tm = tiles_m - 1 - tm;          // heaviest rows first
         m0 = tm * TC_BM;
         n0 = tn * BN;
         if ((tri & 1) && n0 > m0 + TC_BM - 1) return false;
@@ -626,7 +639,8 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int ri = 0; ri < rounds; ++ri) {
+                const int t = tile_at(ri);
                 int z, m0, n0, kb0, kb1;
                 if (!tile_of(t, z, m0, n0, kb0, kb1)) continue;
                 const int zA = batchA ? z : 0, zB = batchB ? z : 0;
@@ -652,7 +666,8 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int it = 0, j = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int ri = 0; ri < rounds; ++ri) {
+                const int t = tile_at(ri);
                 int z, m0, n0, kb0, kb1;
                 if (!tile_of(t, z, m0, n0, kb0, kb1)) continue;
                 const int as = j & 1;
@@ -693,7 +708,8 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int row = q * 32 + lane;                         // row of the A tile this thread splits
         constexpr int VECB = Cfg::B_BYTES / 16;
         int it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int ri = 0; ri < rounds; ++ri) {
+            const int t = tile_at(ri);
             int z, m0, n0, kb0, kb1;
             if (!tile_of(t, z, m0, n0, kb0, kb1)) continue;
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -744,7 +760,8 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;
         const bool vec_ok = ((ldc & 3) == 0) && ((sC & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
         int j = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int ri = 0; ri < rounds; ++ri) {
+            const int t = tile_at(ri);
             int z, m0, n0, kb0, kb1;
             if (!tile_of(t, z, m0, n0, kb0, kb1)) continue;
             const int as = j & 1;
