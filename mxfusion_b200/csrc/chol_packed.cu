@@ -215,13 +215,36 @@ potrf_diag_kernel(T* __restrict__ A, int64_t lda, int64_t sA, int n, int k0, int
     if (tid == 0) bad_s = 0;
     pdl_wait();
 
+    // 16-byte accesses when the block is aligned (lda % 4 == 0, 16-byte aligned base): the block is 64 KB moved by ONE
+    // CTA, so the number of load / store round trips -- not bandwidth -- sets the time of this phase
+    const bool vec4 = (sizeof(T) == 4) && ((lda & 3) == 0) && ((sA & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    if (vec4) {
 #pragma unroll 8
-    for (int e = tid; e < NB * NB; e += PD_THREADS) {
-        const int r = e / NB, c = e - r * NB;
-        T v = (r == c) ? T(1) : T(0);
-        if (r < nbk && c < nbk && c <= r) v = As[(int64_t)(k0 + r) * lda + k0 + c];
-        D[r * LD + c] = v;
-        W[r * LD + c] = T(0);
+        for (int e4 = tid; e4 < NB * NB / 4; e4 += PD_THREADS) {
+            const int r = e4 / (NB / 4), c = (e4 - r * (NB / 4)) * 4;
+            T v[4] = {T(0), T(0), T(0), T(0)};
+            if (r < nbk && c <= r) {                       // chunks entirely above the diagonal are never read
+                const float4 q = *reinterpret_cast<const float4*>(&As[(int64_t)(k0 + r) * lda + k0 + c]);
+                v[0] = (T)q.x; v[1] = (T)q.y; v[2] = (T)q.z; v[3] = (T)q.w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int cc = c + u;
+                T x = (r == cc) ? T(1) : T(0);
+                if (r < nbk && cc < nbk && cc <= r) x = v[u];
+                D[r * LD + cc] = x;
+                W[r * LD + cc] = T(0);
+            }
+        }
+    } else {
+#pragma unroll 8
+        for (int e = tid; e < NB * NB; e += PD_THREADS) {
+            const int r = e / NB, c = e - r * NB;
+            T v = (r == c) ? T(1) : T(0);
+            if (r < nbk && c < nbk && c <= r) v = As[(int64_t)(k0 + r) * lda + k0 + c];
+            D[r * LD + c] = v;
+            W[r * LD + c] = T(0);
+        }
     }
     __syncthreads();
     PD_STAMP(0);
@@ -319,13 +342,14 @@ potrf_diag_kernel(T* __restrict__ A, int64_t lda, int64_t sA, int n, int k0, int
     // ---- write back ---------------------------------------------------------------------------------------------
     if (tid == 0 && bad_s != 0 && info) atomicCAS(&info[s], 0, k0 + bad_s);
     // factor block (the strict upper triangle of A is zeroed once, after the last block: MXNet potrf convention)
+    T* dv = pack + (int64_t)s * pack_stride + off_dinv + (int64_t)(k0 / NB) * NB * NB;
+    T* dvT = pack + (int64_t)s * pack_stride + off_dinvT + (int64_t)(k0 / NB) * NB * NB;
 #pragma unroll 8
     for (int e = tid; e < NB * NB; e += PD_THREADS) {
         const int r = e / NB, c = e - r * NB;
         if (r < nbk && c < nbk) As[(int64_t)(k0 + r) * lda + k0 + c] = (c <= r) ? D[r * LD + c] : T(0);
     }
-    T* dv = pack + (int64_t)s * pack_stride + off_dinv + (int64_t)(k0 / NB) * NB * NB;
-    T* dvT = pack + (int64_t)s * pack_stride + off_dinvT + (int64_t)(k0 / NB) * NB * NB;
+    // (16-byte stores were measured and do not help: this phase sits at one SM's ~32 B/clk write path to L2)
 #pragma unroll 8
     for (int e = tid; e < NB * NB; e += PD_THREADS) {
         const int r = e / NB, c = e - r * NB;

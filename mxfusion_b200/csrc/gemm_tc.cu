@@ -563,7 +563,7 @@ template <bool B_MN>
 __global__ void __launch_bounds__(PeCfg::THREADS, 1)
 gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   float* __restrict__ C, int64_t ldc, int64_t sC, int m, int n, int k, float alpha, float beta,
-                  int tri, int batchA, int batchB, int tiles_m, int tiles_n, int S) {
+                  int tri, int batchA, int batchB, int tiles_m, int tiles_n, int S, int snake) {
     using Cfg = PeCfg;
     constexpr int BN = Cfg::BN;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -615,7 +615,7 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // 8 x 41 tiles of a 1024 solve leaves the slowest CTA with 14 units against a mean of 10).
     const int rounds = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     auto tile_at = [&](int i) -> int {
-        const int b = (i & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+        const int b = (snake && (i & 1)) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
         const int p = i * (int)gridDim.x + b;
         return p < total_tiles ? p : -1;
     };
@@ -625,7 +625,7 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int r = t - z * tiles_per_batch;
         int tm = r / tiles_n;
         const int tn = r - tm * tiles_n;
-        if ((tri & 2) && !(tri & 4)) tm = tiles_m - 1 - tm;          // heaviest rows first
+        if (snake && (tri & 2) && !(tri & 4)) tm = tiles_m - 1 - tm;          // heaviest rows first
         m0 = tm * TC_BM;
         n0 = tn * BN;
         if ((tri & 1) && n0 > m0 + TC_BM - 1) return false;
@@ -903,8 +903,9 @@ static int launch_tc_pe(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C
     const int tiles_m = cdiv(m, TC_BM), tiles_n = cdiv(n, PeCfg::BN);
     const int64_t total = (int64_t)tiles_m * tiles_n * S;
     const int grid = (int)std::min<int64_t>(total, kNumSMs);
+    static const int snake = [] { const char* e = getenv("MXF_GEMM_PE_SNAKE"); return e ? atoi(e) : 1; }();
     kern<<<grid, PeCfg::THREADS, PeCfg::SMEM, st>>>(tmA, tmB, C, ldc, sC, m, n, k, alpha, beta, tri, batchA, batchB, tiles_m,
-                                                    tiles_n, S);
+                                                    tiles_n, S, (snake && (tri & 6)) ? 1 : 0);
     return after_launch();
 }
 
