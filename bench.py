@@ -26,16 +26,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_ROWS, M_IND, D_IN, BATCH = 1000000, 1024, 8, 4096
+KERNEL = 'rbf'
+# other BASELINE.json configs (not the bench line the driver reads; `--workload c2|c3` prints the same JSON for them)
+WORKLOADS = {'headline': (1000000, 1024, 8, 4096, 'rbf'), 'c2': (100000, 512, 8, 2048, 'rbf'),
+             'c3': (1000000, 1024, 16, 4096, 'matern52')}
 JITTER, LR = 1e-6, 1e-2
 KBUILD_NCU_TRAFFIC_BYTES = 4070277632      # profiles/r1b_kbuild_raw.csv: 32.06 MB read + 4038.2 MB written per launch
 METRIC = "svgp_elbo_iters_per_sec"
 UNIT = "minibatch iterations (B=4096 rows: ELBO fwd + grad + Adam) per second, summed over GPUs"
 
 
-def synthetic(n=N_ROWS, d=D_IN, m=M_IND):
+def synthetic(n=None, d=None, m=None):
     """SURVEY.md section 8(d): X ~ U(-3,3)^(N x D), f = sum_d sin(x_d)/sqrt(D), Y = f + 0.05 N(0,1);
     Z = first M rows of a seed-1 permutation of X."""
     import torch
+    n, d, m = n or N_ROWS, d or D_IN, m or M_IND
     g = torch.Generator(device='cpu').manual_seed(0)
     X = torch.rand((n, d), generator=g, dtype=torch.float32) * 6.0 - 3.0
     Y = (torch.sin(X).sum(dim=1, keepdim=True) / math.sqrt(d) +
@@ -97,7 +102,7 @@ def build_inference(X, Y, Z, n_total, world, data_resident, dtype='float32', dev
     import torch
     import mxfusion_b200 as mf
     from mxfusion_b200.components.variables import PositiveTransformation
-    from mxfusion_b200.components.distributions.gp.kernels import RBF
+    from mxfusion_b200.components.distributions.gp.kernels import RBF, Matern52
     from mxfusion_b200.modules.gp_modules import SVGPRegression
     from mxfusion_b200.inference import GradBasedInference, MAP, MinibatchInferenceLoop
     mf.config.DEFAULT_DTYPE = dtype
@@ -105,7 +110,7 @@ def build_inference(X, Y, Z, n_total, world, data_resident, dtype='float32', dev
     m.N = mf.Variable()
     m.X = mf.Variable(shape=(m.N, D_IN))
     m.noise_var = mf.Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=0.01)
-    m.kernel = RBF(input_dim=D_IN, variance=1, lengthscale=1)
+    m.kernel = (RBF if KERNEL == 'rbf' else Matern52)(input_dim=D_IN, variance=1, lengthscale=1)
     m.Z = mf.Variable(shape=tuple(Z.shape), initial_value=Z)
     m.Y = SVGPRegression.define_variable(X=m.X, kernel=m.kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
                                          shape=(m.N, 1))
@@ -162,13 +167,13 @@ def kernel_rooflines(device, pk):
     var = torch.ones((1, 1), device=device)
     out = torch.empty((1, N_ROWS, M_IND), device=device)
     for _ in range(3):
-        _raw.kbuild_fwd(_raw.RBF, X, Z, ls, var, out=out)
+        _raw.kbuild_fwd(_raw.RBF if KERNEL == 'rbf' else _raw.MATERN52, X, Z, ls, var, out=out)
     torch.cuda.synchronize()
     ts = []
     for _ in range(10):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        _raw.kbuild_fwd(_raw.RBF, X, Z, ls, var, out=out)
+        _raw.kbuild_fwd(_raw.RBF if KERNEL == 'rbf' else _raw.MATERN52, X, Z, ls, var, out=out)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
@@ -176,8 +181,10 @@ def kernel_rooflines(device, pk):
     nbytes = 4 * (N_ROWS * M_IND + N_ROWS * D_IN + M_IND * D_IN + D_IN + 1)
     ach = nbytes / ms / 1e6
     del out
-    return {'bound': 'hbm', 'kernel': 'kbuild_fwd_kernel<float,RBF> K(X,Z) N=1e6 M=1024 D=8', 'achieved': ach,
-            'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'], 'traffic': KBUILD_NCU_TRAFFIC_BYTES,
+    return {'bound': 'hbm', 'kernel': 'kbuild_fwd_stream_kernel<float,%s> K(X,Z) N=%d M=%d D=%d' % (KERNEL, N_ROWS, M_IND, D_IN),
+            'achieved': ach,
+            'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
+            'traffic': KBUILD_NCU_TRAFFIC_BYTES if (KERNEL, N_ROWS, M_IND, D_IN) == ('rbf', 1000000, 1024, 8) else None,
             'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture '
                               'profiles/r1b_kbuild_raw.csv (0.032 GB read + 4.038 GB written)',
             'ms_per_launch': ms, 'algorithmic_bytes': nbytes}
@@ -221,7 +228,7 @@ def cpu_reference_iters_per_sec(X, Y, Z, n_total, seconds_budget=20.0, max_iters
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     M = Z.shape[0]
-    step = torch_ref.SVGPStepCPU(torch_ref.RBF, Z, np.array([0.01]), np.array([1.0]), np.array([1.0]),
+    step = torch_ref.SVGPStepCPU(torch_ref.RBF if KERNEL == 'rbf' else torch_ref.MATERN52, Z, np.array([0.01]), np.array([1.0]), np.array([1.0]),
                                  np.zeros((M, 1)), np.zeros((M, M)), np.ones((M,)), JITTER,
                                  n_total / float(BATCH), LR, dtype=torch.float32)
     rng = np.random.RandomState(1234)
@@ -248,13 +255,18 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='headline', choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global N_ROWS, M_IND, D_IN, BATCH, KERNEL, UNIT
+    N_ROWS, M_IND, D_IN, BATCH, KERNEL = WORKLOADS[args.workload]
+    UNIT = UNIT.replace('B=4096', 'B=%d' % BATCH)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     warmup = max(args.warmup, 3)
-    config = {'workload': 'SVGPRegression N=1e6 M=1024 D=8 RBF minibatch=4096 f32 (BASELINE headline; '
-                          'jitter 1e-6, Adam lr 1e-2, rv_scaling=N/B)', 'N': N_ROWS, 'M': M_IND, 'D': D_IN,
+    config = {'workload': 'SVGPRegression N=%d M=%d D=%d %s minibatch=%d f32 (BASELINE %s; '
+                          'jitter 1e-6, Adam lr 1e-2, rv_scaling=N/B)' % (N_ROWS, M_IND, D_IN, KERNEL, BATCH, args.workload),
+              'N': N_ROWS, 'M': M_IND, 'D': D_IN,
               'batch_per_gpu': BATCH, 'parallelism': 'dp%d' % world,
               'sharding': 'rows split across ranks, one NCCL all-reduce of the flat gradient per step'}
 
