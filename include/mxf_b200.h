@@ -231,6 +231,10 @@ int mxf_normal_logpdf_sum_bwd(int dtype, const void* x, int64_t sX, const void* 
 int mxf_normal_reparam(int dtype, const void* eps, const void* m, int64_t sM, const void* v, int64_t sV,
                        int S, int64_t n, uint64_t seed, uint64_t offset, const int* step_counter, void* w,
                        void* eps_out, void* stream);
+/* Adjoint of the draw: gm = gw, gv = gw * eps / (2 sqrt(v)); an operand shared by the samples (sM / sV = 0) receives
+ * the sum over samples; gm / gv may be NULL. */
+int mxf_normal_reparam_bwd(int dtype, const void* gw, const void* eps, const void* v, int64_t sM, int64_t sV, int S,
+                           int64_t n, void* gm, void* gv, void* stream);
 
 /* ---- optimiser (mx.gluon.Trainer('adam').step(batch_size), minibatch_loop.py:71-91) ----
  * One fused update over a flat parameter bucket:

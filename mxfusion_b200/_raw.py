@@ -483,3 +483,18 @@ def params_pack_grads(flat, gflat, grads, offs, sizes, kinds):
     check(lib().mxf_params_pack_grads(dtype_code(flat), n, gp, (ctypes.c_int64 * n)(*offs), (ctypes.c_int64 * n)(*sizes),
                                       (ctypes.c_int * n)(*kinds), ptr(flat), ptr(gflat), stream_ptr()),
           'mxf_params_pack_grads')
+
+
+def normal_reparam_bwd(gw, eps, v, m_samples, need=(True, True)):
+    """(gm, gv) of the reparameterised draw; `m_samples` = leading size of the mean (1: shared, gradients are summed)."""
+    require_cuda(gw, eps, v)
+    S = gw.shape[0]
+    gwf, ef, vf = _flat(_c(gw)), _flat(_c(eps)), _flat(_c(v))
+    n = gwf.shape[1]
+    shape = tuple(gw.shape[1:])
+    gm = torch.empty(((m_samples if m_samples > 1 else 1), n), dtype=gw.dtype, device=gw.device) if need[0] else None
+    gv = torch.empty((vf.shape[0], n), dtype=gw.dtype, device=gw.device) if need[1] else None
+    check(lib().mxf_normal_reparam_bwd(dtype_code(gw), ptr(gwf), ptr(ef), ptr(vf), n if m_samples > 1 else 0,
+                                       _bstride(vf, S), S, n, ptr(gm), ptr(gv), stream_ptr()), 'mxf_normal_reparam_bwd')
+    return (None if gm is None else gm.reshape((gm.shape[0],) + shape),
+            None if gv is None else gv.reshape((gv.shape[0],) + shape))

@@ -380,6 +380,28 @@ gather_rows_kernel(const T* __restrict__ src, int64_t cols, const int64_t* __res
     }
 }
 
+
+// Adjoint of the reparameterised draw w = eps sqrt(v) + m:  gm = gw (summed over the samples when m is shared),
+// gv = gw eps / (2 sqrt(v)) (summed likewise).  One launch instead of the five elementwise / reduction operators autograd
+// would issue per weight tensor (normal.py:89-92 differentiated).
+template <typename T>
+__global__ void __launch_bounds__(256)
+normal_reparam_bwd_kernel(const T* __restrict__ gw, const T* __restrict__ eps, const T* __restrict__ v, int64_t sM,
+                          int64_t sV, int S, int64_t n, T* __restrict__ gm, T* __restrict__ gv) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T am = 0, av = 0;
+        for (int s = 0; s < S; ++s) {
+            const T g = gw[s * n + i];
+            const T dv = g * eps[s * n + i] * (T(0.5) * Num<T>::rsqrt_(v[s * sV + i]));
+            if (gm) { if (sM) gm[s * n + i] = g; else am += g; }
+            if (gv) { if (sV) gv[s * n + i] = dv; else av += dv; }
+        }
+        if (gm && !sM) gm[i] = am;
+        if (gv && !sV) gv[i] = av;
+    }
+}
+
 static inline int grid_for(int64_t n, int threads = 256) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)8 * kNumSMs));
 }
@@ -518,5 +540,14 @@ extern "C" int mxf_gather_rows(int dtype, const void* src, int64_t cols, const i
     if (rows == 0) return MXF_OK;
     MXF_DISPATCH_DTYPE(dtype, gather_rows_kernel<T><<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(
                                   (const T*)src, cols, idx, off, rows, (T*)out));
+    return after_launch();
+}
+
+extern "C" int mxf_normal_reparam_bwd(int dtype, const void* gw, const void* eps, const void* v, int64_t sM, int64_t sV,
+                                      int S, int64_t n, void* gm, void* gv, void* stream) {
+    if (!gw || !eps || !v || S <= 0 || n < 0) return MXF_EINVAL;
+    if (n == 0 || (!gm && !gv)) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, normal_reparam_bwd_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)gw, (const T*)eps, (const T*)v, sM, sV, S, n, (T*)gm, (T*)gv));
     return after_launch();
 }

@@ -237,11 +237,8 @@ class _NormalReparam(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gw):
         e, v = ctx.saved_tensors
-        gm = gw if ctx.mS == gw.shape[0] else gw.sum(dim=0, keepdim=True)
-        # d/dv [eps sqrt(v)] = eps / (2 sqrt(v))
-        gv = gw * e * (0.5 / torch.sqrt(v))
-        if ctx.vS != gv.shape[0]:
-            gv = gv.sum(dim=0, keepdim=True)
+        # gm = gw, gv = gw eps / (2 sqrt(v)), summed over the samples for shared operands: one launch
+        gm, gv = R.normal_reparam_bwd(gw, e, v, ctx.mS, need=tuple(ctx.needs_input_grad[:2]))
         return gm, gv, None, None, None, None, None
 
 

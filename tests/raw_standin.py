@@ -286,3 +286,11 @@ def params_pack_grads(flat, gflat, grads, offs, sizes, kinds):
         else:
             gv = g.reshape(-1)
             gflat[o:o + n] = gv * torch.sigmoid(flat[o:o + n]) if k == 1 else gv
+
+
+def normal_reparam_bwd(gw, eps, v, m_samples, need=(True, True)):
+    gm = gw if m_samples == gw.shape[0] else gw.sum(dim=0, keepdim=True)
+    gv = gw * eps * (0.5 / torch.sqrt(v))
+    if v.shape[0] != gv.shape[0]:
+        gv = gv.sum(dim=0, keepdim=True)
+    return (gm if need[0] else None), (gv if need[1] else None)

@@ -554,3 +554,24 @@ def test_gemm_skinny_long_k(cuda, shape):
     want = 0.5 * (A64 @ Bop) + C0
     bound = 2e-6 * (np.abs(A64) @ np.abs(Bop) + np.abs(C0)) + 1e-6
     assert np.all(np.abs(C.cpu().numpy() - want) <= bound)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('shared', [(True, True), (False, True), (False, False)])
+def test_reparam_adjoint(cuda, prec, shared):
+    """mxf_normal_reparam_bwd against autograd of eps * sqrt(v) + m (normal.py:89-92), with operands shared by the samples
+    (gradient summed over S) or sampled."""
+    from mxfusion_b200 import ops
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(4)
+    S, shape = 3, (37, 5)
+    m = rng.randn(1 if shared[0] else S, *shape)
+    v = rng.rand(1 if shared[1] else S, *shape) + 0.2
+    eps, gw = rng.randn(S, *shape), rng.randn(S, *shape)
+    tm, tv = T(m, cuda, tdt).requires_grad_(), T(v, cuda, tdt).requires_grad_()
+    w = ops.normal_draw(tm, tv, S, eps=T(eps, cuda, tdt))
+    (w * T(gw, cuda, tdt)).sum().backward()
+    rm, rv = torch.tensor(m, requires_grad=True), torch.tensor(v, requires_grad=True)
+    ((torch.tensor(eps) * torch.sqrt(rv) + rm) * torch.tensor(gw)).sum().backward()
+    np.testing.assert_allclose(tm.grad.cpu().numpy(), rm.grad.numpy(), rtol=rtol * 10, atol=atol * 10)
+    np.testing.assert_allclose(tv.grad.cpu().numpy(), rv.grad.numpy(), rtol=rtol * 10, atol=atol * 10)
