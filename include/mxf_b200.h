@@ -223,6 +223,18 @@ int mxf_normal_logpdf_sum(int dtype, const void* x, int64_t sX, const void* m, i
 int mxf_normal_logpdf_sum_bwd(int dtype, const void* x, int64_t sX, const void* m, int64_t sM,
                               const void* v, int64_t sV, int S, int64_t n, double scale,
                               const void* gout, void* gx, void* gm, void* gv, void* stream);
+/* Multi-tensor form of the two calls above: `count` Normal factors in one launch each way (HOST arrays of DEVICE
+ * pointers / per-entry sizes).  Entry t: x, m, v with sample strides sX / sM / sV (0 = shared by the S[t] samples), n[t]
+ * elements per sample, scalar[t] bit 0 / 1 / 2 = x / m / v is ONE element per sample (a constant prior parameter is read in
+ * place, not broadcast into a copy), scale[t].  out[0] += sum_t scale_t / S_t sum log N (caller zeroes out).
+ * The adjoint writes gx[t] / gm[t] / gv[t] (NULL = not needed; scalar operands cannot receive a gradient here). */
+int mxf_normal_logpdf_multi(int dtype, int count, const void* const* x, const void* const* m, const void* const* v,
+                            const int64_t* sX, const int64_t* sM, const int64_t* sV, const int64_t* n, const int* S,
+                            const int* scalar, const double* scale, void* out, void* stream);
+int mxf_normal_logpdf_multi_bwd(int dtype, int count, const void* const* x, const void* const* m, const void* const* v,
+                                const int64_t* sX, const int64_t* sM, const int64_t* sV, const int64_t* n, const int* S,
+                                const int* scalar, const double* scale, const void* gout, void* const* gx,
+                                void* const* gm, void* const* gv, void* stream);
 /* Reparameterised draw (normal.py:89-92): w[s][i] = eps[s][i]*sqrt(v[i]) + m[i].
  * If eps == NULL a counter-based Philox4x32-10 standard-normal stream keyed by
  * (seed, offset) is generated in-kernel and, if eps_out != NULL, stored for the adjoint.

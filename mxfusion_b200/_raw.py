@@ -498,3 +498,64 @@ def normal_reparam_bwd(gw, eps, v, m_samples, need=(True, True)):
                                        _bstride(vf, S), S, n, ptr(gm), ptr(gv), stream_ptr()), 'mxf_normal_reparam_bwd')
     return (None if gm is None else gm.reshape((gm.shape[0],) + shape),
             None if gv is None else gv.reshape((gv.shape[0],) + shape))
+
+
+def _nl_tables(entries):
+    import ctypes
+    T = len(entries)
+    xs, ms, vs, sX, sM, sV, ns, Ss, flags, scales = [], [], [], [], [], [], [], [], [], []
+    for x, m, v, scale in entries:
+        require_cuda(x, m, v)
+        x, m, v = _flat(x), _flat(m), _flat(v)
+        S = max(x.shape[0], m.shape[0], v.shape[0])
+        n = max(x.shape[1], m.shape[1], v.shape[1])
+        fl = 0
+        for bit, t in ((1, x), (2, m), (4, v)):
+            if t.shape[1] != n:
+                if t.shape[1] != 1:
+                    raise _lib.MXFusionB200Error("normal_logpdf_multi: operands must be full-size or one element per sample")
+                fl |= bit
+        xs.append(x); ms.append(m); vs.append(v)
+        sX.append(_bstride(x, S)); sM.append(_bstride(m, S)); sV.append(_bstride(v, S))
+        ns.append(n); Ss.append(S); flags.append(fl); scales.append(float(scale))
+    arr = lambda ct, vals: (ct * T)(*vals)
+    c = dict(x=arr(ctypes.c_void_p, [t.data_ptr() for t in xs]), m=arr(ctypes.c_void_p, [t.data_ptr() for t in ms]),
+             v=arr(ctypes.c_void_p, [t.data_ptr() for t in vs]), sX=arr(ctypes.c_int64, sX), sM=arr(ctypes.c_int64, sM),
+             sV=arr(ctypes.c_int64, sV), n=arr(ctypes.c_int64, ns), S=arr(ctypes.c_int, Ss), fl=arr(ctypes.c_int, flags),
+             scale=arr(ctypes.c_double, scales))
+    return T, xs, ms, vs, flags, c
+
+
+def normal_logpdf_multi(entries):
+    """sum_t scale_t * sum(mean_S(log N(x_t | m_t, v_t))) for a list of (x, m, v, scale): ONE launch -> tensor (1,)."""
+    T, xs, ms, vs, flags, c = _nl_tables(entries)
+    out = torch.zeros((1,), dtype=xs[0].dtype, device=xs[0].device)
+    check(lib().mxf_normal_logpdf_multi(dtype_code(xs[0]), T, c['x'], c['m'], c['v'], c['sX'], c['sM'], c['sV'], c['n'],
+                                        c['S'], c['fl'], c['scale'], ptr(out), stream_ptr()), 'mxf_normal_logpdf_multi')
+    return out
+
+
+def normal_logpdf_multi_bwd(entries, gout, needs):
+    """Gradients [(gx, gm, gv)] per entry (None where `needs[t][k]` is False), shaped like the operands: ONE launch."""
+    import ctypes
+    T, xs, ms, vs, flags, c = _nl_tables(entries)
+    gout = _c(gout).reshape(-1)
+    grads, ptrs = [], ([], [], [])
+    for t, (x, m, v, _) in enumerate(entries):
+        row = []
+        for k, (flat, orig, bit) in enumerate(((xs[t], x, 1), (ms[t], m, 2), (vs[t], v, 4))):
+            if needs[t][k]:
+                if flags[t] & bit:
+                    raise _lib.MXFusionB200Error("normal_logpdf_multi_bwd: a one-element operand cannot receive a gradient")
+                g = torch.empty_like(flat)
+                row.append(g.reshape(orig.shape))
+                ptrs[k].append(g.data_ptr())
+            else:
+                row.append(None)
+                ptrs[k].append(None)
+        grads.append(tuple(row))
+    arr = lambda vals: (ctypes.c_void_p * T)(*vals)
+    check(lib().mxf_normal_logpdf_multi_bwd(dtype_code(xs[0]), T, c['x'], c['m'], c['v'], c['sX'], c['sM'], c['sV'], c['n'],
+                                            c['S'], c['fl'], c['scale'], ptr(gout), arr(ptrs[0]), arr(ptrs[1]),
+                                            arr(ptrs[2]), stream_ptr()), 'mxf_normal_logpdf_multi_bwd')
+    return grads

@@ -36,6 +36,21 @@ class Normal(Distribution):
             x, m, v = bc(x), bc(m), bc(v)
         return ops.normal_log_pdf_sum(x, m, v, self.log_pdf_scaling).reshape(())
 
+    def log_pdf_operands(self, F, variables):
+        """(x, mean, variance, scale) for the batched evaluation of all Normal factors of a graph walk
+        (FactorGraph.log_pdf -> ops.normal_log_pdf_sum_multi), or None when this factor needs the general path: every
+        operand must be full-size or a single element per sample, and a single-element operand must not need a gradient."""
+        kw = self.fetch_runtime_inputs(variables)
+        kw.update(self.fetch_runtime_outputs(variables))
+        x, m, v = kw['random_variable'], kw['mean'], kw['variance']
+        n = max(x[0].numel(), m[0].numel(), v[0].numel())
+        S = max(x.shape[0], m.shape[0], v.shape[0])
+        for t in (x, m, v):
+            k = t[0].numel()
+            if t.shape[0] not in (1, S) or (k != n and (k != 1 or t.requires_grad)):
+                return None
+        return x, m, v, self.log_pdf_scaling
+
     def draw_samples_impl(self, mean, variance, rv_shape, num_samples=1, F=None):
         """normal.py:72-92: eps * sqrt(variance) + mean with eps ~ N(0,1) of shape (S,) + rv_shape."""
         full = (num_samples,) + tuple(rv_shape)

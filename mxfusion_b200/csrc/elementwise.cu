@@ -402,6 +402,79 @@ normal_reparam_bwd_kernel(const T* __restrict__ gw, const T* __restrict__ eps, c
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Multi-tensor Normal log-density: all Normal factors of a factor-graph walk (the priors and the variational factors of
+// every weight tensor of a mean-field BNN, plus the likelihood; factor_graph.py:192-238 sums them one operator chain at a
+// time) in ONE launch forwards and ONE launch backwards.  Entry t: x, m, v with sample strides (0 = shared by the
+// samples) and a per-operand "scalar" flag (a constant prior mean / variance of shape (1,) is read in place instead of
+// being broadcast into a weight-shaped copy).  out[0] += sum_t scale_t / S_t sum_{s,i} log N(x | m, v).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int NL_MAX = 16;
+template <typename T>
+struct NlTable {
+    const T* x[NL_MAX]; const T* m[NL_MAX]; const T* v[NL_MAX];
+    T* gx[NL_MAX]; T* gm[NL_MAX]; T* gv[NL_MAX];
+    int64_t sX[NL_MAX], sM[NL_MAX], sV[NL_MAX], n[NL_MAX];
+    T scale[NL_MAX];
+    int S[NL_MAX];
+    unsigned char scalar[NL_MAX];        // bit 0: x, bit 1: m, bit 2: v is a single element per sample
+    int count;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) normal_logpdf_multi_kernel(NlTable<T> tb, T* __restrict__ out) {
+    __shared__ T red[32];
+    const int t = blockIdx.y;
+    if (t >= tb.count) return;
+    const T* x = tb.x[t]; const T* m = tb.m[t]; const T* v = tb.v[t];
+    const int64_t sX = tb.sX[t], sM = tb.sM[t], sV = tb.sV[t], n = tb.n[t];
+    const int S = tb.S[t];
+    const int fx = tb.scalar[t] & 1, fm = tb.scalar[t] & 2, fv = tb.scalar[t] & 4;
+    const T c0 = T(-0.91893853320467274178);
+    T acc = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        for (int s = 0; s < S; ++s) {
+            const T xv = x[s * sX + (fx ? 0 : i)], mv = m[s * sM + (fm ? 0 : i)], vv = v[s * sV + (fv ? 0 : i)];
+            const T d = xv - mv;
+            acc += c0 - T(0.5) * Num<T>::log_(vv) - d * d / (T(2) * vv);
+        }
+    }
+    const T tot = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, tot * tb.scale[t] / T(S));
+}
+
+// Adjoint: per-entry gx / gm / gv (nullptr = not needed).  Scalar operands never receive a gradient here (the caller
+// keeps such entries out of the batch).
+template <typename T>
+__global__ void __launch_bounds__(256) normal_logpdf_multi_bwd_kernel(NlTable<T> tb, const T* __restrict__ gout) {
+    const int t = blockIdx.y;
+    if (t >= tb.count) return;
+    const T* x = tb.x[t]; const T* m = tb.m[t]; const T* v = tb.v[t];
+    T* gx = tb.gx[t]; T* gm = tb.gm[t]; T* gv = tb.gv[t];
+    const int64_t sX = tb.sX[t], sM = tb.sM[t], sV = tb.sV[t], n = tb.n[t];
+    const int S = tb.S[t];
+    const int fx = tb.scalar[t] & 1, fm = tb.scalar[t] & 2, fv = tb.scalar[t] & 4;
+    const T g = gout[0] * tb.scale[t] / T(S);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T ax = 0, am = 0, av = 0;
+        for (int s = 0; s < S; ++s) {
+            const T xv = x[s * sX + (fx ? 0 : i)], mv = m[s * sM + (fm ? 0 : i)], vv = v[s * sV + (fv ? 0 : i)];
+            const T d = xv - mv;
+            const T dx = -d / vv * g;
+            const T dv = (T(-0.5) / vv + T(0.5) * d * d / (vv * vv)) * g;
+            if (gx) { if (sX) gx[s * n + i] = dx; else ax += dx; }
+            if (gm) { if (sM) gm[s * n + i] = -dx; else am -= dx; }
+            if (gv) { if (sV) gv[s * n + i] = dv; else av += dv; }
+        }
+        if (gx && !sX) gx[i] = ax;
+        if (gm && !sM) gm[i] = am;
+        if (gv && !sV) gv[i] = av;
+    }
+}
+
 static inline int grid_for(int64_t n, int threads = 256) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)8 * kNumSMs));
 }
@@ -550,4 +623,68 @@ extern "C" int mxf_normal_reparam_bwd(int dtype, const void* gw, const void* eps
     MXF_DISPATCH_DTYPE(dtype, normal_reparam_bwd_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
                                   (const T*)gw, (const T*)eps, (const T*)v, sM, sV, S, n, (T*)gm, (T*)gv));
     return after_launch();
+}
+
+template <typename T>
+static int nl_multi(int count, const void* const* x, const void* const* m, const void* const* v, const int64_t* sX,
+                    const int64_t* sM, const int64_t* sV, const int64_t* n, const int* S, const int* scalar,
+                    const double* scale, void* out, const void* gout, void* const* gx, void* const* gm, void* const* gv,
+                    cudaStream_t st) {
+    for (int base = 0; base < count; base += NL_MAX) {
+        NlTable<T> tb;
+        tb.count = std::min(NL_MAX, count - base);
+        int64_t nmax = 1;
+        for (int i = 0; i < NL_MAX; ++i) {
+            const bool on = i < tb.count;
+            const int k = base + i;
+            tb.x[i] = on ? static_cast<const T*>(x[k]) : nullptr;
+            tb.m[i] = on ? static_cast<const T*>(m[k]) : nullptr;
+            tb.v[i] = on ? static_cast<const T*>(v[k]) : nullptr;
+            tb.gx[i] = (on && gx) ? static_cast<T*>(gx[k]) : nullptr;
+            tb.gm[i] = (on && gm) ? static_cast<T*>(gm[k]) : nullptr;
+            tb.gv[i] = (on && gv) ? static_cast<T*>(gv[k]) : nullptr;
+            tb.sX[i] = on ? sX[k] : 0; tb.sM[i] = on ? sM[k] : 0; tb.sV[i] = on ? sV[k] : 0;
+            tb.n[i] = on ? n[k] : 0;
+            tb.S[i] = on ? S[k] : 1;
+            tb.scalar[i] = on ? (unsigned char)scalar[k] : 0;
+            tb.scale[i] = on ? (T)scale[k] : T(0);
+            if (on) {
+                if (!tb.x[i] || !tb.m[i] || !tb.v[i] || tb.n[i] < 0 || tb.S[i] < 1) return MXF_EINVAL;
+                if (gout && ((tb.gx[i] && (tb.scalar[i] & 1)) || (tb.gm[i] && (tb.scalar[i] & 2)) ||
+                             (tb.gv[i] && (tb.scalar[i] & 4))))
+                    return MXF_ENOTIMPL;
+                nmax = std::max(nmax, tb.n[i]);
+            }
+        }
+        dim3 grid((unsigned)std::min<int64_t>(cdiv(nmax, 256), 2 * kNumSMs), tb.count);
+        if (!gout) normal_logpdf_multi_kernel<T><<<grid, 256, 0, st>>>(tb, static_cast<T*>(out));
+        else normal_logpdf_multi_bwd_kernel<T><<<grid, 256, 0, st>>>(tb, static_cast<const T*>(gout));
+        int rc = after_launch();
+        if (rc != MXF_OK) return rc;
+    }
+    return MXF_OK;
+}
+
+extern "C" int mxf_normal_logpdf_multi(int dtype, int count, const void* const* x, const void* const* m,
+                                       const void* const* v, const int64_t* sX, const int64_t* sM, const int64_t* sV,
+                                       const int64_t* n, const int* S, const int* scalar, const double* scale, void* out,
+                                       void* stream) {
+    if (count < 0 || (count > 0 && (!x || !m || !v || !sX || !sM || !sV || !n || !S || !scalar || !scale || !out)))
+        return MXF_EINVAL;
+    if (count == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, return nl_multi<T>(count, x, m, v, sX, sM, sV, n, S, scalar, scale, out, nullptr, nullptr,
+                                                 nullptr, nullptr, (cudaStream_t)stream));
+}
+
+extern "C" int mxf_normal_logpdf_multi_bwd(int dtype, int count, const void* const* x, const void* const* m,
+                                           const void* const* v, const int64_t* sX, const int64_t* sM, const int64_t* sV,
+                                           const int64_t* n, const int* S, const int* scalar, const double* scale,
+                                           const void* gout, void* const* gx, void* const* gm, void* const* gv,
+                                           void* stream) {
+    if (count < 0 || (count > 0 && (!x || !m || !v || !sX || !sM || !sV || !n || !S || !scalar || !scale || !gout ||
+                                    !gx || !gm || !gv)))
+        return MXF_EINVAL;
+    if (count == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, return nl_multi<T>(count, x, m, v, sX, sM, sV, n, S, scalar, scale, nullptr, gout, gx, gm,
+                                                 gv, (cudaStream_t)stream));
 }

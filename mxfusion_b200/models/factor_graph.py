@@ -129,6 +129,7 @@ class FactorGraph(object):
         if targets is not None:
             targets = set(t.uuid if isinstance(t, ModelComponent) else t for t in targets)
         logL = 0.
+        batch = []
         for f in self.ordered_factors:
             if isinstance(f, FunctionEvaluation):
                 outcome = f.eval(F=F, variables=variables, always_return_tuple=True)
@@ -139,6 +140,10 @@ class FactorGraph(object):
                     variables[var.uuid] = v
             elif isinstance(f, Distribution):
                 if targets is None or f.random_variable.uuid in targets:
+                    ops_ = f.log_pdf_operands(F, variables) if hasattr(f, 'log_pdf_operands') else None
+                    if ops_ is not None:
+                        batch.append(ops_)          # Normal factors: evaluated together below, one launch each way
+                        continue
                     term = f.log_pdf_sum(F=F, variables=variables)
                     logL = term if (isinstance(logL, float) and logL == 0.) else logL + term
             elif isinstance(f, Module):
@@ -152,6 +157,10 @@ class FactorGraph(object):
                     logL = term if (isinstance(logL, float) and logL == 0.) else logL + term
             else:
                 raise ModelSpecificationError("There is an object in the factor graph that isn't a factor.")
+        if batch:
+            from .. import ops
+            term = ops.normal_log_pdf_sum_multi(batch).reshape(())
+            logL = term if (isinstance(logL, float) and logL == 0.) else logL + term
         return logL
 
     def draw_samples(self, F, variables, num_samples=1, targets=None):

@@ -225,6 +225,37 @@ def normal_log_pdf_sum(x, mean, variance, scale=1.0):
     return _NormalLogPdfSum.apply(x, mean, variance, float(scale))
 
 
+class _NormalLogPdfMulti(torch.autograd.Function):
+    """All Normal factors of a graph walk in one launch each way; inputs x_0, m_0, v_0, x_1, ... (scales in ctx)."""
+
+    @staticmethod
+    def forward(ctx, scales, *xmv):
+        entries = [(xmv[3 * t], xmv[3 * t + 1], xmv[3 * t + 2], scales[t]) for t in range(len(scales))]
+        ctx.scales = scales
+        ctx.save_for_backward(*xmv)
+        return R.normal_logpdf_multi(entries)
+
+    @staticmethod
+    def backward(ctx, g):
+        xmv, scales = ctx.saved_tensors, ctx.scales
+        entries = [(xmv[3 * t], xmv[3 * t + 1], xmv[3 * t + 2], scales[t]) for t in range(len(scales))]
+        needs = [tuple(ctx.needs_input_grad[1 + 3 * t + k] for k in range(3)) for t in range(len(scales))]
+        grads = R.normal_logpdf_multi_bwd(entries, g, needs)
+        out = [None]
+        for row in grads:
+            out += list(row)
+        return tuple(out)
+
+
+def normal_log_pdf_sum_multi(entries):
+    """sum over the entries (x, mean, variance, scale) of scale * F.sum(F.mean(Normal.log_pdf, axis=0)): the Normal
+    factors of one factor-graph walk in a single launch (and a single adjoint launch)."""
+    flat = []
+    for x, m, v, _ in entries:
+        flat += [x, m, v]
+    return _NormalLogPdfMulti.apply(tuple(float(e[3]) for e in entries), *flat)
+
+
 class _NormalReparam(torch.autograd.Function):
     @staticmethod
     def forward(ctx, m, v, S, eps, seed, offset, step_counter):

@@ -294,3 +294,26 @@ def normal_reparam_bwd(gw, eps, v, m_samples, need=(True, True)):
     if v.shape[0] != gv.shape[0]:
         gv = gv.sum(dim=0, keepdim=True)
     return (gm if need[0] else None), (gv if need[1] else None)
+
+
+def normal_logpdf_multi(entries):
+    out = torch.zeros((1,), dtype=entries[0][0].dtype)
+    for x, m, v, scale in entries:
+        S = max(x.shape[0], m.shape[0], v.shape[0])
+        lp = -0.5 * math.log(2 * math.pi) - 0.5 * torch.log(v) - (x - m) ** 2 / (2 * v)
+        lp = lp.expand((S,) + tuple(lp.shape[1:]))
+        out = out + scale * lp.sum() / S
+    return out
+
+
+def normal_logpdf_multi_bwd(entries, gout, needs):
+    res = []
+    for (x, m, v, scale), need in zip(entries, needs):
+        with torch.enable_grad():
+            xr, mr, vr = (t.detach().clone().requires_grad_() for t in (x, m, v))
+            S = max(x.shape[0], m.shape[0], v.shape[0])
+            lp = -0.5 * math.log(2 * math.pi) - 0.5 * torch.log(vr) - (xr - mr) ** 2 / (2 * vr)
+            lp = lp.expand((S,) + tuple(lp.shape[1:]))
+            (scale * lp.sum() / S * gout.reshape(-1)[0]).backward()
+        res.append(tuple(t.grad if n else None for t, n in zip((xr, mr, vr), need)))
+    return res

@@ -575,3 +575,39 @@ def test_reparam_adjoint(cuda, prec, shared):
     ((torch.tensor(eps) * torch.sqrt(rv) + rm) * torch.tensor(gw)).sum().backward()
     np.testing.assert_allclose(tm.grad.cpu().numpy(), rm.grad.numpy(), rtol=rtol * 10, atol=atol * 10)
     np.testing.assert_allclose(tv.grad.cpu().numpy(), rv.grad.numpy(), rtol=rtol * 10, atol=atol * 10)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+def test_normal_logpdf_multi(cuda, prec):
+    """The multi-tensor Normal log-density (all Normal factors of a graph walk in one launch each way) against the oracle,
+    entry by entry: sampled / shared operands, one-element (constant prior) operands, different sample counts and scales."""
+    from mxfusion_b200 import ops
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(9)
+    spec = [  # (S_x, S_m, S_v, shape, scalar_m, scalar_v, scale)
+        (3, 1, 1, (50, 1), False, False, 1.0), (3, 1, 1, (50, 50), True, True, 1.0), (1, 3, 1, (64, 1), False, True, 24.4),
+        (3, 3, 3, (7,), False, False, 0.5), (1, 1, 1, (5, 2), False, False, 2.0)]
+    spec = spec * 4          # 20 entries: more than one table (16 per launch)
+    entries, ref, leaves = [], 0.0, []
+    for Sx, Sm, Sv, shape, scm, scv, scale in spec:
+        x = rng.randn(Sx, *shape)
+        m = rng.randn(Sm, *((1,) * len(shape) if scm else shape))
+        v = rng.rand(Sv, *((1,) * len(shape) if scv else shape)) + 0.3
+        S = max(Sx, Sm, Sv)
+        lp = on.log_pdf(np.broadcast_to(m, (S,) + shape) if not scm else m, v, np.broadcast_to(x, (S,) + shape))
+        ref += scale * np.sum(np.mean(np.broadcast_to(lp, (S,) + shape), axis=0))
+        tx = T(x, cuda, tdt).requires_grad_()
+        tm = T(m, cuda, tdt).requires_grad_(not scm)
+        tv = T(v, cuda, tdt).requires_grad_(not scv)
+        entries.append((tx, tm, tv, scale))
+        leaves.append((x, m, v, scale, S, shape, scm, scv))
+    got = ops.normal_log_pdf_sum_multi(entries)
+    np.testing.assert_allclose(float(got), ref, rtol=rtol * 5)
+    (got * 1.7).sum().backward()
+    for (tx, tm, tv, _), (x, m, v, scale, S, shape, scm, scv) in zip(entries, leaves):
+        rx, rm, rv = torch.tensor(x, requires_grad=True), torch.tensor(m, requires_grad=True), torch.tensor(v, requires_grad=True)
+        lp = -0.5 * np.log(2 * np.pi) - 0.5 * torch.log(rv) - (rx - rm) ** 2 / (2 * rv)
+        (1.7 * scale * lp.expand((S,) + shape).sum() / S).backward()
+        pairs = [(tx, rx)] + ([] if scm else [(tm, rm)]) + ([] if scv else [(tv, rv)])
+        for t, r in pairs:
+            np.testing.assert_allclose(t.grad.cpu().numpy(), r.grad.numpy(), rtol=rtol * 20, atol=atol * 20)
