@@ -247,6 +247,14 @@ int mxf_normal_reparam(int dtype, const void* eps, const void* m, int64_t sM, co
  * the sum over samples; gm / gv may be NULL. */
 int mxf_normal_reparam_bwd(int dtype, const void* gw, const void* eps, const void* v, int64_t sM, int64_t sV, int S,
                            int64_t n, void* gm, void* gv, void* stream);
+/* Multi-tensor forms (HOST arrays of DEVICE pointers / sizes): `count` independent draws in one launch, entry t with its
+ * own Philox offset[t] (same seed and step counter), and their adjoints in one launch. */
+int mxf_normal_reparam_multi(int dtype, int count, const void* const* m, const void* const* v, const int64_t* sM,
+                             const int64_t* sV, const int64_t* n, const int* S, uint64_t seed, const uint64_t* offset,
+                             const int* step_counter, void* const* w, void* const* eps_out, void* stream);
+int mxf_normal_reparam_multi_bwd(int dtype, int count, const void* const* gw, const void* const* eps,
+                                 const void* const* v, const int64_t* sM, const int64_t* sV, const int64_t* n,
+                                 const int* S, void* const* gm, void* const* gv, void* stream);
 
 /* ---- optimiser (mx.gluon.Trainer('adam').step(batch_size), minibatch_loop.py:71-91) ----
  * One fused update over a flat parameter bucket:

@@ -60,6 +60,8 @@ def _declare(lib):
         'mxf_normal_reparam': (i, [i, p, p, l, p, l, i, l, u, u, p, p, p, p]),
         'mxf_normal_logpdf_multi': (i, [i, i, p, p, p, p, p, p, p, p, p, p, p, p]),
         'mxf_normal_logpdf_multi_bwd': (i, [i, i, p, p, p, p, p, p, p, p, p, p, p, p, p, p, p]),
+        'mxf_normal_reparam_multi': (i, [i, i, p, p, p, p, p, p, u, p, p, p, p, p]),
+        'mxf_normal_reparam_multi_bwd': (i, [i, i, p, p, p, p, p, p, p, p, p, p]),
         'mxf_normal_reparam_bwd': (i, [i, p, p, p, l, l, i, l, p, p, p]),
         'mxf_adam_step': (i, [i, p, p, p, p, l, d, d, d, d, d, p, p]),
         'mxf_gather_rows': (i, [i, p, l, p, p, l, p, p]),

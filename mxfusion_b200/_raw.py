@@ -559,3 +559,53 @@ def normal_logpdf_multi_bwd(entries, gout, needs):
                                             c['S'], c['fl'], c['scale'], ptr(gout), arr(ptrs[0]), arr(ptrs[1]),
                                             arr(ptrs[2]), stream_ptr()), 'mxf_normal_logpdf_multi_bwd')
     return grads
+
+
+def normal_reparam_multi(entries, seed, offsets, step_counter=None):
+    """Draws for a list of (m, v, S): w_t (S, *shape) = eps * sqrt(v) + m with in-kernel Philox streams (seed, offsets[t]);
+    ONE launch.  Returns [(w, eps)]."""
+    import ctypes
+    T = len(entries)
+    ms, vs, outs, sM, sV, ns, Ss = [], [], [], [], [], [], []
+    for m, v, S in entries:
+        require_cuda(m, v)
+        shape = tuple(m.shape[1:])
+        mf, vf = _flat(m), _flat(v)
+        n = mf.shape[1]
+        w = torch.empty((S, n), dtype=m.dtype, device=m.device)
+        e = torch.empty_like(w)
+        ms.append(mf); vs.append(vf); outs.append((w, e, shape))
+        sM.append(_bstride(mf, S)); sV.append(_bstride(vf, S)); ns.append(n); Ss.append(int(S))
+    vp = lambda ts: (ctypes.c_void_p * T)(*[t.data_ptr() for t in ts])
+    check(lib().mxf_normal_reparam_multi(dtype_code(ms[0]), T, vp(ms), vp(vs), (ctypes.c_int64 * T)(*sM),
+                                         (ctypes.c_int64 * T)(*sV), (ctypes.c_int64 * T)(*ns), (ctypes.c_int * T)(*Ss),
+                                         int(seed), (ctypes.c_uint64 * T)(*[int(o) for o in offsets]), ptr(step_counter),
+                                         vp([o[0] for o in outs]), vp([o[1] for o in outs]), stream_ptr()),
+          'mxf_normal_reparam_multi')
+    return [(w.reshape((w.shape[0],) + shape), e.reshape((e.shape[0],) + shape)) for w, e, shape in outs]
+
+
+def normal_reparam_multi_bwd(entries, needs):
+    """Adjoints for a list of (gw, eps, v, m_samples): [(gm, gv)] (None where not needed); ONE launch."""
+    import ctypes
+    T = len(entries)
+    gws, es, vs, sM, sV, ns, Ss, res, pm, pv = [], [], [], [], [], [], [], [], [], []
+    for (gw, e, v, m_samples), need in zip(entries, needs):
+        require_cuda(gw, e, v)
+        S = gw.shape[0]
+        shape = tuple(gw.shape[1:])
+        gwf, ef, vf = _flat(gw), _flat(e), _flat(v)
+        n = gwf.shape[1]
+        gm = torch.empty(((m_samples if m_samples > 1 else 1), n), dtype=gw.dtype, device=gw.device) if need[0] else None
+        gv = torch.empty((vf.shape[0], n), dtype=gw.dtype, device=gw.device) if need[1] else None
+        gws.append(gwf); es.append(ef); vs.append(vf)
+        sM.append(n if m_samples > 1 else 0); sV.append(_bstride(vf, S)); ns.append(n); Ss.append(S)
+        pm.append(None if gm is None else gm.data_ptr()); pv.append(None if gv is None else gv.data_ptr())
+        res.append((None if gm is None else gm.reshape((gm.shape[0],) + shape),
+                    None if gv is None else gv.reshape((gv.shape[0],) + shape)))
+    vp = lambda ts: (ctypes.c_void_p * T)(*[t.data_ptr() for t in ts])
+    check(lib().mxf_normal_reparam_multi_bwd(dtype_code(gws[0]), T, vp(gws), vp(es), vp(vs), (ctypes.c_int64 * T)(*sM),
+                                             (ctypes.c_int64 * T)(*sV), (ctypes.c_int64 * T)(*ns), (ctypes.c_int * T)(*Ss),
+                                             (ctypes.c_void_p * T)(*pm), (ctypes.c_void_p * T)(*pv), stream_ptr()),
+          'mxf_normal_reparam_multi_bwd')
+    return res

@@ -51,6 +51,22 @@ class Normal(Distribution):
                 return None
         return x, m, v, self.log_pdf_scaling
 
+    def draw_operands(self, F, variables, num_samples):
+        """(mean, variance, num_samples, (seed, offset)) for the batched draw of independent Normal factors
+        (FactorGraph.draw_samples -> ops.normal_draw_multi), or None when the generator injects fixed noise."""
+        gen = self._rand_gen
+        if not getattr(gen, 'in_kernel', False):
+            return None
+        from ..variables.runtime_variable import arrays_as_samples
+        kw = arrays_as_samples(F, self.fetch_runtime_inputs(variables))
+        mean, variance = kw['mean'], kw['variance']
+        rv_shape = self._realized_shape(variables)
+        if tuple(mean.shape[1:]) != tuple(rv_shape):
+            mean = mean.expand((mean.shape[0],) + tuple(rv_shape))
+        if tuple(variance.shape[1:]) != tuple(rv_shape):
+            variance = variance.expand((variance.shape[0],) + tuple(rv_shape))
+        return mean, variance, num_samples, gen.next_stream()
+
     def draw_samples_impl(self, mean, variance, rv_shape, num_samples=1, F=None):
         """normal.py:72-92: eps * sqrt(variance) + mean with eps ~ N(0,1) of shape (S,) + rv_shape."""
         full = (num_samples,) + tuple(rv_shape)

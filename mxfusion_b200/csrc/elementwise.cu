@@ -475,6 +475,85 @@ __global__ void __launch_bounds__(256) normal_logpdf_multi_bwd_kernel(NlTable<T>
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Multi-tensor reparameterised draw and its adjoint: the draws of all (independent) Normal factors of a posterior graph
+// walk -- one weight tensor each in a mean-field BNN -- in ONE launch each way.  Entry t has its own Philox stream
+// (seed, offset_t); the device step counter is mixed in as for the single-tensor kernel.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int RP_MAX = 16;
+template <typename T>
+struct RpTable {
+    const T* m[RP_MAX]; const T* v[RP_MAX];
+    T* w[RP_MAX]; T* eps[RP_MAX];                 // forward: outputs; adjoint: w = upstream gradient (read), eps (read)
+    T* gm[RP_MAX]; T* gv[RP_MAX];
+    int64_t sM[RP_MAX], sV[RP_MAX], n[RP_MAX];
+    unsigned long long offset[RP_MAX];
+    int S[RP_MAX];
+    int count;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+normal_reparam_multi_kernel(RpTable<T> tb, uint64_t seed, const int* __restrict__ step_counter) {
+    const int t = blockIdx.y;
+    if (t >= tb.count) return;
+    uint64_t offset = tb.offset[t];
+    if (step_counter) offset += (uint64_t)(uint32_t)(*step_counter) << 32;
+    const T* m = tb.m[t]; const T* v = tb.v[t];
+    T* w = tb.w[t]; T* eps_out = tb.eps[t];
+    const int64_t sM = tb.sM[t], sV = tb.sV[t], n = tb.n[t];
+    const int64_t total = (int64_t)tb.S[t] * n, quads = (total + 3) / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+        uint32_t r[4];
+        philox4x32_10((uint64_t)q, offset, seed, r);
+        float z[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float u1 = ((float)r[2 * h] + 1.0f) * 2.3283064365386963e-10f;
+            const float u2 = (float)r[2 * h + 1] * 2.3283064365386963e-10f;
+            const float rad = sqrtf(-2.0f * __logf(u1));
+            float sn, cs;
+            __sincosf(6.283185307179586f * u2, &sn, &cs);
+            z[2 * h] = rad * cs;
+            z[2 * h + 1] = rad * sn;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t e = 4 * q + u;
+            if (e < total) {
+                const int64_t sidx = e / n, i = e - sidx * n;
+                const T ev = (T)z[u];
+                if (eps_out) eps_out[e] = ev;
+                w[e] = fma(ev, Num<T>::sqrt_(v[sidx * sV + i]), m[sidx * sM + i]);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) normal_reparam_multi_bwd_kernel(RpTable<T> tb) {
+    const int t = blockIdx.y;
+    if (t >= tb.count) return;
+    const T* gw = tb.w[t]; const T* eps = tb.eps[t]; const T* v = tb.v[t];
+    T* gm = tb.gm[t]; T* gv = tb.gv[t];
+    const int64_t sM = tb.sM[t], sV = tb.sV[t], n = tb.n[t];
+    const int S = tb.S[t];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T am = 0, av = 0;
+        for (int s = 0; s < S; ++s) {
+            const T g = gw[s * n + i];
+            const T dv = g * eps[s * n + i] * (T(0.5) * Num<T>::rsqrt_(v[s * sV + i]));
+            if (gm) { if (sM) gm[s * n + i] = g; else am += g; }
+            if (gv) { if (sV) gv[s * n + i] = dv; else av += dv; }
+        }
+        if (gm && !sM) gm[i] = am;
+        if (gv && !sV) gv[i] = av;
+    }
+}
+
 static inline int grid_for(int64_t n, int threads = 256) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)8 * kNumSMs));
 }
@@ -687,4 +766,59 @@ extern "C" int mxf_normal_logpdf_multi_bwd(int dtype, int count, const void* con
     if (count == 0) return MXF_OK;
     MXF_DISPATCH_DTYPE(dtype, return nl_multi<T>(count, x, m, v, sX, sM, sV, n, S, scalar, scale, nullptr, gout, gx, gm,
                                                  gv, (cudaStream_t)stream));
+}
+
+template <typename T>
+static int rp_multi(int bwd, int count, const void* const* m, const void* const* v, const int64_t* sM, const int64_t* sV,
+                    const int64_t* n, const int* S, uint64_t seed, const uint64_t* offset, const int* step_counter,
+                    void* const* w, void* const* eps, void* const* gm, void* const* gv, cudaStream_t st) {
+    for (int base = 0; base < count; base += RP_MAX) {
+        RpTable<T> tb;
+        tb.count = std::min(RP_MAX, count - base);
+        int64_t work = 1;
+        for (int i = 0; i < RP_MAX; ++i) {
+            const bool on = i < tb.count;
+            const int k = base + i;
+            tb.m[i] = (on && m) ? static_cast<const T*>(m[k]) : nullptr;
+            tb.v[i] = on ? static_cast<const T*>(v[k]) : nullptr;
+            tb.w[i] = on ? static_cast<T*>(w[k]) : nullptr;
+            tb.eps[i] = (on && eps) ? static_cast<T*>(eps[k]) : nullptr;
+            tb.gm[i] = (on && gm) ? static_cast<T*>(gm[k]) : nullptr;
+            tb.gv[i] = (on && gv) ? static_cast<T*>(gv[k]) : nullptr;
+            tb.sM[i] = on ? sM[k] : 0; tb.sV[i] = on ? sV[k] : 0; tb.n[i] = on ? n[k] : 0;
+            tb.S[i] = on ? S[k] : 1;
+            tb.offset[i] = (on && offset) ? offset[k] : 0;
+            if (on) {
+                if (!tb.v[i] || !tb.w[i] || tb.n[i] < 0 || tb.S[i] < 1 || (!bwd && !tb.m[i]) || (bwd && !tb.eps[i]))
+                    return MXF_EINVAL;
+                work = std::max(work, bwd ? tb.n[i] : (tb.n[i] * tb.S[i] + 3) / 4);
+            }
+        }
+        dim3 grid((unsigned)std::min<int64_t>(cdiv(work, 256), 2 * kNumSMs), tb.count);
+        if (!bwd) normal_reparam_multi_kernel<T><<<grid, 256, 0, st>>>(tb, seed, step_counter);
+        else normal_reparam_multi_bwd_kernel<T><<<grid, 256, 0, st>>>(tb);
+        int rc = after_launch();
+        if (rc != MXF_OK) return rc;
+    }
+    return MXF_OK;
+}
+
+extern "C" int mxf_normal_reparam_multi(int dtype, int count, const void* const* m, const void* const* v,
+                                        const int64_t* sM, const int64_t* sV, const int64_t* n, const int* S,
+                                        uint64_t seed, const uint64_t* offset, const int* step_counter, void* const* w,
+                                        void* const* eps_out, void* stream) {
+    if (count < 0 || (count > 0 && (!m || !v || !sM || !sV || !n || !S || !offset || !w))) return MXF_EINVAL;
+    if (count == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, return rp_multi<T>(0, count, m, v, sM, sV, n, S, seed, offset, step_counter, w, eps_out,
+                                                 nullptr, nullptr, (cudaStream_t)stream));
+}
+
+extern "C" int mxf_normal_reparam_multi_bwd(int dtype, int count, const void* const* gw, const void* const* eps,
+                                            const void* const* v, const int64_t* sM, const int64_t* sV, const int64_t* n,
+                                            const int* S, void* const* gm, void* const* gv, void* stream) {
+    if (count < 0 || (count > 0 && (!gw || !eps || !v || !sM || !sV || !n || !S || !gm || !gv))) return MXF_EINVAL;
+    if (count == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, return rp_multi<T>(1, count, nullptr, v, sM, sV, n, S, 0, nullptr, nullptr,
+                                                 const_cast<void* const*>(gw), const_cast<void* const*>(eps), gm, gv,
+                                                 (cudaStream_t)stream));
 }

@@ -167,7 +167,26 @@ class FactorGraph(object):
         """factor_graph.py:240-297."""
         from ..modules.module import Module
         samples = {}
+        pending = []            # independent Normal draws, issued together (one launch, one adjoint launch)
+
+        def flush():
+            if not pending:
+                return
+            from .. import ops
+            from ..components.distributions.random_gen import step_counter
+            seed = pending[0][1][3][0]
+            dev = pending[0][1][0].device
+            ws = ops.normal_draw_multi([(m, v, ns) for _, (m, v, ns, _) in pending], seed,
+                                       [st[1] for _, (_, _, _, st) in pending], step_counter(dev))
+            for (fac, _), w in zip(pending, ws):
+                var = fac.outputs[0][1]
+                variables[var.uuid] = w
+                samples[var.uuid] = w
+            del pending[:]
+
         for f in self.ordered_factors:
+            if pending and any(v.uuid not in variables for _, v in f.inputs):
+                flush()                                    # this factor consumes a draw that is still pending
             if isinstance(f, FunctionEvaluation):
                 outcome = f.eval(F=F, variables=variables, always_return_tuple=True)
                 for v, (_, var) in zip(outcome, f.outputs):
@@ -180,6 +199,11 @@ class FactorGraph(object):
                 elif any(known):
                     raise InferenceError("Part of the outputs of the distribution " + f.__class__.__name__ +
                                          " has been observed!")
+                if hasattr(f, 'draw_operands') and all(v.uuid in variables for _, v in f.inputs):
+                    ops_ = f.draw_operands(F, variables, num_samples)
+                    if ops_ is not None:
+                        pending.append((f, ops_))
+                        continue
                 outcome = f.draw_samples(F=F, num_samples=num_samples, variables=variables,
                                          always_return_tuple=True)
                 for v, (_, var) in zip(outcome, f.outputs):
@@ -193,6 +217,7 @@ class FactorGraph(object):
                     samples[uuid] = v
             else:
                 raise ModelSpecificationError("There is an object in the factor graph that isn't a factor.")
+        flush()
         if targets:
             return tuple(samples[t.uuid if isinstance(t, ModelComponent) else t] for t in targets)
         return samples

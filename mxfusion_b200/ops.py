@@ -280,6 +280,42 @@ def normal_draw(mean, variance, num_samples, eps=None, seed=0, offset=0, step_co
     return _NormalReparam.apply(mean, variance, int(num_samples), eps, int(seed), int(offset), step_counter)
 
 
+class _NormalReparamMulti(torch.autograd.Function):
+    """Independent reparameterised draws of several Normal factors in one launch (and one adjoint launch).  Inputs
+    m_0, v_0, m_1, v_1, ...; outputs w_0, w_1, ..."""
+
+    @staticmethod
+    def forward(ctx, meta, *mv):
+        S_list, seed, offsets, step_counter = meta
+        entries = [(mv[2 * t], mv[2 * t + 1], S_list[t]) for t in range(len(S_list))]
+        outs = R.normal_reparam_multi(entries, seed, offsets, step_counter)
+        ctx.mS = [mv[2 * t].shape[0] for t in range(len(S_list))]
+        ctx.save_for_backward(*[o[1] for o in outs], *[mv[2 * t + 1] for t in range(len(S_list))])
+        return tuple(o[0] for o in outs)
+
+    @staticmethod
+    def backward(ctx, *gws):
+        T = len(ctx.mS)
+        saved = ctx.saved_tensors
+        eps, vs = saved[:T], saved[T:]
+        gws = [torch.zeros_like(eps[t]) if gws[t] is None else gws[t] for t in range(T)]
+        needs = [(ctx.needs_input_grad[1 + 2 * t], ctx.needs_input_grad[2 + 2 * t]) for t in range(T)]
+        grads = R.normal_reparam_multi_bwd([(gws[t], eps[t], vs[t], ctx.mS[t]) for t in range(T)], needs)
+        out = [None]
+        for gm, gv in grads:
+            out += [gm, gv]
+        return tuple(out)
+
+
+def normal_draw_multi(entries, seed, offsets, step_counter=None):
+    """entries: [(mean, variance, num_samples)] -> [w_t]; in-kernel Philox streams (seed, offsets[t])."""
+    mv = []
+    for m, v, _ in entries:
+        mv += [m, v]
+    meta = (tuple(int(e[2]) for e in entries), int(seed), tuple(int(o) for o in offsets), step_counter)
+    return list(_NormalReparamMulti.apply(meta, *mv))
+
+
 # --------------------------------------------------------------------------------------------------
 # fused SVGP bound
 # --------------------------------------------------------------------------------------------------

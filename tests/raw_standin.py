@@ -317,3 +317,16 @@ def normal_logpdf_multi_bwd(entries, gout, needs):
             (scale * lp.sum() / S * gout.reshape(-1)[0]).backward()
         res.append(tuple(t.grad if n else None for t, n in zip((xr, mr, vr), need)))
     return res
+
+
+def normal_reparam_multi(entries, seed, offsets, step_counter=None):
+    out = []
+    for (m, v, S), off in zip(entries, offsets):
+        g = torch.Generator().manual_seed(int(seed) * 1000003 + int(off))
+        eps = torch.randn((S,) + tuple(m.shape[1:]), generator=g, dtype=m.dtype)
+        out.append((eps * torch.sqrt(v) + m, eps))
+    return out
+
+
+def normal_reparam_multi_bwd(entries, needs):
+    return [normal_reparam_bwd(gw, e, v, ms, need=need) for (gw, e, v, ms), need in zip(entries, needs)]

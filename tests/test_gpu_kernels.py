@@ -611,3 +611,41 @@ def test_normal_logpdf_multi(cuda, prec):
         pairs = [(tx, rx)] + ([] if scm else [(tm, rm)]) + ([] if scv else [(tv, rv)])
         for t, r in pairs:
             np.testing.assert_allclose(t.grad.cpu().numpy(), r.grad.numpy(), rtol=rtol * 20, atol=atol * 20)
+
+
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+def test_normal_draw_multi(cuda, prec):
+    """Batched reparameterised draws (one launch for all entries, one for their adjoints): moments of the noise, exact
+    adjoints given the realised noise, independent streams per entry, and a different draw per optimiser step."""
+    from mxfusion_b200 import ops
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(2)
+    shapes = [(50, 1), (50,), (50, 50), (1, 50), (1,), (333, 7)] * 3        # 18 entries: two tables
+    S = 4
+    ms = [T(rng.randn(1, *sh), cuda, tdt).requires_grad_() for sh in shapes]
+    vs = [T(rng.rand(1, *sh) + 0.3, cuda, tdt).requires_grad_() for sh in shapes]
+    ctr = torch.zeros((1,), dtype=torch.int32, device=cuda)
+    ws = ops.normal_draw_multi([(m, v, S) for m, v in zip(ms, vs)], seed=3, offsets=list(range(1, len(shapes) + 1)),
+                               step_counter=ctr)
+    gws = [T(rng.randn(S, *sh), cuda, tdt) for sh in shapes]
+    sum((w * g).sum() for w, g in zip(ws, gws)).backward()
+    zs = []
+    for m, v, w, g, sh in zip(ms, vs, ws, gws, shapes):
+        assert tuple(w.shape) == (S,) + sh
+        eps = ((w - m) / torch.sqrt(v)).detach()
+        zs.append(eps.flatten())
+        np.testing.assert_allclose(m.grad.cpu().numpy(), g.sum(0, keepdim=True).cpu().numpy(), rtol=rtol * 10, atol=atol * 10)
+        want = (g * eps * 0.5 / torch.sqrt(v.detach())).sum(0, keepdim=True)
+        np.testing.assert_allclose(v.grad.cpu().numpy(), want.cpu().numpy(), rtol=max(rtol * 100, 1e-6), atol=atol * 100)
+    z = torch.cat(zs).double()
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02
+    # entries 0 and 6 have the same shape but different offsets: different noise
+    assert not torch.allclose(zs[0], zs[6])
+    ctr.fill_(1)
+    ws2 = ops.normal_draw_multi([(m.detach(), v.detach(), S) for m, v in zip(ms, vs)], seed=3,
+                                offsets=list(range(1, len(shapes) + 1)), step_counter=ctr)
+    assert not torch.allclose(ws2[2], ws[2].detach())
+    ctr.fill_(0)
+    ws3 = ops.normal_draw_multi([(m.detach(), v.detach(), S) for m, v in zip(ms, vs)], seed=3,
+                                offsets=list(range(1, len(shapes) + 1)), step_counter=ctr)
+    assert torch.equal(ws3[2], ws[2].detach())
