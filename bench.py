@@ -10,6 +10,11 @@ MinibatchInferenceLoop).  `value` has the data set resident in HBM; `e2e` stream
 pinned host memory and reads the loss back every step.  Data-parallel runs give every rank a 1/G shard
 of the rows and the same per-rank batch (weak scaling), with one NCCL all-reduce of the flat gradient
 bucket per step; value = G * steps / time, in minibatch iterations per second.
+
+Extra keys: `roofline` (K(X,Z) at the full headline size against the measured HBM peak, `traffic` from the committed ncu
+capture), `roofline_tensor` (the 4096^3 tcgen05 3xTF32 GEMM against half the measured bf16 peak), `cpu_baseline` (the
+op-for-op CPU restatement of the reference's step on all host cores, ~12 s sample), `clocks`.  `--workload c2|c3` runs the
+other SVGP configs of BASELINE.json through the same code and prints the same JSON (not the line the driver reads).
 """
 import argparse
 import json
