@@ -15,13 +15,21 @@
 
 namespace mxf {
 
+// 1 / sqrt(x) for x >= 1e-14 (never denormal here): one MUFU.RSQ, without rsqrtf's denormal fix-up instructions
+template <typename T> __device__ __forceinline__ T rsqrt_pos(T x) { return Num<T>::rsqrt_(x); }
+template <> __device__ __forceinline__ float rsqrt_pos<float>(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <typename T, int KIND>
 __device__ __forceinline__ T kern_value(T r2, T var) {
     if (KIND == MXF_KERN_RBF) {
         return var * Num<T>::exp_(T(-0.5) * r2);
     } else {
         T r2c = r2 > T(1e-14) ? r2 : T(1e-14);
-        T R = r2c * Num<T>::rsqrt_(r2c);
+        T R = r2c * rsqrt_pos<T>(r2c);
         if (KIND == MXF_KERN_MATERN52) {
             const T s5 = T(2.23606797749978969641);
             T poly = fma(s5, R, fma(T(5.0 / 3.0), r2, T(1)));
@@ -69,6 +77,26 @@ __device__ __forceinline__ T kern_dr2(T r2, T var, T* k_over_var) {
             *k_over_var = e;
             return -var * e * dRdr2;
         }
+    }
+}
+
+// Matern value with the variance folded into the exponent (fp32 streaming kernel: var * exp(-a R) = 2^(log2 var - a log2e R),
+// one FFMA + one MUFU.EX2 instead of two multiplies + FMUL + MUFU); l2v = log2(var) is computed once per thread.
+template <int KIND>
+__device__ __forceinline__ float matern_value_l2(float r2, float l2v) {
+    const float r2c = r2 > 1e-14f ? r2 : 1e-14f;
+    const float R = r2c * rsqrt_pos<float>(r2c);
+    float y;
+    if (KIND == MXF_KERN_MATERN52) {
+        const float poly = fmaf(2.2360679774997896f, R, fmaf(5.0f / 3.0f, r2, 1.0f));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(-2.2360679774997896f * 1.4426950408889634f, R, l2v)));
+        return poly * y;
+    } else if (KIND == MXF_KERN_MATERN32) {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(-1.7320508075688772f * 1.4426950408889634f, R, l2v)));
+        return fmaf(1.7320508075688772f, R, 1.0f) * y;
+    } else {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(-1.4426950408889634f, R, l2v)));
+        return y;
     }
 }
 
@@ -306,6 +334,7 @@ kbuild_fwd_stream_kernel(const T* __restrict__ X, const T* __restrict__ X2, cons
     T dadd = T(0);
     if (SYM) dadd = diag_const + (diag_add ? diag_add[(int64_t)s * sDiag] : T(0));
     const bool full4 = vec_ok && (j0 + 3 < N2);
+    const float l2v = log2f((float)v);
 
     for (int rt = wr * KS_RM; rt < nrows; rt += WR * KS_RM) {
         T acc[KS_RM][4];
@@ -336,6 +365,7 @@ kbuild_fwd_stream_kernel(const T* __restrict__ X, const T* __restrict__ X2, cons
                 // the Matern square root would amplify (sqrt(1e-7) in f32)
                 if (SYM && i == j0 + c) e = RBF_FOLD ? -log2(v) : T(0);
                 if (RBF_FOLD) o[c] = (sizeof(T) == 4) ? (T)ex2_approx(-(float)e) : (T)exp2(-(double)e);
+                else if (sizeof(T) == 4) o[c] = (T)matern_value_l2<KIND>((float)e, l2v);
                 else o[c] = kern_value<T, KIND>(e, v);
                 if (SYM && i == j0 + c) o[c] += dadd;
             }
