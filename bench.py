@@ -36,7 +36,7 @@ KERNEL = 'rbf'
 WORKLOADS = {'headline': (1000000, 1024, 8, 4096, 'rbf'), 'c2': (100000, 512, 8, 2048, 'rbf'),
              'c3': (1000000, 1024, 16, 4096, 'matern52')}
 JITTER, LR = 1e-6, 1e-2
-KBUILD_NCU_TRAFFIC_BYTES = 4070277632      # profiles/r1b_kbuild_raw.csv: 32.06 MB read + 4038.2 MB written per launch
+KBUILD_NCU_TRAFFIC_BYTES = 4068866256      # profiles/r1e_kbuild_raw.csv: 32.06 MB read + 4036.8 MB written per launch
 METRIC = "svgp_elbo_iters_per_sec"
 UNIT = "minibatch iterations (B=4096 rows: ELBO fwd + grad + Adam) per second, summed over GPUs"
 
@@ -191,7 +191,7 @@ def kernel_rooflines(device, pk):
             'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
             'traffic': KBUILD_NCU_TRAFFIC_BYTES if (KERNEL, N_ROWS, M_IND, D_IN) == ('rbf', 1000000, 1024, 8) else None,
             'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture '
-                              'profiles/r1b_kbuild_raw.csv (0.032 GB read + 4.038 GB written)',
+                              'profiles/r1e_kbuild_raw.csv (0.032 GB read + 4.037 GB written)',
             'ms_per_launch': ms, 'algorithmic_bytes': nbytes}
 
 
