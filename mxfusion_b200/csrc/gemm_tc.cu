@@ -83,11 +83,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// hi part of the 3xTF32 split: round-to-nearest (ties away) to 10 mantissa bits, written as integer arithmetic on the bit
+// pattern (IADD + LOP3).  `cvt.rna.tf32.f32` compiles to the same two instructions PLUS an inf / NaN guard (FSETP + SEL):
+// the converter warps were the kernel's issue bottleneck at ~10 ALU instructions per element (ncu: ALU pipe 48 %, the
+// stall samples on those VIADD / LOP3 / FSETP lines), and an operand that close to FLT_MAX overflows the product anyway.
 __device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// lo part: x - hi is exact in fp32 and at most 2^-11 |x|; the tensor core reads only its upper 19 bits, so it is passed
+// unrounded (truncation error 2^-10 * 2^-11 |x| = 2^-21 |x|, of random sign because hi was rounded to nearest).
+__device__ __forceinline__ float lo_tf32(float d) { return d; }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64) with 2 = SWIZZLE_128B.
@@ -236,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 x = hi[i];
                 float4 h, l;
                 h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-                l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+                l.x = lo_tf32(x.x - h.x); l.y = lo_tf32(x.y - h.y); l.z = lo_tf32(x.z - h.z); l.w = lo_tf32(x.w - h.w);
                 hi[i] = h;
                 lo[i] = l;
             }
@@ -461,8 +466,8 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const float h0 = to_tf32(x.x), h1 = to_tf32(x.y), h2 = to_tf32(x.z), h3 = to_tf32(x.w);
                     hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
                     hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
-                    lo[4 * c] = __float_as_uint(to_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(to_tf32(x.y - h1));
-                    lo[4 * c + 2] = __float_as_uint(to_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(to_tf32(x.w - h3));
+                    lo[4 * c] = __float_as_uint(lo_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(lo_tf32(x.y - h1));
+                    lo[4 * c + 2] = __float_as_uint(lo_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(lo_tf32(x.w - h3));
                 }
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::TMEM_A0 + s * 64);
                 tmem_st32(ta, hi);
@@ -477,7 +482,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const float4 x = braw[i];
                 float4 h, l;
                 h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-                l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+                l.x = lo_tf32(x.x - h.x); l.y = lo_tf32(x.y - h.y); l.z = lo_tf32(x.z - h.z); l.w = lo_tf32(x.w - h.w);
                 bh[i] = h;
                 bl[i] = l;
             }
@@ -729,8 +734,8 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const float h0 = to_tf32(x.x), h1 = to_tf32(x.y), h2 = to_tf32(x.z), h3 = to_tf32(x.w);
                         hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
                         hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
-                        lo[4 * c] = __float_as_uint(to_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(to_tf32(x.y - h1));
-                        lo[4 * c + 2] = __float_as_uint(to_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(to_tf32(x.w - h3));
+                        lo[4 * c] = __float_as_uint(lo_tf32(x.x - h0)); lo[4 * c + 1] = __float_as_uint(lo_tf32(x.y - h1));
+                        lo[4 * c + 2] = __float_as_uint(lo_tf32(x.z - h2)); lo[4 * c + 3] = __float_as_uint(lo_tf32(x.w - h3));
                     }
                     const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::TMEM_A0 + s * 64);
                     tmem_st32(ta, hi);
@@ -744,7 +749,7 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const float4 x = braw[i];
                     float4 h, l;
                     h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-                    l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+                    l.x = lo_tf32(x.x - h.x); l.y = lo_tf32(x.y - h.y); l.z = lo_tf32(x.z - h.z); l.w = lo_tf32(x.w - h.w);
                     bh[i] = h;
                     bl[i] = l;
                 }
