@@ -1,27 +1,14 @@
-"""AddKernel: covariance by summing the covariance matrices of a list of kernels
-(mxfusion/components/distributions/gp/kernels/add_kernel.py:19-88).  Each sub-kernel's matrix comes from its own CUDA path
-(stationary: mxf_kbuild_fwd, linear: mxf_gemm); the combination is one elementwise pass."""
-from .kernel import CombinationKernel
+"""Sum of kernels (mxfusion/components/distributions/gp/kernels/add_kernel.py:19-88): nested sums are flattened."""
+import operator
+
+from .kernel import _FoldKernel
 
 
-class AddKernel(CombinationKernel):
+class AddKernel(_FoldKernel):
+    OP = staticmethod(operator.add)
+
     def __init__(self, sub_kernels, name='add', dtype=None, ctx=None):
-        kernels = []
-        for k in sub_kernels:
-            if isinstance(k, AddKernel):
-                kernels.extend(k.sub_kernels)        # flatten nested combinations of the same kind
-            else:
-                kernels.append(k)
-        super(AddKernel, self).__init__(sub_kernels=kernels, name=name, dtype=dtype, ctx=ctx)
+        super(AddKernel, self).__init__(sub_kernels, name=name, dtype=dtype, ctx=ctx)
 
-    def _compute_K(self, F, X, X2=None, **kernel_params):
-        K = self.sub_kernels[0].K(F=F, X=X, X2=X2, **kernel_params)
-        for k in self.sub_kernels[1:]:
-            K = K + k.K(F=F, X=X, X2=X2, **kernel_params)
-        return K
 
-    def _compute_Kdiag(self, F, X, **kernel_params):
-        K = self.sub_kernels[0].Kdiag(F=F, X=X, **kernel_params)
-        for k in self.sub_kernels[1:]:
-            K = K + k.Kdiag(F=F, X=X, **kernel_params)
-        return K
+AddKernel.FLATTEN = (AddKernel,)

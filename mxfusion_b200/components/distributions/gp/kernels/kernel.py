@@ -184,3 +184,27 @@ class CombinationKernel(Kernel):
             rep.__dict__[k.name] = k
         rep.active_dims = copy(self.active_dims)
         return rep
+
+
+class _FoldKernel(CombinationKernel):
+    """Combination by folding a binary operator over the sub-kernels' covariance matrices / diagonals.  Each sub-kernel's
+    matrix comes from its own CUDA path (stationary: mxf_kbuild_fwd, linear: mxf_gemm); the fold is one elementwise pass
+    per operand.  `FLATTEN` names the classes whose sub-kernels are absorbed at construction."""
+    OP = None
+    FLATTEN = ()
+
+    def __init__(self, sub_kernels, name, dtype=None, ctx=None):
+        flat = []
+        for k in sub_kernels:
+            flat.extend(k.sub_kernels if isinstance(k, self.FLATTEN) else [k])
+        super(_FoldKernel, self).__init__(sub_kernels=flat, name=name, dtype=dtype, ctx=ctx)
+
+    def _fold(self, parts):
+        from functools import reduce
+        return reduce(type(self).OP, parts)
+
+    def _compute_K(self, F, X, X2=None, **kernel_params):
+        return self._fold([k.K(F=F, X=X, X2=X2, **kernel_params) for k in self.sub_kernels])
+
+    def _compute_Kdiag(self, F, X, **kernel_params):
+        return self._fold([k.Kdiag(F=F, X=X, **kernel_params) for k in self.sub_kernels])
