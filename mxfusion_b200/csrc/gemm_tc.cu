@@ -59,6 +59,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tma
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Start fetching a TMA descriptor (kernel parameter space) while the CTA is still initialising barriers / allocating TMEM.
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -148,6 +152,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int k_end = (tri & 2) ? min(k, m0 + TC_BM) : k;
     const int kb_end = (k_end + TC_BK - 1) / TC_BK;
 
+    if (threadIdx.x == 32) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(bar_full(s), 1);
@@ -371,6 +379,10 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int k_end = (tri & 2) ? min(k, m0 + TC_BM) : k;
     const int kb_end = (k_end + TC_BK - 1) / TC_BK;
 
+    if (threadIdx.x == 32) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::R; ++s) {
             mbar_init(bar_full(s), 1);
@@ -586,6 +598,10 @@ gemm_tc_pe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         reinterpret_cast<volatile uint32_t*>(base_ptr + Cfg::BARS0 + 8 * (2 * Cfg::R + 2 * Cfg::C + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 32) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::R; ++s) {
             mbar_init(bar_full(s), 1);
