@@ -951,7 +951,8 @@ int gemm_tc_f32(int transA, int transB, int m, int n, int k, double alpha, const
     const int batchA = (S > 1 && sA != 0) ? 1 : 0, batchB = (S > 1 && sB != 0) ? 1 : 0;
     // tile width: 64-wide tiles when 128-wide ones would leave most SMs idle
     const int64_t tiles128 = (int64_t)cdiv(n, 128) * cdiv(m, TC_BM) * S;
-    const bool bn64 = !wide && tiles128 < 100;   // `wide`: C aliases A (in-place panel), one CTA must own full rows
+    static const int bn64_max = [] { const char* e = getenv("MXF_GEMM_BN64_MAX"); return e ? atoi(e) : 100; }();
+    const bool bn64 = !wide && tiles128 < bn64_max;   // `wide`: C aliases A (in-place panel), one CTA must own full rows
     // 256-wide tiles halve the A-operand traffic per flop (the kernel is shared-memory-bandwidth bound): worth it once
     // they still fill the machine
     static const int bn256_min = [] { const char* e = getenv("MXF_GEMM_BN256_MIN"); return e ? atoi(e) : 120; }();
