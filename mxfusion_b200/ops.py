@@ -587,6 +587,7 @@ def mlp_tanh(x, weights, biases):
 # --------------------------------------------------------------------------------------------------
 # variational sparse GP (Titsias collapsed bound): streamed whitened statistics
 # --------------------------------------------------------------------------------------------------
+STATS_KEEP_BYTES = 16 << 30     # keep L^-1 K(Z, X) for the adjoint when it is at most this large
 STATS_CHUNK_ROWS = 28672     # upper bound on the rows of X per streamed block: K(Z, X_c) is M x 28k (~115 MB at M = 1024)
 
 
@@ -631,9 +632,15 @@ class _WhitenedStats(torch.autograd.Function):
         b = torch.zeros((S, M, P), dtype=X.dtype, device=X.device)
         G = _syrk_splits(M) if S == 1 else 1
         parts = torch.zeros((G, M, M), dtype=X.dtype, device=X.device) if G > 1 else None
+        # 180 GB of HBM: when the whitened matrix L^-1 K(Z, X) fits a budget (4.1 GB at N=1e6, M=1024) its blocks are kept
+        # for the adjoint, which then skips the K-build + solve recomputation of every block
+        keep = any(ctx.needs_input_grad) and S * M * N * X.element_size() <= STATS_KEEP_BYTES
+        kept = [] if keep else None
         for c0 in range(0, N, chunk):
             Xc, Yc = X[:, c0:c0 + chunk], Y[:, c0:c0 + chunk]
             A = R.trsm_solve(L, pack, R.kbuild_fwd(kind, Z, Xc, ls, var))       # :77, :81 on this block
+            if kept is not None:
+                kept.append(A)
             Bc = A.shape[2]
             if G > 1 and Bc % (4 * G) == 0 and A.is_contiguous():
                 # :84 syrk(LinvKuf): M x M x Bc has too few output tiles for 148 SMs -> split the K axis into G slabs
@@ -646,6 +653,7 @@ class _WhitenedStats(torch.autograd.Function):
             R.gemm(A, Yc.contiguous(), beta=1.0, C=b)                           # :90 gemm2(LinvKuf, Y)
         Phi = R.copy_ltu(Phi)
         ctx.kind, ctx.chunk = kind, chunk
+        ctx.kept = kept
         ctx.save_for_backward(X, Y, Z, ls, var, L, pack, Phi, b)
         return Phi, b
 
@@ -661,7 +669,10 @@ class _WhitenedStats(torch.autograd.Function):
         dZ = dls = dvar = None
         for c0 in range(0, N, chunk):
             Xc, Yc = X[:, c0:c0 + chunk], Y[:, c0:c0 + chunk].contiguous()
-            A = R.trsm_solve(L, pack, R.kbuild_fwd(kind=ctx.kind, X=Z, X2=Xc, ls=ls, var=var))
+            if ctx.kept is not None:
+                A = ctx.kept[c0 // chunk]
+            else:
+                A = R.trsm_solve(L, pack, R.kbuild_fwd(kind=ctx.kind, X=Z, X2=Xc, ls=ls, var=var))
             Abar = R.gemm(G, A)
             R.gemm(gb, Yc, transB=True, beta=1.0, C=Abar)
             Kbar = R.trsm_solve(L, pack, Abar, transpose=True)
