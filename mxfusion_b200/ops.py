@@ -667,15 +667,17 @@ class _WhitenedStats(torch.autograd.Function):
         dX = torch.empty_like(X) if need[2] else None
         dY = torch.empty_like(Y) if need[3] else None
         dZ = dls = dvar = None
+        # the solve with L^T is applied once to the M x M / M x P factors instead of to every M x B_c block
+        Gp = R.trsm_solve(L, pack, G.clone(), transpose=True)
+        gbp = R.trsm_solve(L, pack, gb.clone(), transpose=True)
         for c0 in range(0, N, chunk):
             Xc, Yc = X[:, c0:c0 + chunk], Y[:, c0:c0 + chunk].contiguous()
             if ctx.kept is not None:
                 A = ctx.kept[c0 // chunk]
             else:
                 A = R.trsm_solve(L, pack, R.kbuild_fwd(kind=ctx.kind, X=Z, X2=Xc, ls=ls, var=var))
-            Abar = R.gemm(G, A)
-            R.gemm(gb, Yc, transB=True, beta=1.0, C=Abar)
-            Kbar = R.trsm_solve(L, pack, Abar, transpose=True)
+            Kbar = R.gemm(Gp, A)                                                # L^-T (G A + bbar Y^T), re-associated:
+            R.gemm(gbp, Yc, transB=True, beta=1.0, C=Kbar)                      # (L^-T G) A + (L^-T bbar) Y^T
             dZc, dXc, dlsc, dvarc = R.kbuild_bwd(ctx.kind, Z, Xc, ls, var, Kbar, need_dX=True, need_dX2=need[2])
             dZ = dZc if dZ is None else dZ + dZc
             dls = dlsc if dls is None else dls + dlsc
