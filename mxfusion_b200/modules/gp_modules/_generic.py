@@ -19,10 +19,12 @@ def _eye(M, like):
 def svgp_log_pdf(F, kern, kern_params, X, Y, Z, noise_var, mu, S_W, S_diag, jitter, log_pdf_scaling, mean=None):
     """svgp_regression.py:61-109 (homoscedastic noise)."""
     D, M = Y.shape[-1], Z.shape[-2]
-    if noise_var.dim() != 2 or noise_var.shape[-1] != 1:
-        raise NotImplementedError("heteroscedastic noise_var of shape (N, P) (svgp_regression.py:61-67)")
-    noise_var = noise_var.unsqueeze(-2)                                  # :61-62
-    beta_sum = D * torch.sum(1 / noise_var, dim=-1)                      # :64-67
+    if noise_var.dim() == 2:                                             # :61-62 (heteroscedastic noise has ndim 3)
+        noise_var = noise_var.unsqueeze(-2)
+    if noise_var.shape[-1] == 1:                                         # :64-67
+        beta_sum = D * torch.sum(1 / noise_var, dim=-1)
+    else:
+        beta_sum = torch.sum(1 / noise_var, dim=-1)
     Kuu = kern.K(F, Z, **kern_params)                                    # :69
     if jitter > 0.:
         Kuu = Kuu + _eye(M, Z) * jitter                                  # :70-72

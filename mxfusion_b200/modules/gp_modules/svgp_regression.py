@@ -39,7 +39,8 @@ class SVGPRegressionLogPdf(VariationalInference):
         S_diag = variables[self.posterior.qU_cov_diag]
         kern = self.model.kernel
         mean = variables[self.model.mean] if self.model.has_mean else None
-        if getattr(kern, 'KIND', None) is None:          # Add / Multiply / Linear / static kernels: primitive-by-primitive
+        if getattr(kern, 'KIND', None) is None or noise_var.dim() == 3:     # combination kernels, or per-point noise
+            # (svgp_regression.py:61-67: noise_var of shape (N, 1|P)): primitive-by-primitive
             from . import _generic
             return _generic.svgp_log_pdf(F, kern, kern.fetch_parameters(variables), X, Y, Z, noise_var, mu, S_W,
                                          S_diag, self.jitter, self.log_pdf_scaling, mean=mean)

@@ -535,6 +535,47 @@ def golden_gp_distributions():
     save('gp_distributions', **out)
 
 
+# ------------------------------------------------------------------------------------------------ heteroscedastic SVGP
+def golden_svgp_hetero():
+    """svgp_regression.py:61-67: noise_var with one value per data point, shape (N, 1) and (N, P)."""
+    out = {}
+    for i, (P, cols, seed) in enumerate([(1, 1, 0), (2, 1, 1), (2, 2, 2)]):
+        np.random.seed(seed)
+        N, M, Din = 11, 4, 3
+        X, Y, Z = np.random.rand(N, Din), np.random.rand(N, P), np.random.rand(M, Din)
+        qU_mean, qU_cov_W, qU_cov_diag = np.random.rand(M, P), np.random.rand(M, M), np.random.rand(M,)
+        noise_var = np.random.rand(N, cols) + 0.1
+        lengthscale, variance = np.random.rand(Din) + 0.3, np.random.rand(1) + 0.3
+        m = Model()
+        m.N = Variable()
+        m.X = Variable(shape=(m.N, Din))
+        m.Z = Variable(shape=(M, Din), initial_value=nd(Z))
+        m.noise_var = Variable(shape=(N, cols), transformation=PositiveTransformation(), initial_value=nd(noise_var))
+        kernel = RBF(input_dim=Din, ARD=True, variance=nd(variance), lengthscale=nd(lengthscale), dtype=DT)
+        m.Y = SVGPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                             shape=(m.N, P), dtype=DT)
+        gp = m.Y.factor
+        gp.svgp_log_pdf.jitter = 1e-8
+        infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), dtype=DT)
+        infr.initialize(X=X.shape, Y=Y.shape)
+        post = gp._extra_graphs[0]
+        infr.params[post.qU_mean] = nd(qU_mean)
+        infr.params[post.qU_cov_W] = nd(qU_cov_W)
+        infr.params[post.qU_cov_diag] = nd(qU_cov_diag)
+        executor = infr.create_executor()
+        with mx.autograd.record():
+            loss, loss_g = executor(mx.nd.zeros(1), nd(X), nd(Y))
+            loss_g.backward()
+        g = grads_of(infr, dict(Z=m.Z, noise_var=m.noise_var, qU_mean=post.qU_mean, qU_cov_W=post.qU_cov_W,
+                                qU_cov_diag=post.qU_cov_diag, lengthscale=kernel.lengthscale, variance=kernel.variance))
+        r = dict(X=X, Y=Y, Z=Z, qU_mean=qU_mean, qU_cov_W=qU_cov_W, qU_cov_diag=qU_cov_diag, noise_var=noise_var,
+                 lengthscale=lengthscale, variance=variance, loss=loss.asnumpy(), **{'grad_' + k: v for k, v in g.items()})
+        for k, v in r.items():
+            out['case%d_%s' % (i, k)] = v
+    out['n_cases'] = 3
+    save('svgp_hetero', **out)
+
+
 if __name__ == '__main__':
     golden_kernels()
     golden_svgp()
@@ -545,6 +586,7 @@ if __name__ == '__main__':
     golden_svi()
     golden_predict()
     golden_sparsegp()
+    golden_svgp_hetero()
     golden_gp_distributions()
     golden_combo_kernels()
     golden_combo_modules()

@@ -344,3 +344,39 @@ def run_gp_distributions(g, device):
         variables1 = {cgp.X.uuid: T(X[:1]), cgp.X_cond.uuid: T(Xc[:1]), cgp.Y_cond.uuid: T(Yc[:1])}
         variables1.update({getattr(cgp, n).uuid: T(v[:1]) for n, v in kp.items()})
         yield 'c%d cgp draw' % i, cgp.draw_samples(F=F, variables=variables1, num_samples=ns).cpu().numpy(), c('cgp_draw')
+
+
+def run_svgp_hetero_case(mf, g, i, device):
+    """Case i of svgp_hetero.npz: SVGP with one noise variance per data point (svgp_regression.py:61-67)."""
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.components.distributions.gp.kernels import RBF
+    from mxfusion_b200.modules.gp_modules import SVGPRegression
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    c = lambda k: g['case%d_%s' % (i, k)]
+    X, Y, Z, noise_var = c('X'), c('Y'), c('Z'), c('noise_var')
+    N, Din = X.shape
+    M, P = Z.shape[0], Y.shape[1]
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, Din))
+    m.Z = mf.Variable(shape=(M, Din), initial_value=Z)
+    m.noise_var = mf.Variable(shape=noise_var.shape, transformation=PositiveTransformation(), initial_value=noise_var)
+    kernel = RBF(input_dim=Din, ARD=True, variance=c('variance'), lengthscale=c('lengthscale'))
+    m.Y = SVGPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                         shape=(m.N, P))
+    gp = m.Y.factor
+    gp.svgp_log_pdf.jitter = 1e-8
+    infr = GradBasedInference(MAP(model=m, observed=[m.X, m.Y]), context=device)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    post = gp._extra_graphs[0]
+    infr.params[post.qU_mean] = c('qU_mean')
+    infr.params[post.qU_cov_W] = c('qU_cov_W')
+    infr.params[post.qU_cov_diag] = c('qU_cov_diag')
+    infr.params.gflat.zero_()
+    loss, loss_g = infr.create_executor()(None, torch.tensor(X, device=device), torch.tensor(Y, device=device))
+    loss_g.backward()
+    grads = dict(Z=param_grad(infr, m.Z), noise_var=param_grad(infr, m.noise_var),
+                 qU_mean=param_grad(infr, post.qU_mean), qU_cov_W=param_grad(infr, post.qU_cov_W),
+                 qU_cov_diag=param_grad(infr, post.qU_cov_diag), lengthscale=param_grad(infr, kernel.lengthscale),
+                 variance=param_grad(infr, kernel.variance))
+    return float(loss), grads

@@ -278,3 +278,14 @@ def test_product_gp_distributions_match_reference(mf):
     K = ok.K(0, g['c0_X'], g['c0_ls'], g['c0_var'])[0]
     want = scipy.stats.multivariate_normal.logpdf(g['c0_Y'][0, :, 0], mean=None, cov=K)
     np.testing.assert_allclose(g['c0_gp_log_pdf'][0], want, rtol=1e-9)
+
+
+def test_product_svgp_heteroscedastic_noise(mf):
+    """noise_var with one value per data point, shapes (N, 1) and (N, P) (svgp_regression.py:61-67), against the
+    reference's own run: value and all gradients (primitive-by-primitive path)."""
+    g = gc.load('svgp_hetero')
+    for i in range(int(g['n_cases'])):
+        loss, grads = gc.run_svgp_hetero_case(mf, g, i, torch.device('cpu'))
+        np.testing.assert_allclose(loss, float(g['case%d_loss' % i]), rtol=1e-10, err_msg='case %d' % i)
+        for k, v in grads.items():
+            np.testing.assert_allclose(v, g['case%d_grad_%s' % (i, k)], rtol=1e-6, atol=1e-8, err_msg='case %d %s' % (i, k))
