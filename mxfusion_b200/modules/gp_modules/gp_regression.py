@@ -60,30 +60,71 @@ class GPRegressionMeanVariancePrediction(SamplingAlgorithm):
         self.diagonal_variance = diagonal_variance
 
     def compute(self, F, variables):
-        X = variables[self.model.X]
-        N = X.shape[-2]
-        noise_var = variables[self.model.noise_var]
-        X_cond = variables[self.graphs[1].X]
-        L = variables[self.graphs[1].L]
-        LinvY = variables[self.graphs[1].LinvY]
-        kern = self.model.kernel
-        kern_params = kern.fetch_parameters(variables)
-        X, noise_var, X_cond, L, LinvY, kern_params = arrays_as_samples(
-            F, [X, noise_var, X_cond, L, LinvY, kern_params])
-        Kxt = kern.K(F, X_cond, X, **kern_params)
-        LinvKxt = ops.trsm(L, Kxt)
-        mu = ops.gemm2(LinvKxt, LinvY, True, False)
-        if self.model.has_mean:
-            mu = mu + variables[self.model.mean]
-        if self.diagonal_variance:
-            var = kern.Kdiag(F, X, **kern_params) - torch.sum(torch.square(LinvKxt), dim=-2)
-            if not self.noise_free:
-                var = var + noise_var
-        else:
-            var = kern.K(F, X, **kern_params) - ops.syrk(LinvKxt, True)
-            if not self.noise_free:
-                var = var + torch.eye(N, dtype=X.dtype, device=X.device).unsqueeze(0) * noise_var.unsqueeze(-2)
-        outcomes = {self.model.Y.uuid: (mu, var)}
+        outcomes = {self.model.Y.uuid: _gp_predict_moments(self, F, variables)}
+        if self.target_variables:
+            return tuple(outcomes[v] for v in self.target_variables)
+        return outcomes
+
+
+def _gp_predict_moments(alg, F, variables):
+    """Predictive mean and (diagonal or full) covariance (gp_regression.py:158-190 / :225-259)."""
+    X = variables[alg.model.X]
+    N = X.shape[-2]
+    noise_var = variables[alg.model.noise_var]
+    X_cond = variables[alg.graphs[1].X]
+    L = variables[alg.graphs[1].L]
+    LinvY = variables[alg.graphs[1].LinvY]
+    kern = alg.model.kernel
+    kern_params = kern.fetch_parameters(variables)
+    X, noise_var, X_cond, L, LinvY, kern_params = arrays_as_samples(
+        F, [X, noise_var, X_cond, L, LinvY, kern_params])
+    Kxt = kern.K(F, X_cond, X, **kern_params)
+    LinvKxt = ops.trsm(L, Kxt)
+    mu = ops.gemm2(LinvKxt, LinvY, True, False)
+    if alg.model.has_mean:
+        mu = mu + variables[alg.model.mean]
+    if alg.diagonal_variance:
+        var = kern.Kdiag(F, X, **kern_params) - torch.sum(torch.square(LinvKxt), dim=-2)
+        if not alg.noise_free:
+            var = var + noise_var
+    else:
+        var = kern.K(F, X, **kern_params) - ops.syrk(LinvKxt, True)
+        if not alg.noise_free:
+            var = var + torch.eye(N, dtype=X.dtype, device=X.device).unsqueeze(0) * noise_var.unsqueeze(-2)
+    return mu, var
+
+
+def _draw_from_moments(alg, mu, var):
+    """Samples from N(mu, var) (independent per point, or through the Cholesky factor of the full covariance):
+    gp_regression.py:246-268."""
+    from ...components.distributions.random_gen import MXNetRandomGenerator
+    gen = alg._rand_gen if alg._rand_gen is not None else MXNetRandomGenerator
+    out_shape = (alg.num_samples,) + tuple(mu.shape[1:])
+    die = gen.sample_normal(shape=out_shape, dtype=mu.dtype, ctx=mu.device)
+    if alg.diagonal_variance:
+        return mu + die * torch.sqrt(var.unsqueeze(-1))
+    cov = var
+    if getattr(alg, 'jitter', 0.) > 0.:
+        n = cov.shape[-1]
+        cov = cov + torch.eye(n, dtype=cov.dtype, device=cov.device) * alg.jitter
+    Lc = ops.potrf(cov)
+    return mu + ops.gemm2(Lc.expand((alg.num_samples,) + tuple(Lc.shape[1:])), die)
+
+
+class GPRegressionSamplingPrediction(SamplingAlgorithm):
+    """gp_regression.py:199-275: draws from the predictive distribution."""
+
+    def __init__(self, model, posterior, observed, rand_gen=None, noise_free=True, diagonal_variance=True, jitter=0.):
+        super(GPRegressionSamplingPrediction, self).__init__(model=model, observed=observed,
+                                                             extra_graphs=[posterior])
+        self.noise_free = noise_free
+        self.diagonal_variance = diagonal_variance
+        self._rand_gen = rand_gen
+        self.jitter = jitter
+
+    def compute(self, F, variables):
+        mu, var = _gp_predict_moments(self, F, variables)
+        outcomes = {self.model.Y.uuid: _draw_from_moments(self, mu, var)}
         if self.target_variables:
             return tuple(outcomes[v] for v in self.target_variables)
         return outcomes

@@ -61,49 +61,81 @@ class SVGPRegressionMeanVariancePrediction(SamplingAlgorithm):
         self.diagonal_variance = diagonal_variance
 
     def compute(self, F, variables):
-        X = variables[self.model.X]
-        N = X.shape[-2]
-        Z = variables[self.model.inducing_inputs]
-        noise_var = variables[self.model.noise_var]
-        mu = variables[self.graphs[1].qU_mean]
-        S_W = variables[self.graphs[1].qU_cov_W]
-        S_diag = variables[self.graphs[1].qU_cov_diag]
-        kern = self.model.kernel
-        kern_params = kern.fetch_parameters(variables)
-        kp = kern._strip(kern_params) if getattr(kern, 'KIND', None) is not None else None
-        S = ops.syrk(S_W) + ops.make_diagonal(S_diag)
-        if getattr(kern, 'KIND', None) is None:
-            Kuu = kern.K(F, Z, **kern_params)
-            if self.jitter > 0.:
-                Kuu = Kuu + torch.eye(Z.shape[-2], dtype=Z.dtype, device=Z.device).unsqueeze(0) * self.jitter
-        else:
-            (Zs,) = _active(F, kern, Z)
-            Kuu = ops.kernel_matrix(kern.KIND, Zs, None, kp['lengthscale'], kp['variance'], diag_const=self.jitter)
-        L = ops.potrf(Kuu)
-        Ls = ops.potrf(S)
-        LinvLs = ops.trsm(L, Ls)
-        Linvmu = ops.trsm(L, mu)
-        LinvSLinvT = ops.syrk(LinvLs)
-        wv = ops.trsm(L, Linvmu, transpose=True)
-        Kxt = kern.K(F, Z, X, **kern_params)
-        mean_f = ops.gemm2(Kxt, wv, True, False)
-        if self.model.has_mean:
-            mean_f = mean_f + variables[self.model.mean]
-        LinvKxt = ops.trsm(L, Kxt)
-        tmp = ops.gemm2(LinvSLinvT, LinvKxt)
-        if self.diagonal_variance:
-            var = kern.Kdiag(F, X, **kern_params) - torch.sum(torch.square(LinvKxt), dim=-2) + \
-                torch.sum(tmp * LinvKxt, dim=-2)
-            var = var.unsqueeze(-1)
-            if not self.noise_free:
-                var = var + noise_var
-        else:
-            var = kern.K(F, X, **kern_params) - ops.syrk(LinvKxt, True) + ops.gemm2(LinvKxt, tmp, True, False)
-            var = var.unsqueeze(-1)
-            if not self.noise_free:
-                var = var + torch.eye(N, dtype=X.dtype, device=X.device).reshape(1, N, N, 1) * \
-                    noise_var.unsqueeze(-2)
-        outcomes = {self.model.Y.uuid: (mean_f, var)}
+        outcomes = {self.model.Y.uuid: _svgp_predict_moments(self, F, variables)}
+        if self.target_variables:
+            return tuple(outcomes[v] for v in self.target_variables)
+        return outcomes
+
+
+def _svgp_predict_moments(self, F, variables, squeeze_var=False):
+    """Predictive mean and (diagonal or full) covariance (svgp_regression.py:145-182 / :216-266)."""
+    X = variables[self.model.X]
+    N = X.shape[-2]
+    Z = variables[self.model.inducing_inputs]
+    noise_var = variables[self.model.noise_var]
+    mu = variables[self.graphs[1].qU_mean]
+    S_W = variables[self.graphs[1].qU_cov_W]
+    S_diag = variables[self.graphs[1].qU_cov_diag]
+    kern = self.model.kernel
+    kern_params = kern.fetch_parameters(variables)
+    kp = kern._strip(kern_params) if getattr(kern, 'KIND', None) is not None else None
+    S = ops.syrk(S_W) + ops.make_diagonal(S_diag)
+    if getattr(kern, 'KIND', None) is None:
+        Kuu = kern.K(F, Z, **kern_params)
+        if self.jitter > 0.:
+            Kuu = Kuu + torch.eye(Z.shape[-2], dtype=Z.dtype, device=Z.device).unsqueeze(0) * self.jitter
+    else:
+        (Zs,) = _active(F, kern, Z)
+        Kuu = ops.kernel_matrix(kern.KIND, Zs, None, kp['lengthscale'], kp['variance'], diag_const=self.jitter)
+    L = ops.potrf(Kuu)
+    Ls = ops.potrf(S)
+    LinvLs = ops.trsm(L, Ls)
+    Linvmu = ops.trsm(L, mu)
+    LinvSLinvT = ops.syrk(LinvLs)
+    wv = ops.trsm(L, Linvmu, transpose=True)
+    Kxt = kern.K(F, Z, X, **kern_params)
+    mean_f = ops.gemm2(Kxt, wv, True, False)
+    if self.model.has_mean:
+        mean_f = mean_f + variables[self.model.mean]
+    LinvKxt = ops.trsm(L, Kxt)
+    tmp = ops.gemm2(LinvSLinvT, LinvKxt)
+    if self.diagonal_variance:
+        var = kern.Kdiag(F, X, **kern_params) - torch.sum(torch.square(LinvKxt), dim=-2) + \
+            torch.sum(tmp * LinvKxt, dim=-2)
+        var = var.unsqueeze(-1)
+        if not self.noise_free:
+            var = var + noise_var
+    else:
+        var = kern.K(F, X, **kern_params) - ops.syrk(LinvKxt, True) + ops.gemm2(LinvKxt, tmp, True, False)
+        var = var.unsqueeze(-1)
+        if not self.noise_free:
+            var = var + torch.eye(N, dtype=X.dtype, device=X.device).reshape(1, N, N, 1) * \
+                noise_var.unsqueeze(-2)
+    if squeeze_var:
+        var = var.squeeze(-1)
+    return mean_f, var
+
+
+class SVGPRegressionSamplingPrediction(SamplingAlgorithm):
+    """svgp_regression.py:192-280: draws from the predictive distribution."""
+
+    def __init__(self, model, posterior, observed, rand_gen=None, noise_free=True, diagonal_variance=True, jitter=0.):
+        super(SVGPRegressionSamplingPrediction, self).__init__(model=model, observed=observed,
+                                                               extra_graphs=[posterior])
+        self.noise_free = noise_free
+        self.diagonal_variance = diagonal_variance
+        self._rand_gen = rand_gen
+        self.jitter = jitter
+
+    def compute(self, F, variables):
+        from .gp_regression import _draw_from_moments
+        mu, var = _svgp_predict_moments(self, F, variables, squeeze_var=True)
+        jitter, self.jitter = self.jitter, 0.          # :232-234 use the jitter on Kuu only; :267 adds none to cov
+        try:
+            samples = _draw_from_moments(self, mu, var)
+        finally:
+            self.jitter = jitter
+        outcomes = {self.model.Y.uuid: samples}
         if self.target_variables:
             return tuple(outcomes[v] for v in self.target_variables)
         return outcomes

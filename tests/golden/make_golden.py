@@ -576,6 +576,63 @@ def golden_svgp_hetero():
     save('svgp_hetero', **out)
 
 
+# ------------------------------------------------------------------------------------------------ sampling prediction
+def golden_sampling_prediction():
+    """*SamplingPrediction of the three modules (gpregression_test.py:255-307 pattern) with injected standard normals:
+    diagonal and full-covariance draws, noisy and noise-free."""
+    from mxfusion.modules.gp_modules.gp_regression import GPRegressionSamplingPrediction
+    from mxfusion.modules.gp_modules.svgp_regression import SVGPRegressionSamplingPrediction
+    from mxfusion.modules.gp_modules.sparsegp_regression import SparseGPRegressionSamplingPrediction
+    out = {}
+    np.random.seed(3)
+    N, M, Din, P, Nt, ns = 10, 3, 3, 2, 6, 4
+    X, Y, Z = np.random.rand(N, Din), np.random.rand(N, P), np.random.rand(M, Din)
+    qU_mean, qU_cov_W, qU_cov_diag = np.random.rand(M, P), np.random.rand(M, M), np.random.rand(M,)
+    noise_var, lengthscale, variance = np.random.rand(1) + 0.1, np.random.rand(Din) + 0.3, np.random.rand(1) + 0.3
+    Xt = np.random.rand(Nt, Din)
+    die = np.random.randn(ns, Nt, P)
+    out.update(X=X, Y=Y, Z=Z, qU_mean=qU_mean, qU_cov_W=qU_cov_W, qU_cov_diag=qU_cov_diag, noise_var=noise_var,
+               lengthscale=lengthscale, variance=variance, Xt=Xt, die=die)
+    for module in ('gp', 'svgp', 'sparsegp'):
+        m = Model()
+        m.N = Variable()
+        m.X = Variable(shape=(m.N, Din))
+        m.noise_var = Variable(transformation=PositiveTransformation(), initial_value=nd(noise_var))
+        kernel = RBF(input_dim=Din, ARD=True, variance=nd(variance), lengthscale=nd(lengthscale), dtype=DT)
+        if module == 'gp':
+            m.Y = GPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, shape=(m.N, P), dtype=DT)
+        else:
+            m.Z = Variable(shape=(M, Din), initial_value=nd(Z))
+            cls = SVGPRegression if module == 'svgp' else SparseGPRegression
+            m.Y = cls.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z,
+                                      shape=(m.N, P), dtype=DT)
+            (m.Y.factor.svgp_log_pdf if module == 'svgp' else m.Y.factor.sgp_log_pdf).jitter = 1e-8
+        gp = m.Y.factor
+        infr = Inference(MAP(model=m, observed=[m.X, m.Y]), dtype=DT)
+        infr.initialize(X=X.shape, Y=Y.shape)
+        if module == 'svgp':
+            post = gp._extra_graphs[0]
+            infr.params[post.qU_mean] = nd(qU_mean)
+            infr.params[post.qU_cov_W] = nd(qU_cov_W)
+            infr.params[post.qU_cov_diag] = nd(qU_cov_diag)
+        infr.run(X=nd(X), Y=nd(Y))
+        cls = {'gp': GPRegressionSamplingPrediction, 'svgp': SVGPRegressionSamplingPrediction,
+               'sparsegp': SparseGPRegressionSamplingPrediction}[module]
+        name = {'gp': 'gp_predict', 'svgp': 'svgp_predict', 'sparsegp': 'sgp_predict'}[module]
+        for noise_free in (True, False):
+            for diag in (True, False):
+                alg = cls(gp._module_graph, gp._extra_graphs[0], [gp._module_graph.X],
+                          rand_gen=MockMXNetRandomGenerator(nd(die.flatten())))
+                alg.noise_free, alg.diagonal_variance, alg.jitter = noise_free, diag, 1e-6
+                gp.attach_prediction_algorithms(targets=gp.output_names, conditionals=gp.input_names, algorithm=alg,
+                                                alg_name=name)
+                infr2 = TransferInference(ModulePredictionAlgorithm(m, observed=[m.X], target_variables=[m.Y],
+                                                                    num_samples=ns),
+                                          infr_params=infr.params, dtype=np.float64)
+                out['%s_nf%d_diag%d' % (module, int(noise_free), int(diag))] = infr2.run(X=nd(Xt))[0].asnumpy()
+    save('sampling_prediction', **out)
+
+
 if __name__ == '__main__':
     golden_kernels()
     golden_svgp()
@@ -587,6 +644,7 @@ if __name__ == '__main__':
     golden_predict()
     golden_sparsegp()
     golden_svgp_hetero()
+    golden_sampling_prediction()
     golden_gp_distributions()
     golden_combo_kernels()
     golden_combo_modules()

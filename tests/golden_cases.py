@@ -380,3 +380,55 @@ def run_svgp_hetero_case(mf, g, i, device):
                  qU_cov_diag=param_grad(infr, post.qU_cov_diag), lengthscale=param_grad(infr, kernel.lengthscale),
                  variance=param_grad(infr, kernel.variance))
     return float(loss), grads
+
+
+def run_sampling_prediction(mf, g, module, device):
+    """Rebuilds the sampling-prediction scenario of sampling_prediction.npz; returns {(noise_free, diag): samples}."""
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.components.distributions import MockMXNetRandomGenerator
+    from mxfusion_b200.components.distributions.gp.kernels import RBF
+    from mxfusion_b200.modules.gp_modules import (GPRegression, SVGPRegression, SparseGPRegression,
+                                                  GPRegressionSamplingPrediction, SVGPRegressionSamplingPrediction,
+                                                  SparseGPRegressionSamplingPrediction)
+    from mxfusion_b200.inference import Inference, MAP, TransferInference, ModulePredictionAlgorithm
+    X, Y, Z, Xt, die = g['X'], g['Y'], g['Z'], g['Xt'], g['die']
+    N, Din = X.shape
+    M, P, ns = Z.shape[0], Y.shape[1], die.shape[0]
+    m = mf.Model()
+    m.N = mf.Variable()
+    m.X = mf.Variable(shape=(m.N, Din))
+    m.noise_var = mf.Variable(transformation=PositiveTransformation(), initial_value=g['noise_var'])
+    kernel = RBF(input_dim=Din, ARD=True, variance=g['variance'], lengthscale=g['lengthscale'])
+    if module == 'gp':
+        m.Y = GPRegression.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, shape=(m.N, P))
+    else:
+        m.Z = mf.Variable(shape=(M, Din), initial_value=Z)
+        cls = SVGPRegression if module == 'svgp' else SparseGPRegression
+        m.Y = cls.define_variable(X=m.X, kernel=kernel, noise_var=m.noise_var, inducing_inputs=m.Z, shape=(m.N, P))
+        (m.Y.factor.svgp_log_pdf if module == 'svgp' else m.Y.factor.sgp_log_pdf).jitter = 1e-8
+    gp = m.Y.factor
+    infr = Inference(MAP(model=m, observed=[m.X, m.Y]), context=device)
+    infr.initialize(X=X.shape, Y=Y.shape)
+    if module == 'svgp':
+        post = gp._extra_graphs[0]
+        infr.params[post.qU_mean] = g['qU_mean']
+        infr.params[post.qU_cov_W] = g['qU_cov_W']
+        infr.params[post.qU_cov_diag] = g['qU_cov_diag']
+    infr.run(X=X, Y=Y)
+    cls = {'gp': GPRegressionSamplingPrediction, 'svgp': SVGPRegressionSamplingPrediction,
+           'sparsegp': SparseGPRegressionSamplingPrediction}[module]
+    name = {'gp': 'gp_predict', 'svgp': 'svgp_predict', 'sparsegp': 'sgp_predict'}[module]
+    out = {}
+    for noise_free in (True, False):
+        for diag in (True, False):
+            alg = cls(gp._module_graph, gp._extra_graphs[0], [gp._module_graph.X],
+                      rand_gen=MockMXNetRandomGenerator(torch.tensor(die.flatten(), device=device)))
+            alg.noise_free, alg.diagonal_variance, alg.jitter = noise_free, diag, 1e-6
+            gp.attach_prediction_algorithms(targets=gp.output_names, conditionals=gp.input_names, algorithm=alg,
+                                            alg_name=name)
+            infr2 = TransferInference(ModulePredictionAlgorithm(m, observed=[m.X], target_variables=[m.Y],
+                                                                num_samples=ns),
+                                      infr_params=infr.params, context=device)
+            with torch.no_grad():
+                out[(noise_free, diag)] = infr2.run(X=Xt)[0].cpu().numpy()
+    return out

@@ -289,3 +289,13 @@ def test_product_svgp_heteroscedastic_noise(mf):
         np.testing.assert_allclose(loss, float(g['case%d_loss' % i]), rtol=1e-10, err_msg='case %d' % i)
         for k, v in grads.items():
             np.testing.assert_allclose(v, g['case%d_grad_%s' % (i, k)], rtol=1e-6, atol=1e-8, err_msg='case %d %s' % (i, k))
+
+
+@pytest.mark.parametrize('module', ['gp', 'svgp', 'sparsegp'])
+def test_product_sampling_prediction_matches_reference(mf, module):
+    """*SamplingPrediction of the three GP modules with injected standard normals, four modes each."""
+    g = gc.load('sampling_prediction')
+    got = gc.run_sampling_prediction(mf, g, module, torch.device('cpu'))
+    for (nf, dg), samples in got.items():
+        t = '%s_nf%d_diag%d' % (module, int(nf), int(dg))
+        np.testing.assert_allclose(samples, g[t], rtol=1e-8, atol=1e-10, err_msg=t)
