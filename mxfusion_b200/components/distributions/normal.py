@@ -10,6 +10,16 @@ from ..variables.runtime_variable import arrays_as_samples
 from ... import ops
 
 
+def _to_rv_shape(t, rv_shape):
+    """Broadcast everything after the sample axis to the random variable's shape (NumPy rules: trailing dimensions are
+    aligned, e.g. a (S, 1) mean against a (N, 1) variable)."""
+    rv_shape = tuple(rv_shape)
+    if tuple(t.shape[1:]) == rv_shape:
+        return t
+    t = t.reshape((t.shape[0],) + (1,) * (len(rv_shape) - (t.dim() - 1)) + tuple(t.shape[1:]))
+    return t.expand((t.shape[0],) + rv_shape)
+
+
 class Normal(Distribution):
     def __init__(self, mean, variance, rand_gen=None, dtype=None, ctx=None):
         inputs = [('mean', mean), ('variance', variance)]
@@ -61,18 +71,12 @@ class Normal(Distribution):
         kw = arrays_as_samples(F, self.fetch_runtime_inputs(variables))
         mean, variance = kw['mean'], kw['variance']
         rv_shape = self._realized_shape(variables)
-        if tuple(mean.shape[1:]) != tuple(rv_shape):
-            mean = mean.expand((mean.shape[0],) + tuple(rv_shape))
-        if tuple(variance.shape[1:]) != tuple(rv_shape):
-            variance = variance.expand((variance.shape[0],) + tuple(rv_shape))
-        return mean, variance, num_samples, gen.next_stream()
+        return _to_rv_shape(mean, rv_shape), _to_rv_shape(variance, rv_shape), num_samples, gen.next_stream()
 
     def draw_samples_impl(self, mean, variance, rv_shape, num_samples=1, F=None):
         """normal.py:72-92: eps * sqrt(variance) + mean with eps ~ N(0,1) of shape (S,) + rv_shape."""
         full = (num_samples,) + tuple(rv_shape)
-        mean = mean.expand((mean.shape[0],) + tuple(rv_shape)) if tuple(mean.shape[1:]) != tuple(rv_shape) else mean
-        variance = variance.expand((variance.shape[0],) + tuple(rv_shape)) \
-            if tuple(variance.shape[1:]) != tuple(rv_shape) else variance
+        mean, variance = _to_rv_shape(mean, rv_shape), _to_rv_shape(variance, rv_shape)
         gen = self._rand_gen
         if getattr(gen, 'in_kernel', False):
             from .random_gen import step_counter

@@ -9,4 +9,5 @@ from .minibatch_loop import MinibatchInferenceLoop, RolloverBatchSampler  # noqa
 from .inference import Inference, TransferInference  # noqa: F401
 from .grad_based_inference import GradBasedInference  # noqa: F401
 from .prediction import ModulePredictionAlgorithm  # noqa: F401
-from .forward_sampling import ForwardSamplingAlgorithm, ForwardSampling  # noqa: F401
+from .forward_sampling import (ForwardSamplingAlgorithm, ForwardSampling,  # noqa: F401
+                               VariationalPosteriorForwardSampling, VariationalPosteriorForwardSamplingAlgorithm)

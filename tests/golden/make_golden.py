@@ -633,6 +633,34 @@ def golden_sampling_prediction():
     save('sampling_prediction', **out)
 
 
+# ------------------------------------------------------------------------------------------------ posterior forward sampling
+def golden_vpfs():
+    """VariationalPosteriorForwardSampling (forward_sampling.py:99-157) on the conjugate toy model of `svi`: the latent
+    mean is drawn from q (injected noise), the observation from the model's likelihood given that draw (injected noise)."""
+    from mxfusion.inference import VariationalPosteriorForwardSampling
+    rng = np.random.RandomState(5)
+    N, S = 6, 4
+    y = rng.randn(N, 1)
+    eps_mu, eps_y = rng.randn(S, 1), rng.randn(S, N, 1)
+    m = Model()
+    m.mu = Normal.define_variable(mean=nd([0.]), variance=nd([4.]), shape=(1,), dtype=DT)
+    m.s2 = Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=nd([0.7]))
+    m.y = Normal.define_variable(mean=mxfusion.components.functions.operators.broadcast_to(m.mu, (N, 1)),
+                                 variance=mxfusion.components.functions.operators.broadcast_to(m.s2, (N, 1)),
+                                 shape=(N, 1), dtype=DT, rand_gen=MockMXNetRandomGenerator(nd(eps_y.flatten())))
+    q = create_Gaussian_meanfield(model=m, observed=[m.y], dtype=DT)
+    q.mu.factor._rand_gen = MockMXNetRandomGenerator(nd(eps_mu.flatten()))
+    alg = StochasticVariationalInference(num_samples=S, model=m, posterior=q, observed=[m.y])
+    infr = GradBasedInference(inference_algorithm=alg, dtype=DT)
+    infr.initialize(y=y.shape)
+    infr.params[q.mu.factor.mean] = nd([0.3])
+    infr.params[q.mu.factor.variance] = nd([0.5])
+    infr2 = VariationalPosteriorForwardSampling(S, [], infr, [m.y, m.mu], dtype=np.float64)
+    res = infr2.run()
+    save('vpfs_toy', y=y, eps_mu=eps_mu, eps_y=eps_y, S=S, q_mean=0.3, q_var=0.5, s2=0.7,
+         sample_y=res[0].asnumpy(), sample_mu=res[1].asnumpy())
+
+
 if __name__ == '__main__':
     golden_kernels()
     golden_svgp()
@@ -645,6 +673,7 @@ if __name__ == '__main__':
     golden_sparsegp()
     golden_svgp_hetero()
     golden_sampling_prediction()
+    golden_vpfs()
     golden_gp_distributions()
     golden_combo_kernels()
     golden_combo_modules()

@@ -432,3 +432,30 @@ def run_sampling_prediction(mf, g, module, device):
             with torch.no_grad():
                 out[(noise_free, diag)] = infr2.run(X=Xt)[0].cpu().numpy()
     return out
+
+
+def run_vpfs_toy(mf, g, device):
+    """VariationalPosteriorForwardSampling on the conjugate toy model of vpfs_toy.npz -> (samples of y, samples of mu)."""
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.components.distributions import Normal, MockMXNetRandomGenerator
+    from mxfusion_b200.inference import (GradBasedInference, StochasticVariationalInference, create_Gaussian_meanfield,
+                                         VariationalPosteriorForwardSampling)
+    y = g['y']
+    N, S = y.shape[0], int(g['S'])
+    t = lambda a: torch.tensor(np.atleast_1d(a), dtype=torch.float64)
+    m = mf.Model()
+    m.mu = Normal.define_variable(mean=t(0.), variance=t(4.), shape=(1,))
+    m.s2 = mf.Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=t(g['s2']))
+    m.y = Normal.define_variable(mean=m.mu, variance=m.s2, shape=(N, 1),
+                                 rand_gen=MockMXNetRandomGenerator(torch.tensor(g['eps_y'].flatten(), device=device)))
+    q = create_Gaussian_meanfield(model=m, observed=[m.y])
+    q.mu.factor._rand_gen = MockMXNetRandomGenerator(torch.tensor(g['eps_mu'].flatten(), device=device))
+    alg = StochasticVariationalInference(num_samples=S, model=m, posterior=q, observed=[m.y])
+    infr = GradBasedInference(inference_algorithm=alg, context=device)
+    infr.initialize(y=y.shape)
+    infr.params[q.mu.factor.mean] = t(g['q_mean'])
+    infr.params[q.mu.factor.variance] = t(g['q_var'])
+    infr2 = VariationalPosteriorForwardSampling(S, [], infr, [m.y, m.mu], context=device)
+    with torch.no_grad():
+        res = infr2.run()
+    return res[0].cpu().numpy(), res[1].cpu().numpy()

@@ -299,3 +299,12 @@ def test_product_sampling_prediction_matches_reference(mf, module):
     for (nf, dg), samples in got.items():
         t = '%s_nf%d_diag%d' % (module, int(nf), int(dg))
         np.testing.assert_allclose(samples, g[t], rtol=1e-8, atol=1e-10, err_msg=t)
+
+
+def test_product_variational_posterior_forward_sampling(mf):
+    """Latent drawn from q, observation from the likelihood given that draw (forward_sampling.py:99-157), with injected
+    noise, against the reference's merged-graph implementation."""
+    g = gc.load('vpfs_toy')
+    sy, smu = gc.run_vpfs_toy(mf, g, torch.device('cpu'))
+    np.testing.assert_allclose(smu.reshape(g['sample_mu'].shape), g['sample_mu'], rtol=1e-10)
+    np.testing.assert_allclose(sy.reshape(g['sample_y'].shape), g['sample_y'], rtol=1e-10)
