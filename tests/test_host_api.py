@@ -185,3 +185,31 @@ def test_forward_sampling_draws_from_a_gp_prior(mf):
     K = ok.K(0, X[None], np.array([[0.7]]), np.array([[1.3]]))[0]
     want = np.linalg.cholesky(K) @ die
     np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)
+
+
+def test_inference_save_load_round_trip(mf, tmp_path):
+    """Inference.save / load (inference.py:179-310): one zip with the reference's six members; a freshly built inference
+    of the same topology (different UUIDs) gets the trained values back and reproduces the loss."""
+    import zipfile
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    m, X, Y = gp_notebook_model(mf)
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]))
+    infr.initialize(X=X.shape, Y=Y.shape)
+    infr.run(X=X, Y=Y, max_iter=15, learning_rate=0.05)
+    loss, _ = infr.create_executor()(None, torch.tensor(X), torch.tensor(Y))
+    path = str(tmp_path / 'inference.zip')
+    infr.save(path)
+    with zipfile.ZipFile(path) as zf:
+        names = set(zf.namelist())
+    assert len(names) == 6 and 'version.json' in names          # serialization.py:26-135 archive layout
+    m2, _, _ = gp_notebook_model(mf)
+    infr2 = GradBasedInference(inference_algorithm=MAP(model=m2, observed=[m2.X, m2.Y]))
+    infr2.initialize(X=X.shape, Y=Y.shape)
+    before, _ = infr2.create_executor()(None, torch.tensor(X), torch.tensor(Y))
+    assert abs(float(before) - float(loss)) > 1e-3
+    infr2.load(path)
+    after, _ = infr2.create_executor()(None, torch.tensor(X), torch.tensor(Y))
+    np.testing.assert_allclose(float(after), float(loss), rtol=1e-12)
+    for a, b in ((m.kernel.variance, m2.kernel.variance), (m.kernel.lengthscale, m2.kernel.lengthscale),
+                 (m.noise_var, m2.noise_var)):
+        np.testing.assert_allclose(infr2.params[b].numpy(), infr.params[a].numpy(), rtol=1e-12)
