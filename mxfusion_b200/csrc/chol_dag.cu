@@ -1,0 +1,810 @@
+// Single-launch Cholesky factorisation + triangular inverse for n <= 1024 (f32): a ticketed tile dataflow.
+//
+// linalg.potrf on the M x M matrices of the SVGP bound (svgp_regression.py:83-84) and on the diagonal blocks of the
+// exact-GP covariance (gp_regression.py:61) is a LATENCY problem on a B200: n = 1024 is 0.36 GFLOP behind a chain of
+// 1024 dependent pivots.  The blocked launch-per-step formulation (diagonal-block kernel -> panel GEMM -> trailing
+// GEMM, 8 times, + 10 launches for the hierarchical inverse) spent 0.60 ms there, 45 % of the whole training step.
+//
+// Here the whole factorisation AND the explicit inverse W = L^-1 (which turns every later linalg.trsm with this factor
+// into one tensor-core GEMM, svgp_regression.py:85-87,92) is ONE launch:
+//
+//   * the matrix is cut into 64 x 64 tiles; every lower tile of A and every strictly-lower tile of W is a TICKET;
+//     a CTA takes the next ticket with one atomicAdd when it starts and owns that tile for its whole life: the tile's
+//     accumulator lives in REGISTERS (4 x 4 per thread) while the rank-64 updates arrive one elimination step at a time;
+//   * tickets are numbered so that every tile only depends on tiles with SMALLER ticket numbers, and a ticket is only
+//     handed to a CTA that is already running -- so whatever the number of co-resident CTAs (other kernels may share
+//     the GPU, two factorisations run concurrently in the SVGP step), every wait is on a tile whose CTA is resident:
+//     the schedule cannot deadlock, it only narrows to a look-ahead window when fewer CTAs fit;
+//   * tiles are handed from CTA to CTA through L2: the producer stores the finished tile, fences and releases a flag,
+//     the consumer acquires the flag and pulls the tile with 16-byte cp.async (L2 only, never L1) into XOR-swizzled
+//     shared memory, where the 64 x 64 x 64 product runs conflict-free with 16-byte shared loads;
+//   * the ticket of diagonal tile (c, c) also owns the sub-diagonal tile (c, c-1): the critical path of the whole
+//     factorisation  W_{c-1,c-1} -> L_{c,c-1} -> A_cc -= L L^T -> chol -> W_cc  stays inside one CTA, one L2 hand-off
+//     per 64 columns;
+//   * the 64 x 64 diagonal block is factored as two 32 x 32 warp-register Choleskys (lane = row, shuffles for the
+//     column broadcast) which carry the inverse along (right-looking forward substitution in the same registers).
+//
+// mode 0 runs only the inverse half on an existing factor (mxf_tri_pack).  Everything is FP32 FMA on the CUDA cores:
+// the tiles are too small and the chain too serial for tcgen05 to matter here (the trailing updates of n > 1024
+// factorisations, where it does, stay on gemm_tc.cu), and the result is more accurate than a 3xTF32 update.
+#include <algorithm>
+#include "common.cuh"
+#include "chol_dag.cuh"
+
+namespace mxf {
+
+namespace {
+
+constexpr int B = DG_B;
+constexpr int LDP = 68;                // row stride of the plain (unswizzled) diagonal-block buffers (16-byte rows)
+constexpr int TILE_F = B * B;          // floats per tile
+
+__device__ long long* g_dag_prof = nullptr;     // debug: clock64 / globaltimer stamps of the diagonal tickets (thread 0)
+#define DG_STAMP(c, i) do { if (g_dag_prof && threadIdx.x == 0 && blockIdx.y == 0) g_dag_prof[(c) * 16 + (i)] = clock64(); } while (0)
+
+struct DagParams {
+    float* A;                          // n x n (lda): SPD input -> L (mode 1); existing lower factor (mode 0)
+    int64_t lda, sA;
+    float* pack;                       // per-sample pack base
+    int64_t sP;                        // pack stride between samples (floats)
+    int64_t oW, oWT, oLT, oDinv, oDinvT, oSync;   // offsets within the pack; oWT / oLT / oDinv < 0: not written
+    int ldw, ldlt;
+    int* info;
+    int info_base;                     // added to the failing pivot index (offset of this block in the full matrix)
+    int n, T, mode;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- shared-memory tile layout ---------------------------------------------------------------------------------------
+// A tile is 64 rows x 64 floats, row-major, rows of 16 chunks of 16 bytes; chunk q of row r sits at chunk position
+// q ^ ((r >> SH) & 7).  SH = 0 for tiles whose rows are walked "row = tr + 16 a" (4 consecutive rows per warp) and for
+// tiles walked along their rows (row = t, 8 consecutive chunks per warp); SH = 2 for tiles whose rows are walked
+// "row = 4 tc + b" (8 rows, 4 apart, per warp).  Either way the 16-byte loads of a warp hit distinct bank groups.
+template <int SH>
+__device__ __forceinline__ int tile_off(int r, int q) { return r * B + ((q ^ ((r >> SH) & 7)) << 2); }
+
+// global (rows x cols valid, zero elsewhere; `unit_diag` puts 1 on the padded diagonal) -> swizzled shared tile
+template <int SH>
+__device__ __forceinline__ void load_tile_async(float* dst, const float* __restrict__ src, int64_t ld, int rows, int cols,
+                                                bool vec_ok) {
+    const int tid = threadIdx.x;
+    if (vec_ok && rows >= B && cols >= B) {
+#pragma unroll
+        for (int u = 0; u < TILE_F / 4 / DG_THREADS; ++u) {
+            const int e = tid + u * DG_THREADS;
+            const int r = e >> 4, q = e & 15;
+            cp_async16(dst + tile_off<SH>(r, q), src + (int64_t)r * ld + 4 * q);
+        }
+    } else {
+#pragma unroll 4
+        for (int u = 0; u < TILE_F / DG_THREADS; ++u) {
+            const int e = tid + u * DG_THREADS;
+            const int r = e >> 6, c = e & 63;
+            float v = 0.f;
+            if (r < rows && c < cols) v = __ldcg(src + (int64_t)r * ld + c);
+            dst[tile_off<SH>(r, c >> 2) + (c & 3)] = v;
+        }
+    }
+}
+
+// ---- thread <-> output mapping -----------------------------------------------------------------------------------------
+// 256 threads = 16 (tr) x 16 (tc); a warp holds 4 consecutive tr and 8 consecutive tc.  Thread (tr, tc) owns the
+// outputs (row tr + 16 a, cols 4 tc .. 4 tc + 3), a = 0..3: acc[a][b].
+struct Map {
+    int tr, tc;
+    __device__ __forceinline__ Map() {
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        tr = 4 * (w >> 1) + (l >> 3);
+        tc = 8 * (w & 1) + (l & 7);
+    }
+};
+
+// acc[a][b] (+/-)= sum_t X[tr + 16a][t] * Y[4tc + b][t]       X: SH 0, Y: SH 2
+// Both operands are walked along t, so the two halves of every 16-byte shared load are natural operand PAIRS for the
+// packed FP32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2): p[a][b] = (sum over even t, sum over odd t) costs 32 FFMA2 per
+// 4 t-steps instead of 64 FFMA -- the same FMA-pipe work in half the issue slots, which is what this loop is short of
+// with two warps per scheduler (measured on B200, one CTA alone on its SM: 4.4k -> see profiles/r2_potrf_dataflow.md).
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float pair_sum(unsigned long long v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+
+template <bool SUB>
+__device__ __forceinline__ void mma_nt(const float* __restrict__ X, const float* __restrict__ Y, float (&acc)[4][4],
+                                       const Map& m) {
+    const int sx = m.tr & 7, sy = m.tc & 7;
+    unsigned long long p[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) p[a][b] = 0ull;
+#pragma unroll 4
+    for (int q = 0; q < 16; ++q) {
+        ulonglong2 xa[4], yb[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) xa[a] = *reinterpret_cast<const ulonglong2*>(X + (m.tr + 16 * a) * B + ((q ^ sx) << 2));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) yb[b] = *reinterpret_cast<const ulonglong2*>(Y + (4 * m.tc + b) * B + ((q ^ sy) << 2));
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                ffma2(p[a][b], xa[a].x, yb[b].x);
+                ffma2(p[a][b], xa[a].y, yb[b].y);
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = SUB ? acc[a][b] - pair_sum(p[a][b]) : acc[a][b] + pair_sum(p[a][b]);
+}
+
+// acc[a][b] += sum_t X[tr + 16a][t] * Y[t][4tc + b]           X: SH 0, Y: SH 0
+__device__ __forceinline__ void mma_nn(const float* __restrict__ X, const float* __restrict__ Y, float (&acc)[4][4],
+                                       const Map& m) {
+    const int sx = m.tr & 7;
+#pragma unroll 4
+    for (int q = 0; q < 16; ++q) {
+        float4 xa[4], yu[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) xa[a] = *reinterpret_cast<const float4*>(X + (m.tr + 16 * a) * B + ((q ^ sx) << 2));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = 4 * q + u;
+            yu[u] = *reinterpret_cast<const float4*>(Y + t * B + ((m.tc ^ (t & 7)) << 2));
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float xs[4] = {xa[a].x, xa[a].y, xa[a].z, xa[a].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc[a][0] = fmaf(xs[u], yu[u].x, acc[a][0]);
+                acc[a][1] = fmaf(xs[u], yu[u].y, acc[a][1]);
+                acc[a][2] = fmaf(xs[u], yu[u].z, acc[a][2]);
+                acc[a][3] = fmaf(xs[u], yu[u].w, acc[a][3]);
+            }
+        }
+    }
+}
+
+// registers -> swizzled shared tile (SH 0 or 2), row-major
+template <int SH>
+__device__ __forceinline__ void acc_to_tile(float* dst, const float (&acc)[4][4], const Map& m) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = m.tr + 16 * a;
+        *reinterpret_cast<float4*>(dst + tile_off<SH>(r, m.tc)) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    }
+}
+
+// global tile (guarded) -> registers, L2 loads
+__device__ __forceinline__ void load_acc(float (&acc)[4][4], const float* __restrict__ src, int64_t ld, int rows, int cols,
+                                         bool vec_ok, bool unit_diag, const Map& m) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = m.tr + 16 * a, c0 = 4 * m.tc;
+        if (vec_ok && r < rows && c0 + 3 < cols) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)r * ld + c0));
+            acc[a][0] = v.x; acc[a][1] = v.y; acc[a][2] = v.z; acc[a][3] = v.w;
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float v = (unit_diag && r == c0 + b) ? 1.f : 0.f;
+                if (r < rows && c0 + b < cols) v = __ldcg(src + (int64_t)r * ld + c0 + b);
+                acc[a][b] = v;
+            }
+        }
+    }
+}
+
+// registers -> global tile (guarded), row-major
+__device__ __forceinline__ void store_acc(float* __restrict__ dst, int64_t ld, const float (&acc)[4][4], int rows, int cols,
+                                          bool vec_ok, const Map& m) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = m.tr + 16 * a, c0 = 4 * m.tc;
+        if (r >= rows) continue;
+        if (vec_ok && c0 + 3 < cols) {
+            *reinterpret_cast<float4*>(dst + (int64_t)r * ld + c0) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (c0 + b < cols) dst[(int64_t)r * ld + c0 + b] = acc[a][b];
+        }
+    }
+}
+
+// registers -> global tile, TRANSPOSED: dst[(c) * ld + r] = acc(r, c); rows / cols are the bounds of the SOURCE tile
+__device__ __forceinline__ void store_acc_t(float* __restrict__ dst, int64_t ld, const float (&acc)[4][4], int rows, int cols,
+                                            const Map& m) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = m.tr + 16 * a;
+        if (r >= rows) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int c = 4 * m.tc + b;
+            if (c < cols) dst[(int64_t)c * ld + r] = acc[a][b];
+        }
+    }
+}
+
+// zero a rows x cols region of a global tile
+__device__ __forceinline__ void zero_tile(float* __restrict__ dst, int64_t ld, int rows, int cols, bool vec_ok, const Map& m) {
+    const float z[4][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    store_acc(dst, ld, z, rows, cols, vec_ok, m);
+}
+
+// ---- flags -------------------------------------------------------------------------------------------------------------
+struct Sync {
+    int* ticket;
+    int* abort_flag;
+    int* Lfin;        // [T*T]  L tile (i, j), i > j, final (row-major in A)
+    int* Wfin;        // [T*T]  W tile (i, j), i >= j, final (row-major in W)
+};
+
+// All threads call; thread 0 spins on up to two flags.  Returns false when the launch was aborted (a wait exceeded 2 s:
+// cannot happen by construction, it is the safety net that turns a scheduling bug into an error code instead of a hang).
+__device__ __forceinline__ bool wait_flags(const int* f0, const int* f1, int* abort_flag, int* sh) {
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        while (true) {
+            const bool r0 = (f0 == nullptr) || (ld_acquire(f0) != 0);
+            const bool r1 = (f1 == nullptr) || (ld_acquire(f1) != 0);
+            if (r0 && r1) break;
+            if ((++spins & 127u) == 0u) {
+                if (ld_acquire(abort_flag) != 0) { ok = 0; break; }
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 2000000000ull) { atomicExch(abort_flag, 1); ok = 0; break; }
+            }
+        }
+        *sh = ok;
+    }
+    __syncthreads();
+    const bool ok = (*sh != 0);
+    __syncthreads();
+    return ok;
+}
+
+// all threads' global stores of a finished tile -> visible to every SM, then the flag
+__device__ __forceinline__ void publish(int* flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release(flag, 1);
+    }
+}
+
+// ---- 32-column warp-register Cholesky panel ----------------------------------------------------------------------------
+// Lane i holds row i of the 32 x 32 pivot block in r0[0..31] (entries c <= i meaningful) and, when TWO, row 32 + i of the
+// block below it in r1[0..31].  Column step C: d = pivot (broadcast by the PREVIOUS step, which shuffles it out ahead of its
+// other updates, so that the pivot chain is shuffle -> rsqrt -> fmul -> fma), inv = d^-1/2, l_iC = r_i[C] inv, then
+// r_i[t] -= l_iC l_tC for t > C with l_tC shuffled from lane t; the rows below ride along on the same shuffles (their
+// triangular solve  L21 = A21 L11^-T  costs one extra FMA per shuffle and no extra latency).  Measured on B200
+// (scripts/ubench/chol32.cu): 4.2k cycles for the 32 x 32 block with everything in registers; shared-memory
+// formulations with run-time column loops: 10k-32k; carrying the inverse along (two shuffles per entry): 11k-18k.
+__device__ __forceinline__ float rsqrt_newton(float d) {
+    const float y = rsqrtf(d);
+    return y * fmaf(-0.5f * d * y, y, 1.5f);
+}
+
+// Column steps are template-recursive so that every register index is a compile-time constant: ~40 KB of straight-line
+// code.  Executed COLD (first time on an SM) it runs at ~11 cycles per instruction -- 17k cycles against 3.3k-4.2k warm
+// (scripts/ubench/chol32.cu) -- so (a) there is ONE instantiation, used for both 32-column panels of a diagonal block
+// (the second call is warm by construction), and (b) a diagonal ticket, which has nothing to do until the previous
+// diagonal block is finished, first runs the whole diagonal-block code once on an identity tile to pull it into the
+// instruction caches.  A rotating-register-window loop (4 x 12 KB body) was measured slower than this (31k-35k
+// cycles per diagonal block against 25k-30k, both cold).
+template <int C>
+struct PanelStep {
+    static __device__ __forceinline__ void run(float (&r0)[32], float (&r1)[32], float dcur, int& bad) {
+        if (!(dcur > 0.f) && bad == 0) bad = C + 1;
+        const float inv = rsqrt_newton(dcur);
+        const float l0 = r0[C] * inv;                 // l_iC for lanes >= C (don't-care above the diagonal)
+        const float l1 = r1[C] * inv;
+        r0[C] = l0;
+        r1[C] = l1;
+        float dnext = 0.f;
+        // the next pivot first: lane C+1 needs only its OWN l -- no second shuffle on the pivot chain
+        if (C + 1 < 32) dnext = __shfl_sync(0xffffffffu, fmaf(-l0, l0, r0[(C + 1) & 31]), (C + 1) & 31);
+#pragma unroll
+        for (int t = C + 1; t < 32; ++t) {
+            const float ltc = __shfl_sync(0xffffffffu, l0, t);
+            r0[t] = fmaf(-l0, ltc, r0[t]);
+            r1[t] = fmaf(-l1, ltc, r1[t]);
+        }
+        PanelStep<C + 1>::run(r0, r1, dnext, bad);
+    }
+};
+template <>
+struct PanelStep<32> {
+    static __device__ __forceinline__ void run(float (&)[32], float (&)[32], float, int&) {}
+};
+
+// One warp: Cholesky of the 32 x 32 block at D[p0.., p0..] (row stride LDP) with ONE more row set riding along on the
+// same shuffles (one extra FMA per shuffle, no extra latency; measured 4.4k cycles against 3.1k without it and 7.5k with
+// two extra sets, scripts/ubench/chol32.cu):
+//   inverse == false: the 32 rows below the block, D[p0+32.., p0..] <- D[p0+32.., p0..] L^-T (the panel solve); L is
+//                     written back in place (zeros above its diagonal);
+//   inverse == true:  the rows of the IDENTITY: I L^-T = L^-T, so lane i ends up holding column i of W = L^-1, written to
+//                     Wd[p0.., p0 + i] -- the inverse of the block without a substitution pass; L is written back only
+//                     if write_l (two warps may run the two flavours on the same block at the same time: same code,
+//                     one instruction stream through the caches).
+// Returns the 1-based failing pivot (0: none).
+__device__ __noinline__ int warp_chol_panel32(float* D, float* Wd, int p0, int lane, bool inverse, bool write_l, bool pair_sync) {
+    float r0[32], r1[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(D + (p0 + lane) * LDP + p0 + 4 * q);
+        r0[4 * q] = v.x; r0[4 * q + 1] = v.y; r0[4 * q + 2] = v.z; r0[4 * q + 3] = v.w;
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!inverse) u = *reinterpret_cast<const float4*>(D + (p0 + 32 + lane) * LDP + p0 + 4 * q);
+        r1[4 * q] = u.x; r1[4 * q + 1] = u.y; r1[4 * q + 2] = u.z; r1[4 * q + 3] = u.w;
+    }
+    if (inverse) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r1[c] = (c == lane) ? 1.f : 0.f;
+    }
+    if (pair_sync) asm volatile("bar.sync 1, 64;" ::: "memory");      // both flavours have read the block
+    int bad = 0;
+    PanelStep<0>::run(r0, r1, __shfl_sync(0xffffffffu, r0[0], 0), bad);
+    if (write_l) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float4 v;
+            v.x = (4 * q <= lane) ? r0[4 * q] : 0.f;
+            v.y = (4 * q + 1 <= lane) ? r0[4 * q + 1] : 0.f;
+            v.z = (4 * q + 2 <= lane) ? r0[4 * q + 2] : 0.f;
+            v.w = (4 * q + 3 <= lane) ? r0[4 * q + 3] : 0.f;
+            *reinterpret_cast<float4*>(D + (p0 + lane) * LDP + p0 + 4 * q) = v;
+        }
+    }
+    if (!inverse) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(D + (p0 + 32 + lane) * LDP + p0 + 4 * q) =
+                make_float4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) Wd[(p0 + c) * LDP + p0 + lane] = (c >= lane) ? r1[c] : 0.f;     // W[c][lane]
+    }
+    return bad;
+}
+
+// One warp: W = L^-1 for the 32 x 32 lower-triangular block at D[p0.., p0..] -> Wd[p0.., p0..] (zeros above the diagonal).
+// Lane j owns column j of W; right-looking forward substitution with the 32 running right-hand sides in registers:
+// x_i = acc_i / L_ii, then acc_i' -= L_i'i x_i for i' > i (independent FMAs; L_i'i is a warp-uniform shared-memory load).
+template <int I>
+struct InvStep32 {
+    static __device__ __forceinline__ void run(float (&acc)[32], const float* Dblk, float idg_all) {
+        const float x = acc[I] * __shfl_sync(0xffffffffu, idg_all, I);
+        acc[I] = x;
+#pragma unroll
+        for (int t = I + 1; t < 32; ++t) acc[t] = fmaf(-Dblk[t * LDP + I], x, acc[t]);
+        InvStep32<I + 1>::run(acc, Dblk, idg_all);
+    }
+};
+template <>
+struct InvStep32<32> {
+    static __device__ __forceinline__ void run(float (&)[32], const float*, float) {}
+};
+
+__device__ __noinline__ void warp_inv32(const float* D, float* Wd, int p0, int lane) {
+    const float* Dblk = D + p0 * LDP + p0;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = (i == lane) ? 1.f : 0.f;
+    const float idg_all = 1.0f / Dblk[lane * LDP + lane];
+    InvStep32<0>::run(acc, Dblk, idg_all);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) Wd[(p0 + i) * LDP + p0 + lane] = acc[i];      // acc[i] = 0 for i < lane
+}
+
+// out[r][c] (32 x 32 at Out, stride LDP) = alpha * sum_t X[r][t] * (NT ? Y[c][t] : Y[t][c]) (+ Out if ACCUM)
+// X, Y, Out: 32 x 32 blocks in plain buffers (row stride LDP, 16-byte aligned rows).  Warps w0 .. w0+nw-1 take part: warp w
+// takes rows w - w0, w - w0 + nw, ...; lane = output column; the lane's Y vector sits in registers, the X rows are
+// warp-uniform 16-byte loads.
+template <bool NT, bool ACCUM>
+__device__ __forceinline__ void small_mm32(float* Out, const float* X, const float* Y, float alpha, int w0 = 0, int nw = 8) {
+    const int warp = (threadIdx.x >> 5) - w0, lane = threadIdx.x & 31;
+    if (warp < 0 || warp >= nw) return;
+    float y[32];
+    if (NT) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(Y + lane * LDP + 4 * q);
+            y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) y[t] = Y[t * LDP + lane];
+    }
+    for (int row = warp; row < 32; row += nw) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 x = *reinterpret_cast<const float4*>(X + row * LDP + 4 * q);
+            s0 = fmaf(x.x, y[4 * q], s0);
+            s1 = fmaf(x.y, y[4 * q + 1], s1);
+            s2 = fmaf(x.z, y[4 * q + 2], s2);
+            s3 = fmaf(x.w, y[4 * q + 3], s3);
+        }
+        const float v = alpha * ((s0 + s1) + (s2 + s3));
+        if (ACCUM) Out[row * LDP + lane] += v;
+        else Out[row * LDP + lane] = v;
+    }
+}
+
+// 64 x 64 diagonal block in D (plain, stride LDP; lower part meaningful, padded with identity): factor (FACTOR) and
+// invert.  On exit D = L (zeros above the diagonal), Wd = L^-1 (zeros above).  Tm: 32 x LDP scratch.
+//   warp 0: panel Cholesky of columns 0..31 (L11 and L21), warp 1 the same code on [A11; I] (W11 = L11^-1) -> all:
+//   A22 -= L21 L21^T -> warp 0: Cholesky of [A22; I] (L22, W22) while warps 1..7 form L21 W11 -> all: W21 = -W22 (L21 W11).
+template <bool FACTOR>
+__device__ __forceinline__ int diag_block_64(float* D, float* Wd, float* Tm, long long* st = nullptr) {
+#define DG_ST(i) do { if (st && threadIdx.x == 0) st[i] = clock64(); } while (0)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ int bad_sh[2];
+    if (threadIdx.x < 2) bad_sh[threadIdx.x] = 0;
+    for (int e = threadIdx.x; e < 32 * 32; e += DG_THREADS) {          // zero the upper-right 32 x 32 blocks
+        const int r = e >> 5, c = 32 + (e & 31);
+        D[r * LDP + c] = 0.f;
+        Wd[r * LDP + c] = 0.f;
+    }
+    __syncthreads();
+    if (FACTOR) {
+        if (warp == 0) {
+            const int b = warp_chol_panel32(D, Wd, 0, lane, false, true, true);             // L11, L21
+            if (lane == 0) bad_sh[0] = b;
+        } else if (warp == 1) {
+            warp_chol_panel32(D, Wd, 0, lane, true, false, true);                            // W11 (same code, same time)
+        }
+        __syncthreads();
+        DG_ST(0);
+        small_mm32<true, true>(D + 32 * LDP + 32, D + 32 * LDP, D + 32 * LDP, -1.f);       // A22 -= L21 L21^T
+        __syncthreads();
+        DG_ST(1);
+        if (warp == 0) {
+            const int b = warp_chol_panel32(D, Wd, 32, lane, true, true, false);            // L22, W22
+            if (lane == 0) bad_sh[1] = b;
+        }
+        small_mm32<false, false>(Tm, D + 32 * LDP, Wd, 1.f, 1, 7);                         // Tm = L21 W11 (warps 1..7)
+        __syncthreads();
+        DG_ST(2);
+        DG_ST(3);
+    } else {
+        if (warp == 0) warp_inv32(D, Wd, 0, lane);
+        else if (warp == 1) warp_inv32(D, Wd, 32, lane);
+        __syncthreads();
+        small_mm32<false, false>(Tm, D + 32 * LDP, Wd, 1.f);
+        __syncthreads();
+    }
+    small_mm32<false, false>(Wd + 32 * LDP, Wd + 32 * LDP + 32, Tm, -1.f);                  // W21 = -W22 Tm
+    __syncthreads();
+    DG_ST(4);
+    int bad = 0;
+    if (bad_sh[0] != 0) bad = bad_sh[0];
+    else if (bad_sh[1] != 0) bad = 32 + bad_sh[1];
+    return bad;
+#undef DG_ST
+}
+
+// plain buffer (stride LDP) -> this thread's 4 x 4 outputs
+__device__ __forceinline__ void plain_to_acc(float (&acc)[4][4], const float* P, const Map& m) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const float4 v = *reinterpret_cast<const float4*>(P + (m.tr + 16 * a) * LDP + 4 * m.tc);
+        acc[a][0] = v.x; acc[a][1] = v.y; acc[a][2] = v.z; acc[a][3] = v.w;
+    }
+}
+__device__ __forceinline__ void acc_to_plain(float* P, const float (&acc)[4][4], const Map& m) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        *reinterpret_cast<float4*>(P + (m.tr + 16 * a) * LDP + 4 * m.tc) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+}
+
+// Shared memory: bufX | bufY (one swizzled tile each) | bufO (one tile: an accumulator turned operand).  The diagonal
+// ticket overlays its plain D / Wd / Tm buffers on the same space.
+// One CTA per SM (the request is padded past half of the SM's shared memory): a diagonal ticket is the critical path of
+// the whole factorisation and a single warp carries most of it -- a co-resident CTA busy with tile products takes half of
+// its issue slots (measured: 20k -> see profiles/r2_potrf_dataflow.md).  The bulk tiles have slack to spare.
+constexpr size_t DG_SMEM_USED = sizeof(float) * (3 * TILE_F + 2 * B * LDP + 32 * LDP) + 64;
+constexpr size_t DG_SMEM = DG_SMEM_USED > 120 * 1024 ? DG_SMEM_USED : 120 * 1024;
+
+__global__ void __launch_bounds__(DG_THREADS, 1)
+potrf_dag_kernel(const DagParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bufX = reinterpret_cast<float*>(smem_raw);
+    float* bufY = bufX + TILE_F;
+    float* bufO = bufY + TILE_F;
+    float* Dp = bufO + TILE_F;           // [64][LDP]
+    float* Wp = Dp + B * LDP;            // [64][LDP]
+    float* Tm = Wp + B * LDP;            // [32][LDP]
+    __shared__ int sh_ticket, sh_flag;
+
+    const int s = blockIdx.y;
+    float* A = p.A + (int64_t)s * p.sA;
+    float* pk = p.pack + (int64_t)s * p.sP;
+    float* W = pk + p.oW;
+    float* WT = p.oWT >= 0 ? pk + p.oWT : nullptr;
+    float* LT = p.oLT >= 0 ? pk + p.oLT : nullptr;
+    float* dinv = p.oDinv >= 0 ? pk + p.oDinv : nullptr;
+    float* dinvT = p.oDinv >= 0 ? pk + p.oDinvT : nullptr;
+    int* sy = reinterpret_cast<int*>(pk + p.oSync);
+    const int T = p.T, n = p.n;
+    Sync sync{sy, sy + 1, sy + 2, sy + 2 + T * T};
+    const int64_t lda = p.lda, ldw = p.ldw, ldlt = p.ldlt;
+    const bool factor = p.mode != 0;
+
+    if (threadIdx.x == 0) sh_ticket = atomicAdd(sync.ticket, 1);
+    __syncthreads();
+    int t = sh_ticket;
+    // ---- ticket -> (kind, i, j):  group c = [diag c | A(i, c), i = c+2..T-1 (mode 1) | W(c, j), j = 0..c-1]
+    int c = 0;
+    for (;; ++c) {
+        const int g = 1 + (factor ? max(0, T - c - 2) : 0) + c;
+        if (t < g) break;
+        t -= g;
+    }
+    if (c >= T) return;
+    const int nA = factor ? max(0, T - c - 2) : 0;
+    const Map m;
+    // alignment of the 16-byte paths
+    const bool vA = ((lda & 3) == 0) && ((p.sA & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+    const bool vW = ((ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    auto ext = [n](int blk) { return min(B, n - blk * B); };        // valid rows / cols of tile index blk
+
+    if (t == 0) {
+        // ============================ diagonal ticket c: tiles (c, c) and (c, c-1) ======================================
+        const int i0 = c * B, re = ext(c);
+        float acc2[4][4], acc1[4][4];
+        if (g_dag_prof && threadIdx.x == 0 && blockIdx.y == 0) g_dag_prof[c * 16 + 14] = (long long)globaltimer_ns();
+        DG_STAMP(c, 0);
+        if (c >= 1) {
+            // nothing to do yet: pull the diagonal-block code into the instruction caches on an identity tile
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc2[a][b] = (m.tr + 16 * a == 4 * m.tc + b) ? 1.f : 0.f;
+            acc_to_plain(Dp, acc2, m);
+            __syncthreads();
+            if (factor) diag_block_64<true>(Dp, Wp, Tm);
+            else diag_block_64<false>(Dp, Wp, Tm);
+            __syncthreads();
+        }
+        load_acc(acc2, A + (int64_t)i0 * lda + i0, lda, re, re, vA, true, m);
+        if (factor && c >= 1) {
+            load_acc(acc1, A + (int64_t)i0 * lda + i0 - B, lda, re, B, vA, false, m);
+            for (int k = 0; k + 1 < c; ++k) {
+                if (!wait_flags(&sync.Lfin[c * T + k], &sync.Lfin[(c - 1) * T + k], sync.abort_flag, &sh_flag)) return;
+                load_tile_async<0>(bufX, A + (int64_t)i0 * lda + k * B, lda, re, B, vA);               // L_ck as X
+                load_tile_async<2>(bufO, A + (int64_t)i0 * lda + k * B, lda, re, B, vA);               // L_ck as Y
+                load_tile_async<2>(bufY, A + (int64_t)(i0 - B) * lda + k * B, lda, B, B, vA);          // L_{c-1,k} as Y
+                cp_async_wait_all();
+                __syncthreads();
+                mma_nt<true>(bufX, bufY, acc1, m);
+                mma_nt<true>(bufX, bufO, acc2, m);
+                __syncthreads();
+            }
+            // L_{c,c-1} = A_{c,c-1} W_{c-1,c-1}^T
+            acc_to_tile<0>(bufX, acc1, m);
+            DG_STAMP(c, 1);
+            if (!wait_flags(&sync.Wfin[(c - 1) * T + (c - 1)], nullptr, sync.abort_flag, &sh_flag)) return;
+            DG_STAMP(c, 2);
+            load_tile_async<2>(bufY, W + (int64_t)(i0 - B) * ldw + i0 - B, ldw, B, B, vW);
+            cp_async_wait_all();
+            __syncthreads();
+            DG_STAMP(c, 3);
+            float l1[4][4] = {};
+            mma_nt<false>(bufX, bufY, l1, m);
+            DG_STAMP(c, 4);
+            store_acc(A + (int64_t)i0 * lda + i0 - B, lda, l1, re, B, vA, m);
+            publish(&sync.Lfin[c * T + (c - 1)]);
+            DG_STAMP(c, 5);
+            // A_cc -= L_{c,c-1} L_{c,c-1}^T
+            __syncthreads();
+            acc_to_tile<0>(bufX, l1, m);
+            acc_to_tile<2>(bufY, l1, m);
+            __syncthreads();
+            mma_nt<true>(bufX, bufY, acc2, m);
+            __syncthreads();
+            DG_STAMP(c, 6);
+        }
+        // factor / invert the 64 x 64 block
+        acc_to_plain(Dp, acc2, m);
+        __syncthreads();
+        long long* dst = (g_dag_prof && blockIdx.y == 0) ? g_dag_prof + 256 + c * 8 : nullptr;
+        if (dst && threadIdx.x == 0) dst[5] = clock64();
+        const int bad = factor ? diag_block_64<true>(Dp, Wp, Tm, dst) : diag_block_64<false>(Dp, Wp, Tm, dst);
+        DG_STAMP(c, 7);
+        if (factor && bad != 0 && bad <= re && threadIdx.x == 0 && p.info) atomicCAS(&p.info[s], 0, p.info_base + i0 + bad);
+        float lw[4][4];
+        plain_to_acc(lw, Wp, m);
+        store_acc(W + (int64_t)i0 * ldw + i0, ldw, lw, re, re, vW, m);
+        DG_STAMP(c, 8);
+        publish(&sync.Wfin[c * T + c]);
+        DG_STAMP(c, 9);
+        // by-products, read only after the launch
+        if (WT) store_acc_t(WT + (int64_t)i0 * ldw + i0, ldw, lw, re, re, m);
+        if (dinv) {
+            const int blk = c >> 1, o = (c & 1) * B;
+            float* dv = dinv + (int64_t)blk * 128 * 128 + (int64_t)o * 128 + o;
+            float* dvT = dinvT + (int64_t)blk * 128 * 128 + (int64_t)o * 128 + o;
+            store_acc(dv, 128, lw, B, B, true, m);
+            store_acc_t(dvT, 128, lw, B, B, m);
+            if (c == T - 1 && o == 0) {
+                // the matrix ends in the first half of this 128-block: identity padding for the missing half
+                float id[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) id[a][b] = (m.tr + 16 * a == 4 * m.tc + b) ? 1.f : 0.f;
+                store_acc(dv + (int64_t)B * 128 + B, 128, id, B, B, true, m);
+                store_acc(dvT + (int64_t)B * 128 + B, 128, id, B, B, true, m);
+                zero_tile(dv + B, 128, B, B, true, m);
+                zero_tile(dv + (int64_t)B * 128, 128, B, B, true, m);
+                zero_tile(dvT + B, 128, B, B, true, m);
+                zero_tile(dvT + (int64_t)B * 128, 128, B, B, true, m);
+            }
+        }
+        if (factor) {
+            plain_to_acc(lw, Dp, m);
+            store_acc(A + (int64_t)i0 * lda + i0, lda, lw, re, re, vA, m);
+            if (LT) store_acc_t(LT + (int64_t)i0 * ldlt + i0, ldlt, lw, re, re, m);
+        }
+        if (factor && c >= 1) {
+            // by-products of the sub-diagonal tile (its row-major copy in bufX is still intact): strict upper tile, L^T
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float4 v = *reinterpret_cast<const float4*>(bufX + tile_off<0>(m.tr + 16 * a, m.tc));
+                lw[a][0] = v.x; lw[a][1] = v.y; lw[a][2] = v.z; lw[a][3] = v.w;
+            }
+            zero_tile(A + (int64_t)(i0 - B) * lda + i0, lda, B, re, vA, m);
+            if (LT) {
+                store_acc_t(LT + (int64_t)(i0 - B) * ldlt + i0, ldlt, lw, re, B, m);
+                zero_tile(LT + (int64_t)i0 * ldlt + i0 - B, ldlt, re, B, false, m);
+            }
+        }
+        if (g_dag_prof && threadIdx.x == 0 && blockIdx.y == 0) g_dag_prof[c * 16 + 15] = (long long)globaltimer_ns();
+        return;
+    }
+
+    if (t - 1 < nA) {
+        // ============================ A ticket: tile (i, c), i >= c + 2 =================================================
+        const int i = c + 2 + (t - 1), j = c;
+        const int i0 = i * B, j0 = j * B, re = ext(i);
+        float acc[4][4];
+        load_acc(acc, A + (int64_t)i0 * lda + j0, lda, re, B, vA, false, m);
+        for (int k = 0; k < j; ++k) {
+            if (!wait_flags(&sync.Lfin[i * T + k], &sync.Lfin[j * T + k], sync.abort_flag, &sh_flag)) return;
+            load_tile_async<0>(bufX, A + (int64_t)i0 * lda + k * B, lda, re, B, vA);
+            load_tile_async<2>(bufY, A + (int64_t)j0 * lda + k * B, lda, B, B, vA);
+            cp_async_wait_all();
+            __syncthreads();
+            mma_nt<true>(bufX, bufY, acc, m);
+            __syncthreads();
+        }
+        acc_to_tile<0>(bufX, acc, m);
+        if (!wait_flags(&sync.Wfin[j * T + j], nullptr, sync.abort_flag, &sh_flag)) return;
+        load_tile_async<2>(bufY, W + (int64_t)j0 * ldw + j0, ldw, B, B, vW);
+        cp_async_wait_all();
+        __syncthreads();
+        float l[4][4] = {};
+        mma_nt<false>(bufX, bufY, l, m);
+        store_acc(A + (int64_t)i0 * lda + j0, lda, l, re, B, vA, m);
+        publish(&sync.Lfin[i * T + j]);
+        zero_tile(A + (int64_t)j0 * lda + i0, lda, B, re, vA, m);
+        if (LT) {
+            store_acc_t(LT + (int64_t)j0 * ldlt + i0, ldlt, l, re, B, m);
+            zero_tile(LT + (int64_t)i0 * ldlt + j0, ldlt, re, B, false, m);
+        }
+        return;
+    }
+
+    {
+        // ============================ W ticket: tile (c, j), j < c ======================================================
+        const int i = c, j = t - 1 - nA;
+        const int i0 = i * B, j0 = j * B, re = ext(i);
+        float acc[4][4] = {};
+        for (int k = j; k < i; ++k) {
+            const int* lf = factor ? &sync.Lfin[i * T + k] : nullptr;
+            if (!wait_flags(lf, &sync.Wfin[k * T + j], sync.abort_flag, &sh_flag)) return;
+            load_tile_async<0>(bufX, A + (int64_t)i0 * lda + k * B, lda, re, B, vA);                   // L_ik
+            load_tile_async<0>(bufY, W + (int64_t)(k * B) * ldw + j0, ldw, B, B, vW);                  // W_kj
+            cp_async_wait_all();
+            __syncthreads();
+            mma_nn(bufX, bufY, acc, m);
+            __syncthreads();
+        }
+        acc_to_tile<0>(bufY, acc, m);
+        if (!wait_flags(&sync.Wfin[i * T + i], nullptr, sync.abort_flag, &sh_flag)) return;
+        load_tile_async<0>(bufX, W + (int64_t)i0 * ldw + i0, ldw, re, re, vW);                         // W_ii
+        cp_async_wait_all();
+        __syncthreads();
+        float w[4][4] = {};
+        mma_nn(bufX, bufY, w, m);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) w[a][b] = -w[a][b];
+        store_acc(W + (int64_t)i0 * ldw + j0, ldw, w, re, B, vW, m);
+        publish(&sync.Wfin[i * T + j]);
+        zero_tile(W + (int64_t)j0 * ldw + i0, ldw, B, re, vW, m);
+        if (WT) {
+            store_acc_t(WT + (int64_t)j0 * ldw + i0, ldw, w, re, B, m);
+            zero_tile(WT + (int64_t)i0 * ldw + j0, ldw, re, B, vW, m);
+        }
+        if (dinv && (i >> 1) == (j >> 1)) {               // i = 2b+1, j = 2b: the off-diagonal tile of a 128-block
+            const int blk = i >> 1;
+            float* dv = dinv + (int64_t)blk * 128 * 128;
+            float* dvT = dinvT + (int64_t)blk * 128 * 128;
+            store_acc(dv + (int64_t)B * 128, 128, w, B, B, true, m);
+            zero_tile(dv + B, 128, B, B, true, m);
+            store_acc_t(dvT + B, 128, w, B, B, m);
+            zero_tile(dvT + (int64_t)B * 128, 128, B, B, true, m);
+        }
+    }
+}
+
+}  // namespace
+
+int dag_set_prof(long long* dev_ptr) { return (int)cudaMemcpyToSymbol(g_dag_prof, &dev_ptr, sizeof(dev_ptr)); }
+
+int dag_tickets(int T, int mode) {
+    int tot = 0;
+    for (int c = 0; c < T; ++c) tot += 1 + (mode ? std::max(0, T - c - 2) : 0) + c;
+    return tot;
+}
+
+int dag_launch(int mode, float* A, int64_t lda, int64_t sA, int n, float* pack, int64_t sP, int64_t oW, int64_t oWT,
+               int64_t oLT, int64_t oDinv, int64_t oDinvT, int64_t oSync, int ldw, int ldlt, int* info, int info_base, int S,
+               cudaStream_t st) {
+    if (n <= 0 || S <= 0) return MXF_OK;
+    if (n > DG_MAXN) return MXF_EINVAL;
+    DagParams p;
+    p.A = A; p.lda = lda; p.sA = sA;
+    p.pack = pack; p.sP = sP;
+    p.oW = oW; p.oWT = oWT; p.oLT = oLT; p.oDinv = oDinv; p.oDinvT = oDinvT; p.oSync = oSync;
+    p.ldw = ldw; p.ldlt = ldlt;
+    p.info = info; p.info_base = info_base;
+    p.n = n; p.T = (n + B - 1) / B; p.mode = mode;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM);
+        attr_set = true;
+    }
+    // ticket counter + flags of every sample: one strided memset
+    cudaError_t e;
+    if (S == 1) e = cudaMemsetAsync(pack + oSync, 0, (size_t)DG_SYNC_INTS * sizeof(int), st);
+    else e = cudaMemset2DAsync(pack + oSync, (size_t)sP * sizeof(float), 0, (size_t)DG_SYNC_INTS * sizeof(int), (size_t)S, st);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(dag_tickets(p.T, mode), S);
+    potrf_dag_kernel<<<grid, DG_THREADS, DG_SMEM, st>>>(p);
+    return after_launch();
+}
+
+}  // namespace mxf

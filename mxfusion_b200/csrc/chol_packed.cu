@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
+#include "chol_dag.cuh"
 
 extern "C" int mxf_transpose(int dtype, const void* A, int64_t lda, int64_t sA, void* out, int64_t ldo, int64_t sO,
                              int S, int m, int n, void* stream);
@@ -73,6 +74,34 @@ struct PackLayout {
         }
         total = (off + 3) & ~(int64_t)3;
     }
+    int nq() const { return (n + top - 1) / top; }
+    int64_t wtop() const { return lvl[nlvl - 1]; }      // top-level inverse blocks (top x top each, row stride top)
+    int64_t wtopT() const { return topT; }
+};
+
+// f32: the factor's explicit inverse comes out of the single-launch tile-dataflow kernel (chol_dag.cu) for any
+// n <= 1024, so the "top level" is ONE block W = L^-1 with row stride top = n rounded up to 4; larger factors are cut
+// into 1024-blocks (the last one may be ragged).  No intermediate levels, no scratch; DG_SYNC_INTS ints of flags at the end.
+template <>
+struct PackLayout<float> {
+    int n, nblk, ldt, top;
+    int64_t dinv, dinvT, lt, wtop_, wtopT_, sync, total;
+    explicit PackLayout(int n_) : n(n_) {
+        constexpr int NB = 128;
+        nblk = (n + NB - 1) / NB;
+        ldt = (n + 3) & ~3;
+        top = n <= DG_MAXN ? std::max(4, ldt) : DG_MAXN;
+        dinv = 0;
+        dinvT = (int64_t)nblk * NB * NB;
+        lt = 2 * dinvT;
+        wtop_ = (lt + (int64_t)n * ldt + 3) & ~(int64_t)3;
+        wtopT_ = wtop_ + (int64_t)nq() * top * top;
+        sync = wtopT_ + (int64_t)nq() * top * top;
+        total = (sync + DG_SYNC_INTS + 3) & ~(int64_t)3;
+    }
+    int nq() const { return (n + top - 1) / top; }
+    int64_t wtop() const { return wtop_; }
+    int64_t wtopT() const { return wtopT_; }
 };
 
 constexpr int PD_THREADS = 512;
@@ -431,8 +460,65 @@ template <typename T>
 static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int n, T* pack, const PackLayout<T>& pl,
                                 cudaStream_t st, int row0 = 0, int nrows = -1);
 
+// f32: every (<= 1024)^2 diagonal block is factored AND inverted by one launch of the tile-dataflow kernel; for n > 1024
+// the panel  L21 = A21 W^T  and the trailing update  A22 -= L21 L21^T  are K = 1024 tensor-core GEMMs.
+static int potrf_packed_f32(float* A, int64_t lda, int64_t sA, int S, int n, int* info, float* pack, cudaStream_t st) {
+    const PackLayout<float> pl(n);
+    if (info) {
+        cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int) * (size_t)S, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (n <= DG_MAXN)
+        return dag_launch(1, A, lda, sA, n, pack, pl.total, pl.wtop(), pl.wtopT(), pl.lt, pl.dinv, pl.dinvT, pl.sync, pl.top,
+                          pl.ldt, info, 0, S, st);
+    const int OB = pl.top;
+    for (int o0 = 0; o0 < n; o0 += OB) {
+        const int nb = std::min(OB, n - o0);
+        const int64_t qoff = (int64_t)(o0 / OB) * OB * OB, doff = (int64_t)(o0 / 128) * 128 * 128;
+        int rc = dag_launch(1, A + (int64_t)o0 * lda + o0, lda, sA, nb, pack, pl.total, pl.wtop() + qoff, pl.wtopT() + qoff, -1,
+                            pl.dinv + doff, pl.dinvT + doff, pl.sync, OB, 0, info, o0, S, st);
+        if (rc != MXF_OK) return rc;
+        const int below = n - o0 - nb;
+        if (below > 0) {
+            float* A21 = A + (int64_t)(o0 + nb) * lda + o0;
+            float* A22 = A + (int64_t)(o0 + nb) * lda + (o0 + nb);
+            const float* Wo = pack + pl.wtop() + qoff;
+            float* scr = pack + pl.lt;                      // L^T is written last: its space is free until then
+            rc = gemm_any<float>(0, 1, below, OB, OB, 1.0, A21, lda, sA, Wo, OB, pl.total, 0.0, scr, OB, pl.total, S, 0, st, 0);
+            if (rc != MXF_OK) return rc;
+            rc = gemm_any<float>(0, 1, below, below, OB, -1.0, scr, OB, pl.total, scr, OB, pl.total, 1.0, A22, lda, sA, S, 1, st, 0);
+            if (rc != MXF_OK) return rc;
+            for (int s = 0; s < S; ++s)
+                cudaMemcpy2DAsync(A21 + (int64_t)s * sA, (size_t)lda * sizeof(float), scr + (int64_t)s * pl.total,
+                                  (size_t)OB * sizeof(float), (size_t)OB * sizeof(float), below, cudaMemcpyDeviceToDevice, st);
+        }
+    }
+    if (n > 65535) return MXF_ENOTIMPL;
+    dim3 g(cdiv(n, 256), n, S);
+    launch_pdl(zero_upper_kernel<float>, g, dim3(256), (size_t)0, st, A, lda, sA, n);
+    int rc = mxf_transpose(MXF_F32, A, lda, sA, pack + pl.lt, pl.ldt, pl.total, S, n, n, st);
+    if (rc != MXF_OK) return rc;
+    return after_launch(1);
+}
+
+static int tri_pack_f32(const float* L, int64_t lda, int64_t sA, int S, int n, float* pack, cudaStream_t st) {
+    const PackLayout<float> pl(n);
+    const int OB = pl.top;
+    for (int o0 = 0; o0 < n; o0 += OB) {
+        const int nb = std::min(OB, n - o0);
+        const int64_t qoff = (int64_t)(o0 / OB) * OB * OB, doff = (int64_t)(o0 / 128) * 128 * 128;
+        int rc = dag_launch(0, const_cast<float*>(L) + (int64_t)o0 * lda + o0, lda, sA, nb, pack, pl.total, pl.wtop() + qoff,
+                            pl.wtopT() + qoff, -1, pl.dinv + doff, pl.dinvT + doff, pl.sync, OB, 0, nullptr, 0, S, st);
+        if (rc != MXF_OK) return rc;
+    }
+    return mxf_transpose(MXF_F32, L, lda, sA, pack + pl.lt, pl.ldt, pl.total, S, n, n, st);
+}
+
 template <typename T>
 static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* info, T* pack, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        return potrf_packed_f32(A, lda, sA, S, n, info, pack, st);
+    } else {
     constexpr int NB = TriBlock<T>::NB;
     const PackLayout<T> pl(n);
     const size_t smem = diag_smem<T>();
@@ -497,10 +583,14 @@ static int potrf_packed_impl(T* A, int64_t lda, int64_t sA, int S, int n, int* i
         if (rc != MXF_OK) return rc;
     }
     return after_launch(launches);
+    }
 }
 
 template <typename T>
 static int tri_pack_impl(const T* L, int64_t lda, int64_t sA, int S, int n, T* pack, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        return tri_pack_f32(L, lda, sA, S, n, pack, st);
+    } else {
     constexpr int NB = TriBlock<T>::NB;
     const PackLayout<T> pl(n);
     const size_t smem = diag_smem<T>();
@@ -513,6 +603,7 @@ static int tri_pack_impl(const T* L, int64_t lda, int64_t sA, int S, int n, T* p
     rc = build_inverse_levels<T>(L, lda, sA, S, n, pack, pl, st);
     if (rc != MXF_OK) return rc;
     return after_launch(1);
+    }
 }
 
 // ---- hierarchical inverse blocks -------------------------------------------------------------------------------
@@ -555,6 +646,9 @@ transpose_blocks_kernel(const T* __restrict__ src, T* __restrict__ dst, int b) {
 template <typename T>
 static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int n, T* pack, const PackLayout<T>& pl,
                                 cudaStream_t st, int row0, int nrows) {
+    if constexpr (sizeof(T) == 4) {
+        return MXF_OK;
+    } else {
     constexpr int NB = TriBlock<T>::NB;
     if (pl.top == NB) return MXF_OK;
     if (nrows < 0) nrows = n;
@@ -587,6 +681,7 @@ static int build_inverse_levels(const T* L, int64_t lda, int64_t sA, int S, int 
         ++launches;
     }
     return after_launch(launches);
+    }
 }
 
 // Out-of-place solve with the top-level inverse blocks: X = op(L)^-1 B in (n / top) block steps, each one or two large
@@ -599,26 +694,28 @@ static int trsm_packed_oop_impl(int transpose, int n, int nrhs, const T* L, int6
     const int top = pl.top;
     if (!transpose) {
         for (int k0 = 0; k0 < n; k0 += top) {
-            const T* Wk = pack + pl.lvl[pl.nlvl - 1] + (int64_t)(k0 / top) * top * top;
-            int rc = gemm_any<T>(0, 0, top, nrhs, top, 1.0, Wk, top, sP, B + (int64_t)k0 * ldb, ldb, sB, 0.0,
+            const int kb = std::min(top, n - k0);
+            const T* Wk = pack + pl.wtop() + (int64_t)(k0 / top) * top * top;
+            int rc = gemm_any<T>(0, 0, kb, nrhs, kb, 1.0, Wk, top, sP, B + (int64_t)k0 * ldb, ldb, sB, 0.0,
                                  X + (int64_t)k0 * ldx, ldx, sX, S, 2, st, 0);
             if (rc != MXF_OK) return rc;
-            const int below = n - k0 - top;
+            const int below = n - k0 - kb;
             if (below > 0) {
-                rc = gemm_any<T>(0, 0, below, nrhs, top, -1.0, L + (int64_t)(k0 + top) * lda + k0, lda, sA,
-                                 X + (int64_t)k0 * ldx, ldx, sX, 1.0, B + (int64_t)(k0 + top) * ldb, ldb, sB, S, 0, st, 0);
+                rc = gemm_any<T>(0, 0, below, nrhs, kb, -1.0, L + (int64_t)(k0 + kb) * lda + k0, lda, sA,
+                                 X + (int64_t)k0 * ldx, ldx, sX, 1.0, B + (int64_t)(k0 + kb) * ldb, ldb, sB, S, 0, st, 0);
                 if (rc != MXF_OK) return rc;
             }
         }
     } else {
         const T* LT = pack + pl.lt;
-        for (int k0 = n - top; k0 >= 0; k0 -= top) {
-            const T* Wk = pack + pl.topT + (int64_t)(k0 / top) * top * top;
-            int rc = gemm_any<T>(0, 0, top, nrhs, top, 1.0, Wk, top, sP, B + (int64_t)k0 * ldb, ldb, sB, 0.0,
+        for (int k0 = ((n - 1) / top) * top; k0 >= 0; k0 -= top) {
+            const int kb = std::min(top, n - k0);
+            const T* Wk = pack + pl.wtopT() + (int64_t)(k0 / top) * top * top;
+            int rc = gemm_any<T>(0, 0, kb, nrhs, kb, 1.0, Wk, top, sP, B + (int64_t)k0 * ldb, ldb, sB, 0.0,
                                  X + (int64_t)k0 * ldx, ldx, sX, S, 4, st, 0);
             if (rc != MXF_OK) return rc;
             if (k0 > 0) {
-                rc = gemm_any<T>(0, 0, k0, nrhs, top, -1.0, LT + k0, pl.ldt, sP, X + (int64_t)k0 * ldx, ldx, sX, 1.0, B, ldb,
+                rc = gemm_any<T>(0, 0, k0, nrhs, kb, -1.0, LT + k0, pl.ldt, sP, X + (int64_t)k0 * ldx, ldx, sX, 1.0, B, ldb,
                                  sB, S, 0, st, 0);
                 if (rc != MXF_OK) return rc;
             }
@@ -774,6 +871,8 @@ extern "C" int mxf_debug_set_prof(void* dev_ptr) {
     long long* p = (long long*)dev_ptr;
     return (int)cudaMemcpyToSymbol(g_prof, &p, sizeof(p));
 }
+
+extern "C" int mxf_debug_set_dag_prof(void* dev_ptr) { return dag_set_prof((long long*)dev_ptr); }
 
 extern "C" int mxf_tri_block(int dtype) { return dtype == MXF_F64 ? TriBlock<double>::NB : TriBlock<float>::NB; }
 

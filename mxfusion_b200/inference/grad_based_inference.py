@@ -23,7 +23,6 @@ class GradBasedInference(Inference):
         loop_kw = {k: kwargs.pop(k) for k in ('max_steps', 'on_step') if k in kwargs}
         names = self.observed_variable_names
         self.initialize(**{k: kwargs[k] for k in names})
-        self._apply_loaded()
         infr = self.create_executor()
         if isinstance(self._grad_loop, MinibatchInferenceLoop):
             import torch

@@ -86,6 +86,7 @@ class Inference(object):
             self.params.update_constants(discover_shape_constants(shapes, self._graphs))
         self._initialize_params()
         self._initialized = True
+        self._apply_loaded()
 
     def _to_device(self, d):
         t = torch.as_tensor(d)
@@ -118,8 +119,12 @@ class Inference(object):
                 zf.writestr(name, buf.getvalue())
 
     def load(self, zip_filename=DEFAULT_ZIP):
-        """Restores parameter values saved by `save` into this (already constructed, same-topology)
-        inference.  Variables are matched by graph position + name (UUIDs differ between processes)."""
+        """Restores parameter values saved by `save` into this (already constructed) inference.  UUIDs differ between
+        processes, so the saved graphs are reconciled with the current ones (factor_graph.py:479-590 does this by name
+        and topology): within a graph, components are matched by (type, name) -- independent of the order in which the
+        model was written down -- and components that share a (type, name) pair by their order of appearance.  Any
+        component, parameter or shape that does not match raises SerializationError; nothing is skipped silently.
+        The values are applied ONCE: right away if the inference is initialised, else at the end of `initialize`."""
         with zipfile.ZipFile(zip_filename, 'r') as zf:
             version = json.loads(zf.read(FILENAMES['version_file']))
             if version['serialization_version'] != SERIALIZATION_VERSION:
@@ -127,30 +132,61 @@ class Inference(object):
                                          "the same.")
             graphs = json.loads(zf.read(FILENAMES['graphs']))
             arrays = dict(np.load(io.BytesIO(zf.read(FILENAMES['mxnet_params']))))
+        if len(graphs) != len(self._graphs):
+            raise SerializationError("saved inference holds %d graphs, this one %d" % (len(graphs), len(self._graphs)))
         uuid_map = {}
         for saved, cur in zip(graphs, self._graphs):
-            cur_json = cur.as_json()
-            for a, b in zip(saved['components'], cur_json['components']):
-                if a['type'] != b['type'] or a['name'] != b['name']:
-                    raise SerializationError("saved graph does not match the current graph at component %s / %s"
-                                             % (a, b))
-                uuid_map[a['uuid']] = b['uuid']
-            for sm, cm in zip([c for c in saved['components'] if 'graphs' in c],
-                              [c for c in cur_json['components'] if 'graphs' in c]):
-                for sg, cg in zip(sm['graphs'], cm['graphs']):
-                    for a, b in zip(sg['components'], cg['components']):
-                        uuid_map[a['uuid']] = b['uuid']
-        self._loaded_arrays = {uuid_map.get(k, k): v for k, v in arrays.items()}
+            _reconcile_components(saved['components'], cur.as_json()['components'], uuid_map,
+                                  saved.get('name') or saved.get('class'))
+        unknown = [k for k in arrays if k not in uuid_map]
+        if unknown:
+            raise SerializationError("saved parameters %s belong to no component of the saved graphs" % unknown[:3])
+        self._loaded_arrays = {uuid_map[k]: v for k, v in arrays.items()}
         if self._initialized:
             self._apply_loaded()
 
     def _apply_loaded(self):
+        """Copies the loaded values into the parameters and forgets them, so that later `run` calls continue from the
+        trained state instead of being reset to the checkpoint."""
         loaded = getattr(self, '_loaded_arrays', None)
         if not loaded:
             return
-        for uuid, p in self.params.param_dict.items():
-            if uuid in loaded and tuple(loaded[uuid].shape) == tuple(p.tensor.shape):
-                p.set_data(torch.as_tensor(loaded[uuid]))
+        self._loaded_arrays = None
+        missing = [u for u in loaded if u not in self.params.param_dict]
+        if missing:
+            raise SerializationError("%d saved parameters have no counterpart in this inference (first: %s)"
+                                     % (len(missing), missing[0]))
+        for uuid, value in loaded.items():
+            p = self.params.param_dict[uuid]
+            if tuple(value.shape) != tuple(p.tensor.shape):
+                raise SerializationError("saved parameter %s has shape %s, the current one %s"
+                                         % (uuid, tuple(value.shape), tuple(p.tensor.shape)))
+            p.set_data(torch.as_tensor(value))
+
+
+def _reconcile_components(saved, cur, uuid_map, where):
+    """saved / cur: `as_json()['components']` lists of one graph.  Fills uuid_map[saved uuid] = current uuid."""
+    from collections import Counter
+
+    def key(c):
+        return (c['type'], c['name'])
+    if Counter(key(c) for c in saved) != Counter(key(c) for c in cur):
+        only_saved = sorted(str(k) for k in (Counter(key(c) for c in saved) - Counter(key(c) for c in cur)))
+        only_cur = sorted(str(k) for k in (Counter(key(c) for c in cur) - Counter(key(c) for c in saved)))
+        raise SerializationError("saved graph %r does not match the current graph: only saved %s, only current %s"
+                                 % (where, only_saved[:4], only_cur[:4]))
+    by_key, taken = {}, Counter()
+    for c in cur:
+        by_key.setdefault(key(c), []).append(c)
+    for a in saved:
+        b = by_key[key(a)][taken[key(a)]]
+        taken[key(a)] += 1
+        uuid_map[a['uuid']] = b['uuid']
+        ga, gb = a.get('graphs', []), b.get('graphs', [])
+        if len(ga) != len(gb):
+            raise SerializationError("module %s holds %d graphs in the archive, %d now" % (key(a), len(ga), len(gb)))
+        for sg, cg in zip(ga, gb):
+            _reconcile_components(sg['components'], cg['components'], uuid_map, '%s/%s' % (where, a['name']))
 
 
 class TransferInference(Inference):

@@ -649,3 +649,85 @@ def test_normal_draw_multi(cuda, prec):
     ws3 = ops.normal_draw_multi([(m.detach(), v.detach(), S) for m, v in zip(ms, vs)], seed=3,
                                 offsets=list(range(1, len(shapes) + 1)), step_counter=ctr)
     assert torch.equal(ws3[2], ws[2].detach())
+
+
+@pytest.mark.parametrize('n', [1, 5, 64, 100, 128, 192, 257, 512, 1000, 1024])
+def test_potrf_dataflow_factor_and_inverse(cuda, n):
+    """f32, n <= 1024: the single-launch tile-dataflow kernel (csrc/chol_dag.cu) returns the factor AND its explicit
+    inverse W = L^-1 / W^T in the pack (the operands that make every later trsm one GEMM); an ill-conditioned RBF Gram
+    matrix (the bench's Kuu with jitter 1e-6 has cond ~1e6) keeps the LAPACK-class backward error."""
+    from mxfusion_b200 import _raw, _lib
+    rng = np.random.RandomState(23)
+    S = 3
+    Z = rng.uniform(-3, 3, (S, n, 4))
+    r2 = ((Z[:, :, None, :] - Z[:, None, :, :]) ** 2).sum(-1)
+    A = np.exp(-0.5 * r2) + 1e-4 * np.eye(n)[None]
+    At = T(A, cuda, torch.float32)
+    A32 = At.cpu().numpy().astype(np.float64)
+    L, info, pack = _raw.potrf_packed_(At.clone())
+    assert info.cpu().tolist() == [0] * S
+    got = L.cpu().numpy().astype(np.float64)
+    assert np.all(np.triu(got, 1) == 0)
+    # backward error of the factorisation (what LAPACK guarantees): |L L^T - A| <= c n eps |L||L^T|
+    resid = np.abs(got @ np.swapaxes(got, -1, -2) - A32)
+    bound = np.abs(got) @ np.abs(np.swapaxes(got, -1, -2))
+    assert np.max(resid) <= 4 * 6e-8 * max(8, np.sqrt(n)) * np.max(bound), np.max(resid) / np.max(bound)
+    NB = 128
+    nblk, ldt = (n + NB - 1) // NB, (n + 3) & ~3
+    top = _lib.lib().mxf_tri_top_block(_lib.dtype_code(L), n)
+    assert top == max(4, ldt)
+    off = (2 * nblk * NB * NB + n * ldt + 3) & ~3
+    pk = pack.cpu().numpy().astype(np.float64)
+    W = pk[:, off:off + top * top].reshape(S, top, top)[:, :n, :n]
+    WT = pk[:, off + top * top:off + 2 * top * top].reshape(S, top, top)[:, :n, :n]
+    np.testing.assert_array_equal(WT, np.swapaxes(W, -1, -2))
+    assert np.all(np.triu(W, 1) == 0)
+    # W is the inverse of the computed factor: |W L - I| small relative to |W||L|
+    eye = np.eye(n)[None]
+    res = np.abs(W @ got - eye)
+    bnd = np.abs(W) @ np.abs(got)
+    assert np.max(res) <= 4 * 6e-8 * max(8, n ** 0.5) * np.max(bnd), np.max(res) / np.max(bnd)
+    # the inverse-only mode (pack of an existing factor) gives the same blocks
+    pk2 = _raw.tri_pack(L).cpu().numpy().astype(np.float64)
+    W2 = pk2[:, off:off + top * top].reshape(S, top, top)[:, :n, :n]
+    np.testing.assert_allclose(W2, W, rtol=1e-4, atol=1e-5 * np.max(np.abs(W)))
+
+
+def test_potrf_dataflow_two_concurrent_streams_and_graph(cuda):
+    """Two factorisations on two streams inside one captured CUDA graph (the SVGP step runs chol(Kuu) and chol(S) this way):
+    the ticket order makes the schedule independent of how many CTAs of each launch are resident."""
+    from mxfusion_b200 import _raw
+    rng = np.random.RandomState(24)
+    n = 1024
+    Ws = rng.randn(2, n, n) / np.sqrt(n)
+    A = Ws @ np.swapaxes(Ws, -1, -2) + 0.1 * np.eye(n)[None]
+    want = np.linalg.cholesky(A)
+    A0, A1 = T(A[:1], cuda, torch.float32), T(A[1:], cuda, torch.float32)
+    B0, B1 = A0.clone(), A1.clone()
+    p0, p1 = _raw.new_pack(B0), _raw.new_pack(B1)
+    i0 = torch.zeros((1,), dtype=torch.int32, device=cuda)
+    i1 = torch.zeros((1,), dtype=torch.int32, device=cuda)
+    side, main = torch.cuda.Stream(device=cuda), torch.cuda.Stream(device=cuda)
+
+    def body():
+        B0.copy_(A0)
+        B1.copy_(A1)
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            _raw.potrf_packed_(B1, i1, p1)
+        _raw.potrf_packed_(B0, i0, p0)
+        cur.wait_stream(side)
+    main.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(main):
+        body()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=main):
+        body()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert i0.item() == 0 and i1.item() == 0
+    np.testing.assert_allclose(B0.cpu().numpy()[0], want[0], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(B1.cpu().numpy()[0], want[1], rtol=2e-4, atol=2e-5)

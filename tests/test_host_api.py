@@ -213,3 +213,79 @@ def test_inference_save_load_round_trip(mf, tmp_path):
     for a, b in ((m.kernel.variance, m2.kernel.variance), (m.kernel.lengthscale, m2.kernel.lengthscale),
                  (m.noise_var, m2.noise_var)):
         np.testing.assert_allclose(infr2.params[b].numpy(), infr.params[a].numpy(), rtol=1e-12)
+
+
+def test_load_is_applied_once_and_training_continues(mf, tmp_path):
+    """A checkpoint is applied once (at load, or at the end of initialize when loaded before it): later run() calls
+    continue from the trained state instead of being reset to the archive."""
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    m, X, Y = gp_notebook_model(mf)
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]))
+    infr.run(X=X, Y=Y, max_iter=10, learning_rate=0.05)
+    path = str(tmp_path / 'ckpt.zip')
+    infr.save(path)
+    saved_noise = float(infr.params[m.noise_var])
+    # load BEFORE initialize: picked up by initialize()
+    m2, _, _ = gp_notebook_model(mf)
+    infr2 = GradBasedInference(inference_algorithm=MAP(model=m2, observed=[m2.X, m2.Y]))
+    infr2.load(path)
+    infr2.initialize(X=X.shape, Y=Y.shape)
+    np.testing.assert_allclose(float(infr2.params[m2.noise_var]), saved_noise, rtol=1e-12)
+    infr2.run(X=X, Y=Y, max_iter=30, learning_rate=0.05)
+    trained = float(infr2.params[m2.noise_var])
+    assert abs(trained - saved_noise) > 1e-6
+    infr2.run(X=X, Y=Y, max_iter=1, learning_rate=1e-9)
+    np.testing.assert_allclose(float(infr2.params[m2.noise_var]), trained, rtol=1e-6)   # not reset to the checkpoint
+    # the plain Inference.run path sees a checkpoint loaded before initialize as well
+    from mxfusion_b200.inference import Inference
+    m3, _, _ = gp_notebook_model(mf)
+    infr3 = Inference(MAP(model=m3, observed=[m3.X, m3.Y]))
+    infr3.load(path)
+    infr3.run(X=X, Y=Y)
+    np.testing.assert_allclose(float(infr3.params[m3.noise_var]), saved_noise, rtol=1e-12)
+
+
+def test_load_matches_by_name_and_rejects_mismatches(mf, tmp_path):
+    from mxfusion_b200.common.exceptions import SerializationError
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.components.distributions.gp.kernels import RBF
+    from mxfusion_b200.modules.gp_modules import GPRegression
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    m, X, Y = gp_notebook_model(mf)
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]))
+    infr.run(X=X, Y=Y, max_iter=5, learning_rate=0.05)
+    path = str(tmp_path / 'ckpt.zip')
+    infr.save(path)
+
+    def rebuilt(noise_first, in_dim=1):
+        mm = mf.Model()
+        mm.N = mf.Variable()
+        if noise_first:          # same model written down in another order
+            mm.noise_var = mf.Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=0.01)
+            mm.X = mf.Variable(shape=(mm.N, in_dim))
+        else:
+            mm.X = mf.Variable(shape=(mm.N, in_dim))
+            mm.noise_var = mf.Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=0.01)
+        mm.kernel = RBF(input_dim=in_dim, variance=1, lengthscale=1)
+        mm.Y = GPRegression.define_variable(X=mm.X, kernel=mm.kernel, noise_var=mm.noise_var, shape=(mm.N, 1))
+        return mm
+    m2 = rebuilt(True)
+    infr2 = GradBasedInference(inference_algorithm=MAP(model=m2, observed=[m2.X, m2.Y]))
+    infr2.initialize(X=X.shape, Y=Y.shape)
+    infr2.load(path)
+    for a, b in ((m.kernel.variance, m2.kernel.variance), (m.kernel.lengthscale, m2.kernel.lengthscale),
+                 (m.noise_var, m2.noise_var)):
+        np.testing.assert_allclose(infr2.params[b].numpy(), infr.params[a].numpy(), rtol=1e-12)
+    # a parameter whose shape changed is an error, not a skip
+    m3 = rebuilt(False, in_dim=1)
+    m3.extra = mf.Variable(shape=(2,), initial_value=np.zeros(2))
+    infr3 = GradBasedInference(inference_algorithm=MAP(model=m3, observed=[m3.X, m3.Y]))
+    infr3.initialize(X=X.shape, Y=Y.shape)
+    with pytest.raises(SerializationError):
+        infr3.load(path)
+    X5 = np.random.rand(5, 1)
+    m4 = rebuilt(False)
+    infr4 = GradBasedInference(inference_algorithm=MAP(model=m4, observed=[m4.X, m4.Y]))
+    infr4.initialize(X=X5.shape, Y=(5, 1))           # cached posterior quantities now have N = 5, the archive N = 20
+    with pytest.raises(SerializationError):
+        infr4.load(path)
