@@ -122,6 +122,16 @@ int mxf_potrf_packed(int dtype, void* A, int64_t lda, int64_t sA, int S, int n, 
 int mxf_trsm_packed(int dtype, int transpose, int n, int nrhs, double alpha, const void* L, int64_t lda, int64_t sA,
                     const void* pack, int64_t sP, void* B, int64_t ldb, int64_t sB, int S, void* stream);
 
+/* acc[0] = max(acc[0], max_i |info[i]|): folds the `info` of the factorisations of a step (first non-positive pivot,
+ * 1-based; the reference surfaces a non-PD matrix as an MXNetError at its next synchronisation) into
+ * one device int that the host reads every few steps and maps to InferenceError (common/exceptions.py:20). */
+int mxf_info_max(int* acc, const int* info, int n, void* stream);
+
+/* Element offsets of the pieces of a factor's pack (per sample): out[0..7] = {Dinv, DinvT, L^T, W, W^T, top, ldt, nq}.
+ * W / W^T are nq blocks of top x top elements (row stride top) holding the explicit inverse of the factor's diagonal
+ * blocks of size top (f32, n <= 1024: ONE block, W = L^-1 -- written by the single-launch tile-dataflow potrf). */
+int mxf_tri_pack_layout(int dtype, int n, int64_t* out);
+
 /* When n is a multiple of 2*NB the pack also holds hierarchically built inverses of larger diagonal blocks
  * ([[Wa,0],[-Wc Lca Wa, Wc]], doubling from NB up to mxf_tri_top_block(dtype, n) <= 512, env MXF_TRI_INV) and their
  * transposes.  mxf_trsm_packed_oop then solves in n/top block steps of one or two LARGE GEMMs each (the triangular
@@ -136,6 +146,14 @@ int mxf_trsm_packed_oop(int dtype, int transpose, int n, int nrhs, const void* L
  * symmetric matrix whose lower triangle (diagonal included) is copied from P. */
 int mxf_copy_ltu(int dtype, const void* P, int64_t ldp, int64_t sP,
                  void* out, int64_t ldo, int64_t sO, int S, int n, void* stream);
+/* Same with the lower triangle taken from the SUM of `parts` matrices P + g * sPart (the split-K partial products of
+ * Phi = A A^T, replacing F.sum + the mirror; svgp_regression.py:89-90 as folded in ops.py). */
+int mxf_copy_ltu_sum(int dtype, const void* P, int64_t ldp, int64_t sPart, int parts,
+                     void* out, int64_t ldo, int n, void* stream);
+/* Strided batched 2-D copy dst[s][r][c] = src[s][r][c] (src == NULL: zero fill): the slice assignments around the
+ * solves of svgp_regression.py:85-87 (F.concat / slice_axis in the reference). */
+int mxf_copy2d(int dtype, const void* src, int64_t lds, int64_t sS, void* dst, int64_t ldd, int64_t sD,
+               int S, int rows, int cols, void* stream);
 /* out = alpha * (A + A^T)  (symmetrise; in-place allowed only if out != A is false -> use distinct buffers) */
 int mxf_symmetrize(int dtype, double alpha, const void* A, int64_t lda, int64_t sA,
                    void* out, int64_t ldo, int64_t sO, int S, int n, void* stream);
@@ -173,6 +191,10 @@ int mxf_get_diag(int dtype, const void* A, int64_t lda, int64_t sA, void* out, i
  * learnable parameters or on the upstream gradient never visit the host.  sX/sY/sO batch strides. */
 int mxf_axpby_dev(int dtype, const void* a, const void* X, int64_t sX, const void* b, const void* Y, int64_t sY,
                   void* out, int64_t sO, int S, int64_t n, void* stream);
+/* The same on strided (rows x cols) views: out[s][r][c] = a[s] X[s][r][c] + b[s] Y[s][r][c]; a / b == NULL: 1,
+ * Y == NULL: no second term.  Combines blocks of the solve buffers of svgp_regression.py:85-92 where they lie. */
+int mxf_axpby2d(int dtype, const void* a, const void* X, int64_t ldx, int64_t sX, const void* b, const void* Y,
+                int64_t ldy, int64_t sY, void* out, int64_t ldo, int64_t sO, int S, int rows, int cols, void* stream);
 
 /* Softplus parameter transform (components/variables/var_trans.py:63-91, applied to every constrained
  * parameter on every forward, inference_alg.py:79-80): y = log(1 + exp(x)) + offset, overflow-safe;

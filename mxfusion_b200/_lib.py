@@ -42,6 +42,11 @@ def _declare(lib):
         'mxf_tri_top_block': (i, [i, i]),
         'mxf_trsm_packed_oop': (i, [i, i, i, i, p, l, l, p, l, p, l, l, p, l, l, i, p]),
         'mxf_copy_ltu': (i, [i, p, l, l, p, l, l, i, i, p]),
+        'mxf_copy_ltu_sum': (i, [i, p, l, l, i, p, l, i, p]),
+        'mxf_copy2d': (i, [i, p, l, l, p, l, l, i, i, i, p]),
+        'mxf_axpby2d': (i, [i, p, p, l, l, p, p, l, l, p, l, l, i, i, i, p]),
+        'mxf_tri_pack_layout': (i, [i, i, p]),
+        'mxf_info_max': (i, [p, p, i, p]),
         'mxf_symmetrize': (i, [i, d, p, l, l, p, l, l, i, i, p]),
         'mxf_tril': (i, [i, i, p, l, l, p, l, l, i, i, p]),
         'mxf_transpose': (i, [i, p, l, l, p, l, l, i, i, i, p]),

@@ -198,6 +198,66 @@ def copy_ltu(P, out=None):
     return _sq(lib().mxf_copy_ltu, 'mxf_copy_ltu', P, out=out)
 
 
+def copy_ltu_sum(parts, out=None):
+    """parts (G, n, n): lower triangles of G partial products -> (1, n, n) symmetric sum (one launch)."""
+    require_cuda(parts, out)
+    G, n, _ = parts.shape
+    if out is None:
+        out = torch.empty((1, n, n), dtype=parts.dtype, device=parts.device)
+    check(lib().mxf_copy_ltu_sum(dtype_code(parts), ptr(parts), parts.stride(1), parts.stride(0), G, ptr(out), out.stride(1),
+                                 n, stream_ptr()), 'mxf_copy_ltu_sum')
+    return out
+
+
+def copy2d_(dst, src=None):
+    """dst[s, r, c] = src[s, r, c] for strided (S, rows, cols) views with unit innermost stride; src None: zero fill."""
+    require_cuda(dst, src)
+    S, rows, cols = dst.shape
+    if dst.stride(2) != 1 or (src is not None and (src.stride(2) != 1 or tuple(src.shape) != tuple(dst.shape))):
+        raise _lib.MXFusionB200Error("copy2d_: operands must be (S, rows, cols) views with unit innermost stride")
+    check(lib().mxf_copy2d(dtype_code(dst), ptr(src), 0 if src is None else src.stride(1),
+                           0 if src is None else src.stride(0), ptr(dst), dst.stride(1), dst.stride(0), S, rows, cols,
+                           stream_ptr()), 'mxf_copy2d')
+    return dst
+
+
+_PACK_LAYOUTS = {}
+
+
+def pack_layout(dtype_c, n):
+    """{Dinv, DinvT, LT, W, WT} element offsets + top, ldt, nq of a factor's pack (mxf_tri_pack_layout)."""
+    key = (dtype_c, n)
+    lay = _PACK_LAYOUTS.get(key)
+    if lay is None:
+        import ctypes
+        buf = (ctypes.c_int64 * 8)()
+        check(lib().mxf_tri_pack_layout(dtype_c, n, ctypes.cast(buf, ctypes.c_void_p)), 'mxf_tri_pack_layout')
+        lay = dict(zip(('dinv', 'dinvT', 'lt', 'w', 'wT', 'top', 'ldt', 'nq'), [int(v) for v in buf]))
+        _PACK_LAYOUTS[key] = lay
+    return lay
+
+
+def pack_inverse(pack, like):
+    """(W, WT): the factor's explicit inverse L^-1 and its transpose as (S, n, n) views into `pack` (row stride top), or
+    None when the pack holds no single full-size inverse block (f64 factors, n > 1024)."""
+    S, n, _ = like.shape
+    lay = pack_layout(dtype_code(like), n)
+    if lay['nq'] != 1 or lay['top'] < n:
+        return None
+    top = lay['top']
+    W = pack.as_strided((pack.shape[0], n, n), (pack.stride(0), top, 1), pack.storage_offset() + lay['w'])
+    WT = pack.as_strided((pack.shape[0], n, n), (pack.stride(0), top, 1), pack.storage_offset() + lay['wT'])
+    return W, WT
+
+
+def note_info_(acc, info):
+    """acc[0] = max(acc[0], max |info|) on the device (no synchronisation)."""
+    require_cuda(acc, info)
+    info = _c(info)
+    check(lib().mxf_info_max(ptr(acc), ptr(info), info.numel(), stream_ptr()), 'mxf_info_max')
+    return acc
+
+
 def symmetrize(A, alpha=1.0):
     return _sq(lib().mxf_symmetrize, 'mxf_symmetrize', A, float(alpha))
 
@@ -357,6 +417,31 @@ def axpby_dev(a, X, b=None, Y=None, out=None):
     check(lib().mxf_axpby_dev(dtype_code(X), ptr(a), ptr(X), _bstride(X, S) if X.shape[0] > 1 else 0,
                               ptr(b), ptr(Y), 0 if Y is None else (n if Y.shape[0] > 1 else 0),
                               ptr(out), n, S, n, stream_ptr()), 'mxf_axpby_dev')
+    return out
+
+
+def axpby2d(a, X, b=None, Y=None, out=None):
+    """out = a[s] X + b[s] Y on (S, rows, cols) views with unit innermost stride (any row / batch strides); a, b: device
+    tensors (S,) or None (= 1)."""
+    require_cuda(a, X, b, Y, out)
+    S, rows, cols = X.shape
+    if out is None:
+        out = torch.empty((S, rows, cols), dtype=X.dtype, device=X.device)
+    for t in (X, Y, out):
+        if t is not None and (t.stride(2) != 1 or tuple(t.shape) != (S, rows, cols)):
+            raise _lib.MXFusionB200Error("axpby2d: operands must be (S, rows, cols) views with unit innermost stride")
+
+    def coef(c):
+        if c is None:
+            return None
+        c = _c(c.reshape(-1))
+        if c.numel() != S:
+            raise _lib.MXFusionB200Error("axpby2d: one coefficient per sample expected")
+        return c
+    a, b = coef(a), coef(b)
+    check(lib().mxf_axpby2d(dtype_code(X), ptr(a), ptr(X), X.stride(1), X.stride(0), ptr(b), ptr(Y),
+                            0 if Y is None else Y.stride(1), 0 if Y is None else Y.stride(0), ptr(out), out.stride(1),
+                            out.stride(0), S, rows, cols, stream_ptr()), 'mxf_axpby2d')
     return out
 
 

@@ -905,6 +905,22 @@ extern "C" int mxf_trsm_packed(int dtype, int transpose, int n, int nrhs, double
                                                         sP, (T*)B, ldb, sB, S, (cudaStream_t)stream));
 }
 
+extern "C" int mxf_tri_pack_layout(int dtype, int n, int64_t* out) {
+    if (!out || n <= 0) return MXF_EINVAL;
+    if (dtype == MXF_F64) {
+        const PackLayout<double> pl(n);
+        out[0] = pl.dinv; out[1] = pl.dinvT; out[2] = pl.lt; out[3] = pl.wtop(); out[4] = pl.wtopT(); out[5] = pl.top;
+        out[6] = pl.ldt; out[7] = pl.nq();
+    } else if (dtype == MXF_F32) {
+        const PackLayout<float> pl(n);
+        out[0] = pl.dinv; out[1] = pl.dinvT; out[2] = pl.lt; out[3] = pl.wtop(); out[4] = pl.wtopT(); out[5] = pl.top;
+        out[6] = pl.ldt; out[7] = pl.nq();
+    } else {
+        return MXF_EDTYPE;
+    }
+    return MXF_OK;
+}
+
 extern "C" int mxf_tri_top_block(int dtype, int n) {
     if (n <= 0) return 0;
     return dtype == MXF_F64 ? PackLayout<double>(n).top : PackLayout<float>(n).top;

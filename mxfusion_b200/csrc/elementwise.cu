@@ -615,6 +615,102 @@ extern "C" int mxf_copy_ltu(int dtype, const void* P, int64_t ldp, int64_t sP, v
                                                                (cudaStream_t)stream)));
 }
 
+// out = symmetric matrix whose lower triangle (diagonal included) is the SUM of the lower triangles of the `parts`
+// matrices P[0..parts) (stride sPart): the split-K partial products of Phi = A A^T (svgp_regression.py:89-90 folded,
+// ops.py) are added and mirrored in one pass instead of a reduction launch + a mirror launch.
+template <typename T>
+__global__ void __launch_bounds__(256)
+copy_ltu_sum_kernel(const T* __restrict__ P, int64_t ldp, int64_t sPart, int parts, T* __restrict__ out, int64_t ldo, int n) {
+    __shared__ T tile[32][33];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;       // output tile: rows by.., cols bx..
+    if (bx > by + 31) {
+        // strictly-upper tile: the transposed lower tile (rows bx.., cols by..)
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int ai = bx + r, aj = by + threadIdx.x;
+            T v = T(0);
+            if (ai < n && aj < n)
+                for (int g = 0; g < parts; ++g) v += P[(int64_t)g * sPart + (int64_t)ai * ldp + aj];
+            tile[r][threadIdx.x] = v;
+        }
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int i = by + r, j = bx + threadIdx.x;
+            if (i < n && j < n) out[(int64_t)i * ldo + j] = tile[threadIdx.x][r];
+        }
+        return;
+    }
+    // lower or diagonal tile
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = by + r, j = bx + threadIdx.x;
+        T v = T(0);
+        if (i < n && j < n && j <= i)
+            for (int g = 0; g < parts; ++g) v += P[(int64_t)g * sPart + (int64_t)i * ldp + j];
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = by + r, j = bx + threadIdx.x;
+        if (i >= n || j >= n) continue;
+        out[(int64_t)i * ldo + j] = (j <= i) ? tile[r][threadIdx.x] : tile[threadIdx.x][r];      // diagonal tile: mirror in place
+    }
+}
+
+extern "C" int mxf_copy_ltu_sum(int dtype, const void* P, int64_t ldp, int64_t sPart, int parts, void* out, int64_t ldo,
+                                int n, void* stream) {
+    if (!P || !out || P == out || parts <= 0 || n < 0) return MXF_EINVAL;
+    if (n == 0) return MXF_OK;
+    MXF_DISPATCH_DTYPE(dtype, {
+        dim3 grid(cdiv(n, 32), cdiv(n, 32));
+        launch_pdl(copy_ltu_sum_kernel<T>, grid, dim3(32, 8), (size_t)0, (cudaStream_t)stream, (const T*)P, ldp, sPart, parts,
+                   (T*)out, ldo, n);
+        return after_launch();
+    });
+}
+
+// Strided batched 2-D copy (src == NULL: zero fill): the small right-hand-side blocks that ride along in the solve
+// buffers ([Kuf | Ls | mu], ops.py) without a tensor-library launch.
+template <typename T>
+__global__ void __launch_bounds__(256)
+copy2d_kernel(const T* __restrict__ src, int64_t lds, int64_t sS, T* __restrict__ dst, int64_t ldd, int64_t sD, int rows,
+              int cols) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int s = blockIdx.z;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x)
+            dst[(int64_t)s * sD + (int64_t)r * ldd + c] = src ? src[(int64_t)s * sS + (int64_t)r * lds + c] : T(0);
+}
+
+extern "C" int mxf_copy2d(int dtype, const void* src, int64_t lds, int64_t sS, void* dst, int64_t ldd, int64_t sD, int S,
+                          int rows, int cols, void* stream) {
+    if (!dst || S < 0 || rows < 0 || cols < 0) return MXF_EINVAL;
+    if (S == 0 || rows == 0 || cols == 0) return MXF_OK;
+    if (S > 65535) return MXF_ENOTIMPL;
+    MXF_DISPATCH_DTYPE(dtype, {
+        dim3 grid(std::min(cdiv(cols, 256), 64), std::min(rows, 1024), S);
+        launch_pdl(copy2d_kernel<T>, grid, dim3(256), (size_t)0, (cudaStream_t)stream, (const T*)src, lds, sS, (T*)dst, ldd, sD,
+                   rows, cols);
+        return after_launch();
+    });
+}
+
+// acc[0] = max(acc[0], max_i info[i]): potrf's device-side failure record (first non-positive pivot per sample) folded
+// into one int per device without a host synchronisation; the training loop reads it every few steps.
+__global__ void info_max_kernel(int* __restrict__ acc, const int* __restrict__ info, int n) {
+    int m = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = max(m, info[i] != 0 ? abs(info[i]) : 0);
+    if (m != 0) atomicMax(acc, m);
+}
+
+extern "C" int mxf_info_max(int* acc, const int* info, int n, void* stream) {
+    if (!acc || !info || n < 0) return MXF_EINVAL;
+    if (n == 0) return MXF_OK;
+    info_max_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(acc, info, n);
+    return after_launch();
+}
+
 extern "C" int mxf_symmetrize(int dtype, double alpha, const void* A, int64_t lda, int64_t sA, void* out,
                               int64_t ldo, int64_t sO, int S, int n, void* stream) {
     if (!A || !out || A == out) return MXF_EINVAL;

@@ -214,6 +214,37 @@ extern "C" int mxf_axpby_dev(int dtype, const void* a, const void* X, int64_t sX
     return after_launch();
 }
 
+// out[s][r][c] = a[s] X[s][r][c] + b[s] Y[s][r][c] on strided (rows x cols) views: the blocks of the solve buffers are
+// combined where they lie (no contiguous copies).  a == NULL: 1, b == NULL: 1 (Y == NULL: no second term).
+template <typename T>
+__global__ void __launch_bounds__(256)
+axpby2d_kernel(const T* __restrict__ a, const T* __restrict__ X, int64_t ldx, int64_t sX, const T* __restrict__ b,
+               const T* __restrict__ Y, int64_t ldy, int64_t sY, T* __restrict__ out, int64_t ldo, int64_t sO, int rows,
+               int cols) {
+    const int s = blockIdx.z;
+    const T av = a ? a[s] : T(1);
+    const T bv = b ? b[s] : T(1);
+    for (int r = blockIdx.y; r < rows; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+            T v = av * X[(int64_t)s * sX + (int64_t)r * ldx + c];
+            if (Y) v = fma(bv, Y[(int64_t)s * sY + (int64_t)r * ldy + c], v);
+            out[(int64_t)s * sO + (int64_t)r * ldo + c] = v;
+        }
+}
+
+extern "C" int mxf_axpby2d(int dtype, const void* a, const void* X, int64_t ldx, int64_t sX, const void* b, const void* Y,
+                           int64_t ldy, int64_t sY, void* out, int64_t ldo, int64_t sO, int S, int rows, int cols,
+                           void* stream) {
+    if (!X || !out || S < 0 || rows < 0 || cols < 0) return MXF_EINVAL;
+    if (S == 0 || rows == 0 || cols == 0) return MXF_OK;
+    if (S > 65535) return MXF_ENOTIMPL;
+    dim3 grid((unsigned)std::min<int64_t>((cols + 255) / 256, 64), (unsigned)std::min(rows, 2048), (unsigned)S);
+    MXF_DISPATCH_DTYPE(dtype, axpby2d_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                  (const T*)a, (const T*)X, ldx, sX, (const T*)b, (const T*)Y, ldy, sY, (T*)out, ldo, sO, rows,
+                                  cols));
+    return after_launch();
+}
+
 extern "C" int mxf_softplus_fwd(int dtype, const void* x, double offset, void* y, int64_t n, void* stream) {
     if (!x || !y || n < 0) return MXF_EINVAL;
     if (n == 0) return MXF_OK;

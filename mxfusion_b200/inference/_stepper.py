@@ -33,6 +33,8 @@ class Stepper(object):
         from ..components.distributions import random_gen
         random_gen.set_step_counter(params.adam_t if params.adam_t.is_cuda else None)
         self.static_in = [torch.empty_like(b) for b in example_batch]
+        if self.static_in and self.static_in[0].is_cuda:
+            ops.info_accumulator(self.static_in[0].device)        # created eagerly, never inside a graph capture
         self.loss = None
         self.graph = None
         self.use_graph = bool(use_cuda_graph) and self.static_in[0].is_cuda if self.static_in else False

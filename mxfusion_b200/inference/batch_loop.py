@@ -1,6 +1,7 @@
 """Full-batch gradient loop (mxfusion/inference/batch_loop.py:19-61)."""
 from .grad_loop import GradLoop
 from ._stepper import Stepper
+from .. import ops
 
 
 class BatchInferenceLoop(GradLoop):
@@ -17,8 +18,13 @@ class BatchInferenceLoop(GradLoop):
             dst.copy_(src)
         iter_step = max(max_iter // n_prints, 1)
         loss = None
+        check_every = max(1, min(100, iter_step))
+        dev = data[0].device if data else None
         for i in range(max_iter):
             loss = stepper.step()
+            if dev is not None and ((i + 1) % check_every == 0 or i == max_iter - 1):
+                # non-PD factorisations are recorded on the device; read back every few steps (no per-step sync)
+                ops.check_factorisations(dev, "a Cholesky factorisation at iteration %d" % (i + 1))
             if verbose:
                 print('\rIteration {} loss: {}\t\t\t\t'.format(i + 1, float(loss)), end='')
                 if ((i + 1) % iter_step == 0 and i > 0) or i == max_iter - 1:

@@ -116,6 +116,9 @@ class MinibatchInferenceLoop(GradLoop):
             if verbose:
                 print('epoch-loss: {} '.format(float(loss_acc) / max(nfull, 1)))
             epoch_losses.append(loss_acc / max(nfull, 1))
+            # a non-positive-definite factorisation is recorded on the device by the bounds; surfaced once per epoch
+            # (the reference gets an MXNetError at its per-step asscalar(), minibatch_loop.py:92)
+            ops.check_factorisations(dev, "a Cholesky factorisation during epoch %d" % (e + 1))
             if max_steps is not None and steps_done >= max_steps:
                 break
         self.last_stepper = stepper

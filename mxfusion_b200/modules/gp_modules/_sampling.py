@@ -15,7 +15,6 @@ from ...components.distributions.random_gen import MXNetRandomGenerator
 from ...components.distributions.normal import Normal
 from ...components.distributions.gp import GaussianProcess, ConditionalGaussianProcess
 from ...components.variables.variable import Variable
-from ...util.inference import realize_shape
 from ... import ops
 
 
@@ -23,11 +22,17 @@ def _gen(alg):
     return alg._rand_gen if alg._rand_gen is not None else MXNetRandomGenerator
 
 
+def _y_shape(model, X):
+    """(N, P): the modules define Y with the rows of X and a fixed output dimension (gp_regression.py:320-327)."""
+    return (X.shape[-2], int(model.Y.shape[-1]))
+
+
 class GPRegressionSampling(SamplingAlgorithm):
-    def __init__(self, model, observed, num_samples=1, target_variables=None, rand_gen=None):
+    def __init__(self, model, observed, num_samples=1, target_variables=None, rand_gen=None, dtype=None):
         super(GPRegressionSampling, self).__init__(model=model, observed=observed, num_samples=num_samples,
                                                    target_variables=target_variables)
         self._rand_gen = rand_gen
+        self._dtype = dtype
 
     def compute(self, F, variables):
         X = variables[self.model.X]
@@ -39,9 +44,9 @@ class GPRegressionSampling(SamplingAlgorithm):
         K = kern.K(F, X, **kern_params) + \
             torch.eye(N, dtype=X.dtype, device=X.device).unsqueeze(0) * noise_var.unsqueeze(-2)      # :112-114
         L = ops.potrf(K)
-        Y_shape = realize_shape(self.model.Y.shape, variables)
+        Y_shape = _y_shape(self.model, X)
         out_shape = (self.num_samples,) + tuple(Y_shape)
-        die = _gen(self).sample_normal(shape=out_shape, dtype=self.model.Y_dtype, ctx=X.device)
+        die = _gen(self).sample_normal(shape=out_shape, dtype=self._dtype, ctx=X.device)
         y = ops.gemm2(L.expand((self.num_samples,) + tuple(L.shape[1:])), die)                     # trmm(L, die)
         if getattr(self.model, 'has_mean', False):
             y = y + variables[self.model.mean]
@@ -65,7 +70,7 @@ class InducingGPSampling(SamplingAlgorithm):
         kern = m.kernel
         kern_params = kern.fetch_parameters(variables)
         X, Z, noise_var, kern_params = arrays_as_samples(F, [X, Z, noise_var, kern_params])
-        Y_shape = tuple(realize_shape(m.Y.shape, variables))
+        Y_shape = _y_shape(m, X)
         S, gen, dt = self.num_samples, _gen(self), self._dtype
         # the three factors of the reference's inner graph, stand-alone (only their draw_samples_impl is used)
         gp_u = GaussianProcess(X=Variable(shape=Z.shape[1:]), kernel=kern, rand_gen=gen, dtype=dt)

@@ -176,6 +176,10 @@ class GPRegression(Module):
                                        algorithm=GPRegressionLogPdf(self._module_graph, self._extra_graphs[0],
                                                                     observed), alg_name='gp_log_pdf')
         observed = [v for _, v in self.inputs]
+        from ._sampling import GPRegressionSampling
+        self.attach_draw_samples_algorithms(targets=self.output_names, conditionals=self.input_names,
+                                            algorithm=GPRegressionSampling(self._module_graph, observed, rand_gen=self._rand_gen,
+                                                         dtype=self.dtype), alg_name='gp_sampling')
         self.attach_prediction_algorithms(targets=self.output_names, conditionals=self.input_names,
                                           algorithm=GPRegressionMeanVariancePrediction(
                                               self._module_graph, self._extra_graphs[0], observed),

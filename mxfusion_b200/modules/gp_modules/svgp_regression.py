@@ -196,6 +196,10 @@ class SVGPRegression(Module):
                                        algorithm=SVGPRegressionLogPdf(self._module_graph, self._extra_graphs[0],
                                                                       observed), alg_name='svgp_log_pdf')
         observed = [v for _, v in self.inputs]
+        from ._sampling import InducingGPSampling
+        self.attach_draw_samples_algorithms(targets=self.output_names, conditionals=self.input_names,
+                                            algorithm=InducingGPSampling(self._module_graph, observed, rand_gen=self._rand_gen,
+                                                         dtype=self.dtype), alg_name='svgp_sampling')
         self.attach_prediction_algorithms(targets=self.output_names, conditionals=self.input_names,
                                           algorithm=SVGPRegressionMeanVariancePrediction(
                                               self._module_graph, self._extra_graphs[0], observed),

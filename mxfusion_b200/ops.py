@@ -85,6 +85,7 @@ class _Potrf(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A):
         L, info, pack = R.potrf_packed_(A.clone())
+        _note_info(info)
         ctx.save_for_backward(L, pack)
         ctx.mark_non_differentiable(info)
         return L, info
@@ -331,60 +332,69 @@ class _SVGPLogPdf(torch.autograd.Function):
         dt, dev = X.dtype, X.device
         PP = (P + 3) & ~3                                       # keep every row stride a multiple of 4 elements
         Kuu = R.kbuild_fwd(kind, Z, None, ls, kvar, diag_const=jitter)
-        # all right-hand sides of the solves with L ride in ONE buffer [Kuf | Ls | mu]: one GEMM chain, not three
+        # all right-hand sides of the solves with L ride in ONE buffer [Kuf | Ls | mu]: one GEMM, not three.  S = W W^T +
+        # diag is formed and factored IN PLACE inside that buffer (the factorisation takes any row stride), so Ls never
+        # has to be copied into it.  Padding columns stay uninitialised: a GEMM column only depends on its own column.
         RH = torch.empty((S, M, B + M + PP), dtype=dt, device=dev)
-        R.kbuild_fwd(kind, Z, X, ls, kvar, out=RH[:, :, :B])    # Kuf (:73)
-        Sm = R.gemm(W, W, transB=True, tri=True)                # :76 syrk (lower tiles) ...
-        R.add_diag_(Sm, dvec)                                   # ... + make_diagonal
+        Sm = RH[:, :, B:B + M]
         pk, pks = R.new_pack(Kuu), R.new_pack(Sm)
         info = torch.empty((2, S), dtype=torch.int32, device=dev)
+        Sinv_l = torch.empty((S, M, M), dtype=dt, device=dev)
+        Sinv = torch.empty((S, M, M), dtype=dt, device=dev)
         side = _side_stream(dev)
+
+        def s_branch():
+            R.gemm(W, W, transB=True, beta=0.0, C=Sm, tri=1)    # :76 syrk (lower tiles) ...
+            R.add_diag_(Sm, dvec)                               # ... + make_diagonal
+            R.potrf_packed_(Sm, info[1], pks)                   # :84
         # S^-1 = Ls^-T Ls^-1 is only needed by the adjoint (d logdet S), but it depends on nothing else: it is
         # computed here, on the side stream, while the main stream factors Kuu and runs the solves with L
-        eyeS = torch.eye(M, dtype=dt, device=dev).unsqueeze(0).repeat(S, 1, 1)
-        LsT = torch.empty((S, M, M), dtype=dt, device=dev)
-        Sinv_l = torch.zeros((S, M, M), dtype=dt, device=dev)
-        Sinv = torch.empty((S, M, M), dtype=dt, device=dev)
-        Ls_copy = torch.empty((S, M, M), dtype=dt, device=dev)
         if side is not None:                                    # the two factorisations are independent: overlap them
             cur = torch.cuda.current_stream()
             side.wait_stream(cur)
             join_ls = torch.cuda.Event()
             with torch.cuda.stream(side):
-                R.potrf_packed_(Sm, info[1], pks)               # :84
-                Ls_copy.copy_(Sm)
-                join_ls.record()
-                _sinv_chain(Sm, pks, eyeS, LsT, Sinv_l, Sinv)
+                s_branch()
+                if R.pack_inverse(pks, Sm) is not None:
+                    join_ls.record()                            # S^-1 only reads the pack: the solves need not wait for it
+                    _sinv_chain(Sm, pks, Sinv_l, Sinv)
+                else:
+                    _sinv_chain(Sm, pks, Sinv_l, Sinv)          # reads Ls, which an in-place solve below overwrites
+                    join_ls.record()
+            R.kbuild_fwd(kind, Z, X, ls, kvar, out=RH[:, :, :B])    # Kuf (:73)
+            R.copy2d_(RH[:, :, B + M:B + M + P], mu)
             R.potrf_packed_(Kuu, info[0], pk)                   # :83
             cur.wait_event(join_ls)
         else:
+            R.kbuild_fwd(kind, Z, X, ls, kvar, out=RH[:, :, :B])
+            R.copy2d_(RH[:, :, B + M:B + M + P], mu)
             R.potrf_packed_(Kuu, info[0], pk)
-            R.potrf_packed_(Sm, info[1], pks)
-            Ls_copy.copy_(Sm)
-            _sinv_chain(Sm, pks, eyeS, LsT, Sinv_l, Sinv)
+            s_branch()
+            _sinv_chain(Sm, pks, Sinv_l, Sinv)
         L, Ls = Kuu, Sm
-        RH[:, :, B:B + M].copy_(Ls_copy)
-        RH[:, :, B + M:B + M + P].copy_(mu)
-        if PP > P:
-            RH[:, :, B + M + P:].zero_()
+        sldL, sldLs = R.sumlogdiag(L), R.sumlogdiag(Ls)
         RH = R.trsm_solve(L, pk, RH)                            # :85-87  A = L^-1 Kuf, C = L^-1 Ls, mt = L^-1 mu
         A, C, mt = RH[:, :, :B], RH[:, :, B:B + M], RH[:, :, B + M:B + M + P]
         G = _split_k(M, B) if S == 1 else 1
         if G > 1:
             # Phi = A A^T is M x M x B: 36-72 output tiles on 148 SMs with a 4096-deep K loop each -> split K into G slabs
-            # (batched GEMM over strided views of the same buffer) and add the partial lower triangles
-            Av = A.as_strided((G, M, B // G), (B // G, RH.stride(1), 1))
-            Phi = R.copy_ltu(R.gemm(Av, Av, transB=True, tri=True).sum(dim=0, keepdim=True))
+            # (batched GEMM over strided views of the same buffer); the partial lower triangles are added and mirrored
+            # by one launch
+            Av = A.as_strided((G, M, B // G), (B // G, RH.stride(1), 1), A.storage_offset())
+            parts = torch.empty((G, M, M), dtype=dt, device=dev)
+            R.gemm(Av, Av, transB=True, beta=0.0, C=parts, tri=1)
+            Phi = R.copy_ltu_sum(parts)
         else:
-            Phi = R.copy_ltu(R.gemm(A, A, transB=True, tri=True))
-        T = R.copy_ltu(R.gemm(C, C, transB=True, tri=True))
+            Pl = torch.empty((S, M, M), dtype=dt, device=dev)
+            Phi = R.copy_ltu(R.gemm(A, A, transB=True, beta=0.0, C=Pl, tri=1))
+        Tl = torch.empty((S, M, M), dtype=dt, device=dev)
+        T = R.copy_ltu(R.gemm(C, C, transB=True, beta=0.0, C=Tl, tri=1))
         G1 = R.gemm(A, mt, transA=True)                         # :89  (S,B,P)
         sumr2 = R.reduce(R.RED_SUMSQDIFF, Y, G1)
         trPhi = R.reduce(R.RED_SUMSQ, A)
         trT = R.reduce(R.RED_SUMSQ, C)
         trPhiT = R.reduce(R.RED_DOT, Phi, T)
         mm = R.reduce(R.RED_SUMSQ, mt)
-        sldL, sldLs = R.sumlogdiag(L), R.sumlogdiag(Ls)
         # :94-108 on the reduced scalars in one launch (`KL_u` of the reference is minus the KL):
         #   Q = -sumr2/2 - P B kv/2 - P (tr(Phi T) - tr Phi)/2,  data = beta Q - B P (log 2pi + log nv)/2,
         #   logL = scale data + P (M/2 + sld(Ls) - sld(L)) - P tr(T)/2 - |mt|^2/2
@@ -394,6 +404,7 @@ class _SVGPLogPdf(torch.autograd.Function):
         ctx.kind, ctx.scale, ctx.dims = kind, scale, (S, B, P, M)
         ctx.save_for_backward(X, Y, Z, ls, kvar, W, L, Sinv, RH, Phi, T, G1, beta, Q, pk)
         ctx.info = info
+        _note_info(info)
         return logL
 
     @staticmethod
@@ -402,7 +413,9 @@ class _SVGPLogPdf(torch.autograd.Function):
         S, B, P, M = ctx.dims
         dt, dev = RH.dtype, RH.device
         PP = (P + 3) & ~3
-        A, mt = RH[:, :, :B], RH[:, :, B + M:B + M + P].contiguous()
+        A, mt_v = RH[:, :, :B], RH[:, :, B + M:B + M + P]
+        mt = torch.empty((S, M, P), dtype=dt, device=dev)
+        R.copy2d_(mt, mt_v)
         sc = ctx.scale
         need = ctx.needs_input_grad      # (kind, jitter, scale, X, Y, Z, noise, mu, W, dvec, ls, kvar)
         coef, gsb, neg_gsb, dnoise_s, dkvar_diag, neg_g, minus1 = R.svgp_coef_bwd(P, B, sc, g.contiguous(), beta, Q)
@@ -412,14 +425,12 @@ class _SVGPLogPdf(torch.autograd.Function):
         # first solve with L^T: [E | E_S | E_R | mt]  (mt rides along: w = L^-T mt)
         E4 = torch.empty((S, M, 3 * M + PP), dtype=dt, device=dev)
         R.svgp_bwd_assemble(Phi, T, U, mt, v, coef, out=E4)
-        E4[:, :, 3 * M:3 * M + P].copy_(mt)
-        if PP > P:
-            E4[:, :, 3 * M + P:].zero_()
+        R.copy2d_(E4[:, :, 3 * M:3 * M + P], mt)
         E4 = R.trsm_solve(L, pk, E4, transpose=True)
         # The Kuf branch (one big product + kernel adjoint) and the Kuu branch (second solve + kernel adjoint) are
         # independent from here on: fork the Kuf branch onto the side stream
         w = E4[:, :, 3 * M:3 * M + P]
-        wg = R.axpby_dev(gsb, w)
+        wg = R.axpby2d(gsb, w)
         dKuf = torch.empty((S, M, B), dtype=dt, device=dev)
         side = _side_stream(dev)
         cur = torch.cuda.current_stream() if side is not None else None
@@ -437,36 +448,80 @@ class _SVGPLogPdf(torch.autograd.Function):
         F2 = torch.empty((S, M, 2 * M + PP), dtype=dt, device=dev)
         R.transpose(E4[:, :, :M], out=F2[:, :, :M])
         R.transpose(E4[:, :, M:2 * M], out=F2[:, :, M:2 * M])
-        F2[:, :, 2 * M:2 * M + P].copy_(R.axpby_dev(gsb, v, neg_g, mt))
-        if PP > P:
-            F2[:, :, 2 * M + P:].zero_()
+        R.axpby2d(gsb, v, neg_g, mt, out=F2[:, :, 2 * M:2 * M + P])
         F2 = R.trsm_solve(L, pk, F2, transpose=True)
         dKuu = F2[:, :, :M]
-        dmu = F2[:, :, 2 * M:2 * M + P].contiguous()
+        dmu = torch.empty((S, M, P), dtype=dt, device=dev)
+        R.copy2d_(dmu, F2[:, :, 2 * M:2 * M + P])
         dZ2, _, dls2, dvar2 = R.kbuild_bwd(ctx.kind, Z, None, ls, kvar, dKuu)
         if side is None:
             dZ1, dX, dls1, dvar1 = kuf_branch()
         # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 (S^-1 from the forward pass); W adjoint 2 Sbar W ; diag adjoint diag(Sbar)
-        Sbar = R.axpby_dev(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M].contiguous())
+        Sbar = R.axpby2d(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M])
         dW = R.gemm(Sbar, W, alpha=2.0)
         dd = R.get_diag(Sbar)
         dnoise = dnoise_s.unsqueeze(1)
         dY = R.axpby_dev(neg_gsb, Y, gsb, G1) if need[4] else None          # -g s beta (Y - A^T mt)
         if side is not None:
             cur.wait_stream(side)                                            # join the Kuf branch
-        dZ = dZ1 + dZ2
-        dls = dls1 + dls2
-        dkvar = dvar1 + dvar2 + dkvar_diag.unsqueeze(1)                     # Kff_diag term (:100)
+        dZ = R.axpby2d(None, dZ1, None, dZ2)
+        dls = R.axpby2d(None, dls1.unsqueeze(0), None, dls2.unsqueeze(0)).squeeze(0)
+        dkvar = R.axpby2d(None, dvar1.unsqueeze(0), None, dvar2.unsqueeze(0)).squeeze(0)
+        dkvar = R.axpby2d(None, dkvar.unsqueeze(0), None, dkvar_diag.reshape(1, -1, 1)).squeeze(0)   # Kff_diag term (:100)
         return None, None, None, dX, dY, dZ, dnoise, dmu, dW, dd, dls, dkvar
 
 
-def _sinv_chain(Ls, pks, eye, LsT, Sinv_l, Sinv):
-    """S^-1 = Ls^-T Ls^-1: one solve with the identity, one lower-tiles product, mirror.  Writes into preallocated
-    buffers (they are created on the main stream and only filled on the side stream)."""
-    Li = R.trsm_solve(Ls, pks, eye)                             # Ls^-1
-    R.transpose(Li, out=LsT)
-    R.gemm(LsT, Li, beta=0.0, C=Sinv_l, tri=True)
+def _sinv_chain(Ls, pks, Sinv_l, Sinv):
+    """S^-1 = Ls^-T Ls^-1.  The factor's pack holds the explicit inverse W = Ls^-1 and its transpose (f32, M <= 1024: a
+    by-product of the single-launch potrf): one lower-tiles product W^T W with the zero blocks of both triangular
+    operands skipped, then the mirror.  Without the explicit inverse: a solve with the identity first.  Writes into
+    preallocated buffers (created on the main stream, filled on the side stream)."""
+    inv = R.pack_inverse(pks, Ls)
+    if inv is not None:
+        Wi, WiT = inv
+        R.gemm(WiT, Wi, beta=0.0, C=Sinv_l, tri=5)              # lower tiles; A = W^T is upper triangular
+    else:
+        S, M = Ls.shape[0], Ls.shape[1]
+        eye = torch.eye(M, dtype=Ls.dtype, device=Ls.device).unsqueeze(0).repeat(S, 1, 1)
+        Li = R.trsm_solve(Ls, pks, eye)                         # Ls^-1
+        R.gemm(R.transpose(Li), Li, beta=0.0, C=Sinv_l, tri=1)
     R.copy_ltu(Sinv_l, out=Sinv)
+
+
+# Device-side record of the factorisations' `info` (first non-positive pivot, 1-based; 0 = fine): every fused bound adds
+# max(info) of its potrf calls into one int32 per device, without a host synchronisation.  The training loops read it
+# every `INFO_CHECK_EVERY` steps / at the end of a run and raise InferenceError -- the reference surfaces a non-PD matrix
+# as an MXNetError at its next synchronisation (SURVEY section 5; svgp_regression.py:70-72, gp_regression.py:58-60).
+_INFO_ACC = {}
+
+
+def info_accumulator(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    acc = _INFO_ACC.get(key)
+    if acc is None:
+        acc = torch.zeros((1,), dtype=torch.int32, device=device)
+        _INFO_ACC[key] = acc
+    return acc
+
+
+def _note_info(info):
+    if info.device.type != 'cuda' or not hasattr(R, 'note_info_'):
+        return
+    R.note_info_(info_accumulator(info.device), info)
+
+
+def check_factorisations(device, what="a Cholesky factorisation"):
+    """Raises InferenceError if any potrf on `device` met a non-positive pivot since the last check (one D2H read)."""
+    from .common.exceptions import InferenceError
+    if device.type != 'cuda':
+        return
+    acc = info_accumulator(device)
+    bad = int(acc.item())
+    if bad != 0:
+        acc.zero_()
+        raise InferenceError("%s failed: the matrix is not positive definite (first non-positive pivot %d). Increase "
+                             "`jitter` on the module's log-pdf algorithm (svgp_regression.py:70-72, "
+                             "gp_regression.py:58-60) or check the kernel parameters." % (what, bad))
 
 
 _SIDE_STREAMS = {}
@@ -510,6 +565,7 @@ class _GPLogPdf(torch.autograd.Function):
         S, N, P = X.shape[0], X.shape[1], Y.shape[2]
         K = R.kbuild_fwd(kind, X, None, ls, kvar, diag_add=noise, diag_const=jitter)   # :55-60
         L, info, pk = R.potrf_packed_(K)                                                # :61
+        _note_info(info)
         LinvY = R.trsm_packed_(L, pk, Y.clone())                                        # :66
         logdet_l = R.sumlogdiag(L)                                                      # :67 (diag(L) > 0)
         ss = R.reduce(R.RED_SUMSQ, LinvY)

@@ -330,3 +330,36 @@ def normal_reparam_multi(entries, seed, offsets, step_counter=None):
 
 def normal_reparam_multi_bwd(entries, needs):
     return [normal_reparam_bwd(gw, e, v, ms, need=need) for (gw, e, v, ms), need in zip(entries, needs)]
+
+
+def copy_ltu_sum(parts, out=None):
+    low = torch.tril(parts.sum(dim=0, keepdim=True))
+    r = low + torch.tril(low, -1).transpose(-1, -2)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r.contiguous()
+
+
+def copy2d_(dst, src=None):
+    if src is None:
+        dst.zero_()
+    else:
+        dst.copy_(src)
+    return dst
+
+
+def axpby2d(a, X, b=None, Y=None, out=None):
+    def co(c):
+        return 1.0 if c is None else c.reshape(-1, 1, 1)
+    r = co(a) * X
+    if Y is not None:
+        r = r + co(b) * Y
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r.contiguous()
+
+
+def pack_inverse(pack, like):
+    return None

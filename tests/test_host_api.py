@@ -289,3 +289,51 @@ def test_load_matches_by_name_and_rejects_mismatches(mf, tmp_path):
     infr4.initialize(X=X5.shape, Y=(5, 1))           # cached posterior quantities now have N = 5, the archive N = 20
     with pytest.raises(SerializationError):
         infr4.load(path)
+
+
+def test_gp_modules_draw_samples_by_default(mf):
+    """The three GP modules attach a draw-samples algorithm by default (gp_regression.py:373-378,
+    svgp_regression.py:398-403, sparsegp_regression.py:372-377), so ForwardSampling works on models that contain them.
+    With injected noise the draws are the reference's: chol(K + noise I) eps for the exact GP; U -> F | U -> Y for the
+    inducing-point modules."""
+    from mxfusion_b200.components.variables import PositiveTransformation
+    from mxfusion_b200.components.distributions.gp.kernels import RBF
+    from mxfusion_b200.components.distributions.random_gen import MockMXNetRandomGenerator
+    from mxfusion_b200.modules.gp_modules import GPRegression, SVGPRegression, SparseGPRegression
+    from mxfusion_b200.inference import Inference
+    from mxfusion_b200.inference.forward_sampling import ForwardSamplingAlgorithm
+    from oracle import kernels as ok
+    rng = np.random.RandomState(3)
+    N, M, ns = 7, 4, 3
+    X, Z = rng.rand(N, 2), rng.rand(M, 2)
+    die = rng.randn(ns * N)
+
+    def model(kind):
+        m = mf.Model()
+        m.N = mf.Variable()
+        m.X = mf.Variable(shape=(m.N, 2))
+        m.noise_var = mf.Variable(shape=(1,), transformation=PositiveTransformation(), initial_value=0.3)
+        kern = RBF(input_dim=2, variance=1.3, lengthscale=0.7)
+        gen = MockMXNetRandomGenerator(torch.tensor(die))
+        if kind == 'gp':
+            m.Y = GPRegression.define_variable(X=m.X, kernel=kern, noise_var=m.noise_var, shape=(m.N, 1), rand_gen=gen)
+        else:
+            cls = SVGPRegression if kind == 'svgp' else SparseGPRegression
+            m.Z = mf.Variable(shape=(M, 2), initial_value=Z)
+            m.Y = cls.define_variable(X=m.X, kernel=kern, noise_var=m.noise_var, inducing_inputs=m.Z, shape=(m.N, 1))
+        return m
+    m = model('gp')
+    infr = Inference(ForwardSamplingAlgorithm(m, observed=[m.X], num_samples=ns, target_variables=[m.Y]))
+    infr.initialize(X=X.shape)
+    with torch.no_grad():
+        got = infr.run(X=X)[0].numpy()
+    K = ok.K(0, X[None], np.array([[0.7]]), np.array([[1.3]]))[0] + 0.3 * np.eye(N)
+    want = np.linalg.cholesky(K) @ die.reshape(ns, N, 1)
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)
+    for kind in ('svgp', 'sgp'):
+        m = model(kind)
+        infr = Inference(ForwardSamplingAlgorithm(m, observed=[m.X], num_samples=ns, target_variables=[m.Y]))
+        infr.initialize(X=X.shape)
+        with torch.no_grad():
+            y = infr.run(X=X)[0]
+        assert tuple(y.shape) == (ns, N, 1) and bool(torch.isfinite(y).all())
