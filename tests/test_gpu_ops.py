@@ -1,8 +1,9 @@
 """The fused bounds and differentiable primitives on the real kernels (C ABI through ctypes) against the
 oracle: values vs the NumPy restatement, gradients vs autograd through the torch restatement, both
 float64 (tight) and float32 (the reference's only stated fp32 tolerance is rtol 1e-4 / atol 1e-5 for
-an elementwise density; for the ill-conditioned solves here fp32 is held to 2e-3 relative on values
-and 2e-2 of the gradient's max-norm)."""
+an elementwise density; the fused bounds in fp32 are held to ~10x what a B200 measures against the float64 restatement:
+values 2e-5 relative (measured <= 2.1e-6), every gradient within 2e-4 of its own max-norm (measured <= 2.2e-4 / typically
+1e-5) plus 2e-5 of the call's largest gradient entry for gradients that are cancellation residuals (measured <= 4.1e-6)."""
 import numpy as np
 import pytest
 import torch
@@ -10,6 +11,26 @@ import torch
 from oracle import torch_ref, svgp as osvgp, gp as ogp
 
 pytestmark = pytest.mark.gpu
+
+
+# float32 gates (~10x the errors measured on a B200, printed with -s as MEASURED lines): see module docstring
+F32_VALUE, F32_GRAD, F32_FLOOR = 2e-5, 2e-4, 2e-5
+
+
+def _f32_close(tag, got, want, vtol):
+    rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)))
+    print('MEASURED value %s %.2e' % (tag, rel))
+    np.testing.assert_allclose(got, want, rtol=vtol)
+
+
+def _grad_close(tag, grads, tol, floor):
+    """grads: {name: (got, want)}.  Every gradient within tol of its own max-norm + floor x the largest gradient entry of
+    the call (a gradient that is a cancellation residual is held to the call's resolution, not to its own size)."""
+    gmax = max(float(np.max(np.abs(w))) for _, w in grads.values())
+    for k, (g, w) in grads.items():
+        err, sc = float(np.max(np.abs(g - w))), float(np.max(np.abs(w)))
+        print('MEASURED grad %s %s err/own %.2e err/gmax %.2e' % (tag, k, err / max(sc, 1e-300), err / max(gmax, 1e-300)))
+        assert err <= tol * sc + floor * gmax, (tag, k, err, sc, gmax)
 
 
 def _svgp_inputs(rng, S, B, M, Din, P):
@@ -38,11 +59,9 @@ def test_fused_svgp(cuda, prec, kind, dims):
     got = ops.svgp_log_pdf(kind, t['X'], t['Y'], t['Z'], t['noise'], t['mu'], t['W'], t['dv'], t['ls'], t['var'],
                            jitter=jit, log_pdf_scaling=3.5)
     (got * torch.tensor(gout, dtype=tdt, device=cuda)).sum().backward()
-    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=1e-9 if prec == 'f64' else 2e-3)
-    for k in a:
-        g, w = t[k].grad.double().cpu().numpy(), r[k].grad.numpy()
-        tol = 1e-7 if prec == 'f64' else 2e-2
-        assert np.max(np.abs(g - w)) <= tol * (1e-3 + np.max(np.abs(w))), (k, np.max(np.abs(g - w)), np.max(np.abs(w)))
+    _f32_close('svgp %s %s' % (dims, kind), got.detach().cpu().numpy(), want.detach().numpy(), 1e-9 if prec == 'f64' else F32_VALUE)
+    _grad_close('svgp %s %s %s' % (dims, kind, prec), {k: (t[k].grad.double().cpu().numpy(), r[k].grad.numpy()) for k in a},
+                1e-7 if prec == 'f64' else F32_GRAD, 1e-10 if prec == 'f64' else F32_FLOOR)
 
 
 def test_fused_svgp_reference_fixture_known_answer(cuda):
@@ -74,11 +93,9 @@ def test_fused_gp(cuda, prec, kind, dims):
     want.sum().backward()
     got, L, LinvY = ops.gp_log_pdf(kind, t['X'], t['Y'], t['noise'], t['ls'], t['var'], jitter=1e-6)
     got.sum().backward()
-    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=1e-9 if prec == 'f64' else 2e-3)
-    for k in d:
-        g, w = t[k].grad.double().cpu().numpy(), r[k].grad.numpy()
-        tol = 1e-7 if prec == 'f64' else 2e-2
-        assert np.max(np.abs(g - w)) <= tol * (1e-3 + np.max(np.abs(w))), (k, np.max(np.abs(g - w)), np.max(np.abs(w)))
+    _f32_close('gp %s %s' % (dims, kind), got.detach().cpu().numpy(), want.detach().numpy(), 1e-9 if prec == 'f64' else F32_VALUE)
+    _grad_close('gp %s %s %s' % (dims, kind, prec), {k: (t[k].grad.double().cpu().numpy(), r[k].grad.numpy()) for k in d},
+                1e-7 if prec == 'f64' else F32_GRAD, 1e-10 if prec == 'f64' else F32_FLOOR)
     if prec == 'f64':
         wl = ogp.gp_log_pdf(kind, d['X'], d['Y'], d['noise'], d['ls'], d['var'], jitter=1e-6)
         np.testing.assert_allclose(L.cpu().numpy(), wl[1], rtol=1e-8, atol=1e-11)
@@ -119,7 +136,7 @@ def test_ops_refuse_cpu_tensors():
                                                ('H  SVGP M=1024 D=8 RBF B=4096', 0, 4096, 1024, 8)])
 def test_fused_svgp_at_baseline_shapes_f32(cuda, name, kind, B, M, Din):
     """BASELINE.json configs 2, 3 and the headline shape in float32 (the reference's default dtype) against the float64
-    restatement: value within 2e-3 relative, every gradient within 2e-2 of its max-norm (fp32 with a jittered Kuu)."""
+    restatement, at the module's float32 gates (F32_VALUE / F32_GRAD / F32_FLOOR)."""
     from mxfusion_b200 import ops
     rng = np.random.RandomState(7)
     X = rng.uniform(-3, 3, (1, B, Din))
@@ -134,9 +151,6 @@ def test_fused_svgp_at_baseline_shapes_f32(cuda, name, kind, B, M, Din):
     got = ops.svgp_log_pdf(kind, t['X'], t['Y'], t['Z'], t['noise'], t['mu'], t['W'], t['dv'], t['ls'], t['var'],
                            jitter=1e-4, log_pdf_scaling=25.0)
     got.sum().backward()
-    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=2e-3)
-    for k in a:
-        if k in ('X', 'Y'):
-            continue
-        g, w = t[k].grad.double().cpu().numpy(), r[k].grad.numpy()
-        assert np.max(np.abs(g - w)) <= 2e-2 * (1e-3 + np.max(np.abs(w))), (name, k, np.max(np.abs(g - w)), np.max(np.abs(w)))
+    _f32_close(name, got.detach().cpu().numpy(), want.detach().numpy(), F32_VALUE)
+    _grad_close(name, {k: (t[k].grad.double().cpu().numpy(), r[k].grad.numpy()) for k in a if k not in ('X', 'Y')},
+                F32_GRAD, F32_FLOOR)
