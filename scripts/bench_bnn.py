@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 N, B, H, S = 100000, 4096, 50, 3
-STEPS = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+STEPS = int(sys.argv[1]) if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1].isdigit() else 200
 
 
 def data():
@@ -28,7 +28,8 @@ def data():
     return x, y
 
 
-def gpu_leg(x, y):
+def gpu_leg(x, y, steps=None, warm=10, data_resident=True, wall=False):
+    STEPS = steps if steps is not None else globals()['STEPS']
     import mxfusion_b200 as mf
     from mxfusion_b200 import _lib
     from mxfusion_b200.components.distributions import Normal
@@ -52,14 +53,14 @@ def gpu_leg(x, y):
     observed = [m.y, m.x]
     q = create_Gaussian_meanfield(model=m, observed=observed)
     alg = StochasticVariationalInference(num_samples=S, model=m, posterior=q, observed=observed)
-    loop = MinibatchInferenceLoop(batch_size=B, rv_scaling={m.y: N / float(B)}, rng=np.random.RandomState(0))
+    loop = MinibatchInferenceLoop(batch_size=B, rv_scaling={m.y: N / float(B)}, rng=np.random.RandomState(0),
+                                  data_resident=data_resident)
     infr = GradBasedInference(inference_algorithm=alg, grad_loop=loop, context=dev)
     infr.initialize(y=(N, 1), x=(N, 1))
     for _, v in m.r.factor.parameters.items():
         infr.params[q[v].factor.mean] = v.initial_value
         infr.params[q[v].factor.variance] = torch.full(v.shape, 1e-6)
     st = {}
-    warm = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def on_step(k, loss):
@@ -67,18 +68,21 @@ def gpu_leg(x, y):
             st['first'] = float(loss)
         if k == warm:
             torch.cuda.synchronize()
+            st['t0'] = time.perf_counter()
             e0.record()
         elif k == warm + STEPS:
             e1.record()
             torch.cuda.synchronize()
+            st['t1'] = time.perf_counter()
             st['last'] = float(loss)
     l0 = _lib.launch_count()
     infr.run(max_iter=1 + (warm + STEPS) * B // N + 1, learning_rate=1e-3, max_steps=warm + STEPS, on_step=on_step,
              y=y, x=x)
-    ms = e0.elapsed_time(e1) / STEPS
+    ms = (1e3 * (st['t1'] - st['t0']) if wall else e0.elapsed_time(e1)) / STEPS
     return dict(ms_per_step=ms, iters_per_s=1e3 / ms, first_loss=st['first'], last_loss=st['last'],
                 launches_per_step=getattr(loop.last_stepper, 'launches_per_step', None),
-                eager_launches=_lib.launch_count() - l0)
+                eager_launches=_lib.launch_count() - l0, h2d_bytes_per_step=loop.h2d_bytes_per_step,
+                d2h_bytes_per_step=loop.d2h_bytes_per_step)
 
 
 def cpu_leg(x, y, budget_s=10.0):
@@ -127,12 +131,17 @@ def cpu_leg(x, y, budget_s=10.0):
     return dict(cpu_iters_per_s=n / dt, cpu_iters=n, cpu_cores=os.cpu_count())
 
 
-x, y = data()
-out = dict(workload='mean-field BNN 1-%d-%d-1 tanh, S=%d, SVI MC-ELBO, minibatch=%d, N=%d, f32' % (H, H, S, B, N))
-out.update(gpu_leg(x, y))
-if '--no-cpu' not in sys.argv:
-    out.update(cpu_leg(x, y))
-    out['speedup_vs_cpu'] = out['iters_per_s'] / out['cpu_iters_per_s']
-print(json.dumps(out))
-os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'bnn_bench.json'), 'w'))
+def main():
+    x, y = data()
+    out = dict(workload='mean-field BNN 1-%d-%d-1 tanh, S=%d, SVI MC-ELBO, minibatch=%d, N=%d, f32' % (H, H, S, B, N))
+    out.update(gpu_leg(x, y))
+    if '--no-cpu' not in sys.argv:
+        out.update(cpu_leg(x, y))
+        out['speedup_vs_cpu'] = out['iters_per_s'] / out['cpu_iters_per_s']
+    print(json.dumps(out))
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'bnn_bench.json'), 'w'))
+
+
+if __name__ == '__main__':
+    main()
