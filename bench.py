@@ -487,6 +487,7 @@ def main():
     def emit(line):
         print(json.dumps(line))
         if args.out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
             with open(args.out, 'w') as f:
                 f.write(json.dumps(line, indent=1) + '\n')
 

@@ -8,6 +8,7 @@ import torch
 
 _COUNTER = itertools.count(1)
 _SEED = [0]
+_RANK_SALT = [0]             # mixed into the seed of in-kernel draws: data-parallel ranks draw DIFFERENT noise
 _STEP_COUNTER = [None]       # device int32[1] bumped once per optimiser step (InferenceParameters.adam_t)
 
 
@@ -22,6 +23,12 @@ def step_counter(device=None):
     if t is None or (device is not None and t.device != torch.device(device)):
         return None
     return t
+
+
+def set_rank(rank):
+    """Data-parallel runs (inference/_stepper.py): every rank keeps the same (seed, offset) sequence, so without a salt
+    all ranks would draw identical Monte-Carlo noise and adding ranks would not reduce its variance."""
+    _RANK_SALT[0] = int(rank) * 0x9E3779B1
 
 
 def seed(value):
@@ -43,7 +50,7 @@ class MXNetRandomGenerator(RandomGenerator):
 
     @staticmethod
     def next_stream():
-        return _SEED[0], next(_COUNTER)
+        return (_SEED[0] + _RANK_SALT[0]) & 0x7FFFFFFFFFFFFFFF, next(_COUNTER)
 
     @staticmethod
     def sample_normal(loc=0, scale=1, shape=None, dtype=None, out=None, ctx=None):

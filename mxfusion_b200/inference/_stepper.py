@@ -32,6 +32,12 @@ class Stepper(object):
             infr_executor.pretransformed = params._fused_uuids
         from ..components.distributions import random_gen
         random_gen.set_step_counter(params.adam_t if params.adam_t.is_cuda else None)
+        if self.world > 1:
+            # replicas must start from the same point (e.g. SVGP's default inducing inputs are np.random.randn per process,
+            # svgp_regression.py:318-320) and draw different Monte-Carlo noise
+            for t in (params.flat, params.adam_m, params.adam_v, params.adam_t):
+                dist.broadcast(t, src=0)
+            random_gen.set_rank(dist.get_rank())
         self.static_in = [torch.empty_like(b) for b in example_batch]
         if self.static_in and self.static_in[0].is_cuda:
             ops.info_accumulator(self.static_in[0].device)        # created eagerly, never inside a graph capture

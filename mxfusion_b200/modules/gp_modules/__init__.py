@@ -4,3 +4,4 @@ from .svgp_regression import (SVGPRegression, SVGPRegressionLogPdf, SVGPRegressi
                               SVGPRegressionSamplingPrediction)
 from .sparsegp_regression import (SparseGPRegression, SparseGPRegressionLogPdf,  # noqa: F401
                                   SparseGPRegressionMeanVariancePrediction, SparseGPRegressionSamplingPrediction)
+from .deep_gp import DeepGPRegression, DeepGPLogPdf, DeepGPMeanVariancePrediction  # noqa: F401
