@@ -28,6 +28,7 @@
 // the tiles are too small and the chain too serial for tcgen05 to matter here (the trailing updates of n > 1024
 // factorisations, where it does, stay on gemm_tc.cu), and the result is more accurate than a 3xTF32 update.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "chol_dag.cuh"
 
@@ -52,6 +53,7 @@ struct DagParams {
     int* info;
     int info_base;                     // added to the failing pivot index (offset of this block in the full matrix)
     int n, T, mode;
+    unsigned long long timeout_ns;     // safety net of the flag waits (MXF_DAG_TIMEOUT_S, default 2 s)
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -267,7 +269,7 @@ struct Sync {
 
 // All threads call; thread 0 spins on up to two flags.  Returns false when the launch was aborted (a wait exceeded 2 s:
 // cannot happen by construction, it is the safety net that turns a scheduling bug into an error code instead of a hang).
-__device__ __forceinline__ bool wait_flags(const int* f0, const int* f1, int* abort_flag, int* sh) {
+__device__ __forceinline__ bool wait_flags(const int* f0, const int* f1, int* abort_flag, int* sh, unsigned long long timeout_ns) {
     if (threadIdx.x == 0) {
         int ok = 1;
         unsigned spins = 0;
@@ -280,7 +282,7 @@ __device__ __forceinline__ bool wait_flags(const int* f0, const int* f1, int* ab
                 if (ld_acquire(abort_flag) != 0) { ok = 0; break; }
                 const unsigned long long now = globaltimer_ns();
                 if (t0 == 0) t0 = now;
-                else if (now - t0 > 2000000000ull) { atomicExch(abort_flag, 1); ok = 0; break; }
+                else if (now - t0 > timeout_ns) { atomicExch(abort_flag, 1); ok = 0; break; }
             }
         }
         *sh = ok;
@@ -600,7 +602,7 @@ potrf_dag_kernel(const DagParams p) {
         if (factor && c >= 1) {
             load_acc(acc1, A + (int64_t)i0 * lda + i0 - B, lda, re, B, vA, false, m);
             for (int k = 0; k + 1 < c; ++k) {
-                if (!wait_flags(&sync.Lfin[c * T + k], &sync.Lfin[(c - 1) * T + k], sync.abort_flag, &sh_flag)) return;
+                if (!wait_flags(&sync.Lfin[c * T + k], &sync.Lfin[(c - 1) * T + k], sync.abort_flag, &sh_flag, p.timeout_ns)) return;
                 load_tile_async<0>(bufX, A + (int64_t)i0 * lda + k * B, lda, re, B, vA);               // L_ck as X
                 load_tile_async<2>(bufO, A + (int64_t)i0 * lda + k * B, lda, re, B, vA);               // L_ck as Y
                 load_tile_async<2>(bufY, A + (int64_t)(i0 - B) * lda + k * B, lda, B, B, vA);          // L_{c-1,k} as Y
@@ -613,7 +615,7 @@ potrf_dag_kernel(const DagParams p) {
             // L_{c,c-1} = A_{c,c-1} W_{c-1,c-1}^T
             acc_to_tile<0>(bufX, acc1, m);
             DG_STAMP(c, 1);
-            if (!wait_flags(&sync.Wfin[(c - 1) * T + (c - 1)], nullptr, sync.abort_flag, &sh_flag)) return;
+            if (!wait_flags(&sync.Wfin[(c - 1) * T + (c - 1)], nullptr, sync.abort_flag, &sh_flag, p.timeout_ns)) return;
             DG_STAMP(c, 2);
             load_tile_async<2>(bufY, W + (int64_t)(i0 - B) * ldw + i0 - B, ldw, B, B, vW);
             cp_async_wait_all();
@@ -700,7 +702,7 @@ potrf_dag_kernel(const DagParams p) {
         float acc[4][4];
         load_acc(acc, A + (int64_t)i0 * lda + j0, lda, re, B, vA, false, m);
         for (int k = 0; k < j; ++k) {
-            if (!wait_flags(&sync.Lfin[i * T + k], &sync.Lfin[j * T + k], sync.abort_flag, &sh_flag)) return;
+            if (!wait_flags(&sync.Lfin[i * T + k], &sync.Lfin[j * T + k], sync.abort_flag, &sh_flag, p.timeout_ns)) return;
             load_tile_async<0>(bufX, A + (int64_t)i0 * lda + k * B, lda, re, B, vA);
             load_tile_async<2>(bufY, A + (int64_t)j0 * lda + k * B, lda, B, B, vA);
             cp_async_wait_all();
@@ -709,7 +711,7 @@ potrf_dag_kernel(const DagParams p) {
             __syncthreads();
         }
         acc_to_tile<0>(bufX, acc, m);
-        if (!wait_flags(&sync.Wfin[j * T + j], nullptr, sync.abort_flag, &sh_flag)) return;
+        if (!wait_flags(&sync.Wfin[j * T + j], nullptr, sync.abort_flag, &sh_flag, p.timeout_ns)) return;
         load_tile_async<2>(bufY, W + (int64_t)j0 * ldw + j0, ldw, B, B, vW);
         cp_async_wait_all();
         __syncthreads();
@@ -732,7 +734,7 @@ potrf_dag_kernel(const DagParams p) {
         float acc[4][4] = {};
         for (int k = j; k < i; ++k) {
             const int* lf = factor ? &sync.Lfin[i * T + k] : nullptr;
-            if (!wait_flags(lf, &sync.Wfin[k * T + j], sync.abort_flag, &sh_flag)) return;
+            if (!wait_flags(lf, &sync.Wfin[k * T + j], sync.abort_flag, &sh_flag, p.timeout_ns)) return;
             load_tile_async<0>(bufX, A + (int64_t)i0 * lda + k * B, lda, re, B, vA);                   // L_ik
             load_tile_async<0>(bufY, W + (int64_t)(k * B) * ldw + j0, ldw, B, B, vW);                  // W_kj
             cp_async_wait_all();
@@ -741,7 +743,7 @@ potrf_dag_kernel(const DagParams p) {
             __syncthreads();
         }
         acc_to_tile<0>(bufY, acc, m);
-        if (!wait_flags(&sync.Wfin[i * T + i], nullptr, sync.abort_flag, &sh_flag)) return;
+        if (!wait_flags(&sync.Wfin[i * T + i], nullptr, sync.abort_flag, &sh_flag, p.timeout_ns)) return;
         load_tile_async<0>(bufX, W + (int64_t)i0 * ldw + i0, ldw, re, re, vW);                         // W_ii
         cp_async_wait_all();
         __syncthreads();
@@ -792,6 +794,12 @@ int dag_launch(int mode, float* A, int64_t lda, int64_t sA, int n, float* pack, 
     p.ldw = ldw; p.ldlt = ldlt;
     p.info = info; p.info_base = info_base;
     p.n = n; p.T = (n + B - 1) / B; p.mode = mode;
+    static const unsigned long long timeout_ns = [] {
+        const char* e = getenv("MXF_DAG_TIMEOUT_S");         // raise it under compute-sanitizer (50-100x slower kernels)
+        const double s = e ? atof(e) : 2.0;
+        return (unsigned long long)((s > 0.01 ? s : 2.0) * 1e9);
+    }();
+    p.timeout_ns = timeout_ns;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM);
