@@ -11,6 +11,7 @@
 // store per row for f32), keeps the scaled b-vectors of those columns in registers and walks the
 // rows of the CTA tile, whose scaled a-vectors (pre-multiplied by -2) sit in shared memory and are
 // read as warp-uniform broadcasts.  A warp therefore writes 512 contiguous bytes per row.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mxf {
@@ -409,6 +410,186 @@ static int launch_fwd_stream(const T* X, const T* X2, const T* ls, int ls_len, c
     return after_launch();
 }
 
+// ------------------------------------------------------------------------------------------
+// forward, streaming variant for 8 < D <= 16 (f32): the dot products on the tensor pipe.
+//
+// At D = 16 the FMA formulation needs 16 FFMA + ~8 other instructions per output element and is issue-bound at
+// 0.40-0.48 of the HBM peak (25 % occupancy).  The reference itself forms -2 a.b with a GEMM (stationary.py:102), and
+// that is what this kernel does: every warp owns 64 output columns whose scaled vectors sit in registers as TF32
+// B-fragments (hi and lo halves), walks the rows 16 at a time with the A-fragments read pre-split from shared memory, and
+// issues mma.sync.m16n8k8 TF32 x 3 (a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulate: the 3xTF32 scheme of
+// gemm_tc.cu).  An element then costs 48/1024 MMAs + 2 FADD + 1 MUFU (+ the Matern polynomial) + half a 64-bit
+// streaming store: the kernel is back on the HBM roofline.  (K = 16 is one or two MMA steps: far below the 128 x N x 8
+// tiles tcgen05 wants, and the accumulators are consumed immediately by the exponential -- the warp-level MMA is the
+// right tool for this contraction; the large GEMMs of the path are tcgen05, gemm_tc.cu.)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int KM_COLS = 64;        // output columns per warp (8 n-tiles)
+
+template <int KIND, bool SYM>
+__global__ void __launch_bounds__(256, 1)
+kbuild_fwd_mma_kernel(const float* __restrict__ X, const float* __restrict__ X2, const float* __restrict__ ls, int ls_len,
+                      const float* __restrict__ var, const float* __restrict__ diag_add, float diag_const,
+                      float* __restrict__ out, int64_t ldo, int N, int N2, int D, int chunk_rows, int64_t sX, int64_t sX2,
+                      int64_t sLs, int64_t sVar, int64_t sDiag, int64_t sOut, int vec2_ok) {
+    constexpr int DP = 16;
+    constexpr bool RBF_FOLD = (KIND == MXF_KERN_RBF);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* ah_s = reinterpret_cast<unsigned*>(smem_raw);           // [chunk_rows][DP]  tf32 hi of -2 * scaled row
+    unsigned* al_s = ah_s + (size_t)chunk_rows * DP;                   // [chunk_rows][DP]  tf32 lo
+    float* na_s = reinterpret_cast<float*>(al_s + (size_t)chunk_rows * DP);   // [chunk_rows]  |scaled row|^2
+    float* sc_s = na_s + chunk_rows;                                   // [DP]
+    float* nb_s = sc_s + DP;                                           // [8 * KM_COLS]  column norms (+ folded constants)
+
+    const int s = blockIdx.z;
+    const float* Xs = X + (int64_t)s * sX;
+    const float* X2s = X2 + (int64_t)s * sX2;
+    const float* lss = ls + (int64_t)s * sLs;
+    const float v = var[(int64_t)s * sVar];
+    float* outs = out + (int64_t)s * sOut;
+    const int i0 = blockIdx.y * chunk_rows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int jw = blockIdx.x * (8 * KM_COLS) + warp * KM_COLS;         // first column of this warp
+    const float csq = RBF_FOLD ? 0.84932180028801904272f : 1.0f;       // sqrt(log2(e)/2)
+    const float l2v = log2f(v);
+
+    for (int d = threadIdx.x; d < DP; d += 256) sc_s[d] = d < D ? csq / lss[ls_len == 1 ? 0 : d] : 0.f;
+    __syncthreads();
+    const int nrows = min(chunk_rows, N - i0);
+    for (int e = threadIdx.x; e < chunk_rows * DP; e += 256) {
+        const int r = e / DP, d = e - r * DP;
+        const float x = (r < nrows && d < D) ? Xs[(int64_t)(i0 + r) * D + d] : 0.f;
+        const float a = -2.f * x * sc_s[d];
+        const unsigned hi = f2tf32(a);
+        ah_s[e] = hi;
+        al_s[e] = f2tf32(a - __uint_as_float(hi));
+    }
+    for (int r = threadIdx.x; r < chunk_rows; r += 256) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            const float x = (r < nrows && d < D) ? Xs[(int64_t)(i0 + r) * D + d] * sc_s[d] : 0.f;
+            acc = fmaf(x, x, acc);
+        }
+        na_s[r] = acc;
+    }
+    // column norms of the CTA's 512 columns
+    for (int cidx = threadIdx.x; cidx < 8 * KM_COLS; cidx += 256) {
+        const int j = blockIdx.x * (8 * KM_COLS) + cidx;
+        float n2 = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            const float x = (j < N2 && d < D) ? X2s[(int64_t)j * D + d] * sc_s[d] : 0.f;
+            n2 = fmaf(x, x, n2);
+        }
+        nb_s[cidx] = RBF_FOLD ? n2 - l2v : n2;
+    }
+    // B fragments of this warp's 64 columns: n-tile nt, k-step ks: b0 = (k = 8 ks + t, n = g), b1 = (k = 8 ks + t + 4, n = g)
+    unsigned bh[8][2][2], bl[8][2][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int j = jw + 8 * nt + g;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int d = 8 * ks + t + 4 * h;
+                const float x = (j < N2 && d < D) ? X2s[(int64_t)j * D + d] * sc_s[d] : 0.f;
+                const unsigned hi = f2tf32(x);
+                bh[nt][ks][h] = hi;
+                bl[nt][ks][h] = f2tf32(x - __uint_as_float(hi));
+            }
+    }
+    __syncthreads();
+    if (jw >= N2) return;
+    float nbv[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        nbv[nt][0] = nb_s[warp * KM_COLS + 8 * nt + 2 * t];
+        nbv[nt][1] = nb_s[warp * KM_COLS + 8 * nt + 2 * t + 1];
+    }
+    float dadd = 0.f;
+    if (SYM) dadd = diag_const + (diag_add ? diag_add[(int64_t)s * sDiag] : 0.f);
+
+    for (int rt = 0; rt < nrows; rt += 16) {
+        // A fragments: a0 = (row g, k = t), a1 = (row g + 8, k = t), a2 = (row g, k = t + 4), a3 = (row g + 8, k = t + 4)
+        unsigned ah[2][4], al[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int o0 = (rt + g) * DP + 8 * ks + t, o1 = (rt + g + 8) * DP + 8 * ks + t;
+            ah[ks][0] = ah_s[o0]; ah[ks][1] = ah_s[o1]; ah[ks][2] = ah_s[o0 + 4]; ah[ks][3] = ah_s[o1 + 4];
+            al[ks][0] = al_s[o0]; al[ks][1] = al_s[o1]; al[ks][2] = al_s[o0 + 4]; al[ks][3] = al_s[o1 + 4];
+        }
+        const float na0 = na_s[rt + g], na1 = na_s[rt + g + 8];
+        const int ia = i0 + rt + g, ib = ia + 8;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                mma_tf32_16x8x8(c, al[ks], bh[nt][ks][0], bh[nt][ks][1]);
+                mma_tf32_16x8x8(c, ah[ks], bl[nt][ks][0], bl[nt][ks][1]);
+                mma_tf32_16x8x8(c, ah[ks], bh[nt][ks][0], bh[nt][ks][1]);
+            }
+            const int j = jw + 8 * nt + 2 * t;
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = (q < 2) ? ia : ib, jj = j + (q & 1);
+                float e = c[q] + ((q < 2) ? na0 : na1) + nbv[nt][q & 1];
+                if (SYM && i == jj) e = RBF_FOLD ? -l2v : 0.f;          // exact on the diagonal of K(X, X)
+                if (RBF_FOLD) o[q] = ex2_approx(-e);
+                else o[q] = matern_value_l2<KIND>(e, l2v);
+                if (SYM && i == jj) o[q] += dadd;
+            }
+            if (ia < N) {
+                float* dst = outs + (int64_t)ia * ldo + j;
+                if (vec2_ok && j + 1 < N2) __stcs(reinterpret_cast<float2*>(dst), make_float2(o[0], o[1]));
+                else { if (j < N2) dst[0] = o[0]; if (j + 1 < N2) dst[1] = o[1]; }
+            }
+            if (ib < N) {
+                float* dst = outs + (int64_t)ib * ldo + j;
+                if (vec2_ok && j + 1 < N2) __stcs(reinterpret_cast<float2*>(dst), make_float2(o[2], o[3]));
+                else { if (j < N2) dst[0] = o[2]; if (j + 1 < N2) dst[1] = o[3]; }
+            }
+        }
+    }
+}
+
+template <int KIND>
+static int launch_fwd_mma(const float* X, const float* X2, const float* ls, int ls_len, const float* var, const float* diag_add,
+                          double diag_const, float* out, int64_t ldo, int S, int N, int N2, int D, int64_t sX, int64_t sX2,
+                          int64_t sLs, int64_t sVar, int64_t sDiag, int64_t sOut, cudaStream_t st) {
+    const bool sym = (X2 == nullptr);
+    const float* X2e = sym ? X : X2;
+    const int64_t sX2e = sym ? sX : sX2;
+    const int colblocks = cdiv(N2, 8 * KM_COLS);
+    int chunk = 256;
+    while (chunk > 16 && (int64_t)colblocks * cdiv(N, chunk) * S < 2 * kNumSMs) chunk >>= 1;
+    const size_t smem = (size_t)chunk * 16 * 8 + sizeof(float) * ((size_t)chunk + 16 + 8 * KM_COLS);
+    dim3 grid(colblocks, cdiv(N, chunk), S);
+    if (grid.y > 65535) return MXF_ENOTIMPL;
+    const int vec2_ok = (ldo % 2 == 0) && (sOut % 2 == 0) && (((uintptr_t)out) % 8 == 0);
+    if (sym)
+        kbuild_fwd_mma_kernel<KIND, true><<<grid, 256, smem, st>>>(X, X2e, ls, ls_len, var, diag_add, (float)diag_const, out, ldo, N,
+                                                                    N2, D, chunk, sX, sX2e, sLs, sVar, sDiag, sOut, vec2_ok);
+    else
+        kbuild_fwd_mma_kernel<KIND, false><<<grid, 256, smem, st>>>(X, X2e, ls, ls_len, var, diag_add, (float)diag_const, out, ldo, N,
+                                                                     N2, D, chunk, sX, sX2e, sLs, sVar, sDiag, sOut, vec2_ok);
+    return after_launch();
+}
+
 template <typename T, int KIND, int DP>
 static int dispatch_fwd_stream_wc(const T* X, const T* X2, const T* ls, int ls_len, const T* var, const T* diag_add,
                                   double diag_const, T* out, int64_t ldo, int S, int N, int N2, int D, int64_t sX,
@@ -421,6 +602,15 @@ static int dispatch_fwd_stream_wc(const T* X, const T* X2, const T* ls, int ls_l
 #undef MXF_KS_ARGS
 }
 
+// Measured on B200 (N=1e6, M=1024, D=16): 1.46 ms RBF / 1.74 ms Matern-5/2 = 0.43 / 0.36 of the HBM peak, against 0.48 /
+// 0.40 for the FMA kernel: the legacy warp-level TF32 MMA runs at about the FP32 FMA rate on sm_100 (48 HMMA.1688 per
+// 16 x 64 tile ~ 1.5k cycles per warp), so three of them per multiply-add lose to one FFMA.  Kept as an opt-in
+// (MXF_KBUILD_MMA=1) and as the parity-tested starting point of a tcgen05 version; off by default.
+static bool kbuild_mma_disabled() {
+    static int on = [] { const char* e = getenv("MXF_KBUILD_MMA"); return (e && e[0] == '1') ? 1 : 0; }();
+    return on == 0;
+}
+
 template <typename T, int KIND>
 static int dispatch_fwd_dc(const T* X, const T* X2, const T* ls, int ls_len, const T* var,
                            const T* diag_add, double diag_const, T* out, int64_t ldo, int S, int N,
@@ -431,6 +621,11 @@ static int dispatch_fwd_dc(const T* X, const T* X2, const T* ls, int ls_len, con
 #define MXF_KS_ARGS X, X2, ls, ls_len, var, diag_add, diag_const, out, ldo, S, N, N2, D, sX, sX2, sLs, sVar, sDiag, sOut, st
         if (D <= 4) return dispatch_fwd_stream_wc<T, KIND, 4>(MXF_KS_ARGS);
         if (D <= 8) return dispatch_fwd_stream_wc<T, KIND, 8>(MXF_KS_ARGS);
+        if constexpr (sizeof(T) == 4) {
+            if (D > 8 && D <= 16 && N2 >= 64 && !kbuild_mma_disabled())
+                return launch_fwd_mma<KIND>(X, X2, ls, ls_len, var, diag_add, diag_const, out, ldo, S, N, N2, D, sX, sX2, sLs,
+                                            sVar, sDiag, sOut, st);
+        }
         if (D <= 16 && sizeof(T) == 4) return dispatch_fwd_stream_wc<T, KIND, 16>(MXF_KS_ARGS);
 #undef MXF_KS_ARGS
     }

@@ -6,7 +6,7 @@ set -x
 O=gpurun_out/sanitizer
 mkdir -p $O
 export MXF_DAG_TIMEOUT_S=600
-CS="compute-sanitizer --print-limit 20 --error-exitcode 9"
+CS="compute-sanitizer --print-limit 20 --error-exitcode 9 --report-api-errors no"
 run() {  # name, tool, pytest -k expression, test file
     timeout 900 $CS --tool $2 python -m pytest $4 -x -q -m gpu -k "$3" > $O/$1_$2.log 2>&1
     echo "$1 $2 rc=$?" >> $O/summary.txt
@@ -19,7 +19,7 @@ run potrf_packed memcheck "test_potrf_packed_and_pack_contents and f32 and (65 o
 run gemm_tc memcheck "test_trsm_solve_large_blocks and f32 and (256 or 768)" tests/test_gpu_kernels.py
 run gemm_tc racecheck "test_trsm_solve_large_blocks and f32 and 256" tests/test_gpu_kernels.py
 run kbuild memcheck "test_kbuild_cross and f32" tests/test_gpu_kernels.py
-run kbuild racecheck "test_kbuild_cross and f32 and kind0" tests/test_gpu_kernels.py
+run kbuild racecheck "test_kbuild_cross and f32" tests/test_gpu_kernels.py
 run mlp memcheck "mlp_tanh" tests/test_gpu_kernels.py
 run mlp racecheck "mlp_tanh" tests/test_gpu_kernels.py
 run step memcheck "test_svgp_minibatch_paths_agree" tests/test_gpu_api.py
