@@ -296,10 +296,9 @@ __device__ __forceinline__ bool wait_flags(const int* f0, const int* f1, int* ab
 // all threads' global stores of a finished tile -> visible to every SM, then the flag
 __device__ __forceinline__ void publish(int* flag) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        st_release(flag, 1);
-    }
+    // st.release.gpu orders this thread's AND (by cumulativity through the barrier above) the other threads' prior stores
+    // before the flag: no separate __threadfence() (it was a second full-strength fence on the critical path)
+    if (threadIdx.x == 0) st_release(flag, 1);
 }
 
 // ---- 32-column warp-register Cholesky panel ----------------------------------------------------------------------------
@@ -624,8 +623,7 @@ potrf_dag_kernel(const DagParams p) {
             float l1[4][4] = {};
             mma_nt<false>(bufX, bufY, l1, m);
             DG_STAMP(c, 4);
-            store_acc(A + (int64_t)i0 * lda + i0 - B, lda, l1, re, B, vA, m);
-            publish(&sync.Lfin[c * T + (c - 1)]);
+            store_acc(A + (int64_t)i0 * lda + i0 - B, lda, l1, re, B, vA, m);     // in flight while the update below runs
             DG_STAMP(c, 5);
             // A_cc -= L_{c,c-1} L_{c,c-1}^T
             __syncthreads();
@@ -633,7 +631,7 @@ potrf_dag_kernel(const DagParams p) {
             acc_to_tile<2>(bufY, l1, m);
             __syncthreads();
             mma_nt<true>(bufX, bufY, acc2, m);
-            __syncthreads();
+            publish(&sync.Lfin[c * T + (c - 1)]);       // the tile's stores have long landed: the release is cheap here
             DG_STAMP(c, 6);
         }
         // factor / invert the 64 x 64 block

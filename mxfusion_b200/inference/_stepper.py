@@ -48,16 +48,68 @@ class Stepper(object):
         # eager warm-up steps live on the stream the capture will use
         self.stream = torch.cuda.Stream(device=self.static_in[0].device) if self.use_graph else None
         self.warmup_steps = warmup_steps
+        # data parallel: the gradient of the largest parameter is all-reduced on `comm` while the backward pass continues;
+        # with MXF_DP_INGRAPH=1 (opt-in) the collectives and the Adam update are captured in the step's CUDA graph as well
+        import os
+        self.comm = torch.cuda.Stream(device=self.static_in[0].device) if (self.world > 1 and self.static_in and
+                                                                             self.static_in[0].is_cuda) else None
+        self.in_graph = bool(self.use_graph) and self.world > 1 and os.environ.get('MXF_DP_INGRAPH', '0') == '1'
+        # OFF by default: with torch 2.11 / NCCL 2.28 a dist.all_reduce issued from inside the captured backward pass hung
+        # both ranks on a 2 x B200 box (capture or first replay), so the default data-parallel step
+        # keeps the collective OUTSIDE the graph: replay -> all-reduce of the bucket -> fused Adam.  MXF_DP_EARLY=1 enables
+        # the early reduce for eager (use_cuda_graph=False) steps.
+        self.early_reduce_enabled = os.environ.get('MXF_DP_EARLY', '0') == '1' and (self.in_graph or not self.use_graph)
+        self._early, self._early_segment = None, None
         self.n_calls = 0
         self.launches_per_step = None    # library kernels launched by one forward+backward (counted on an eager step)
+
+    # ---- data-parallel plumbing ------------------------------------------------------------------------------------
+    def _early_reduce(self, t):
+        """Called from inside the backward pass (ops.set_early_reduce) with the gradient of the largest parameter: its
+        all-reduce starts now, on the communication stream, and overlaps the rest of the backward pass."""
+        if self._early is not None:
+            return                                              # one tensor per step
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        self._early = (t.data_ptr(), t.numel())
+
+    def _reduce_rest(self):
+        """All-reduce of the gradient bucket, minus the segment that was reduced early."""
+        p = self.params
+        if self._early is None:
+            dist.all_reduce(p.gflat, op=dist.ReduceOp.SUM)
+            return
+        seg = self._early_segment
+        if seg is None:
+            raise InferenceError("data-parallel step: the early-reduced gradient does not belong to a parameter segment")
+        off, n = seg
+        if off > 0:
+            dist.all_reduce(p.gflat[:off], op=dist.ReduceOp.SUM)
+        if off + n < p.gflat.numel():
+            dist.all_reduce(p.gflat[off + n:], op=dist.ReduceOp.SUM)
 
     def _fwd_bwd(self):
         if self.fused:
             self.params.transform_all_()
             self.params.clear_leaf_grads()
-            loss, loss_for_gradient = self.executor(None, *self.static_in)
-            loss_for_gradient.backward()
+            self._early, self._early_segment = None, None
+            if self.world > 1 and self.comm is not None and self.early_reduce_enabled:
+                ops.set_early_reduce(self._early_reduce)
+            try:
+                loss, loss_for_gradient = self.executor(None, *self.static_in)
+                loss_for_gradient.backward()
+            finally:
+                ops.set_early_reduce(None)
+            if self._early is not None:
+                torch.cuda.current_stream().wait_stream(self.comm)          # the reduced values are packed below
+                for _, p, off, n, k, _ in self.params._segments:
+                    g = (p.tleaf if k == 1 else p.tensor).grad
+                    if g is not None and g.data_ptr() == self._early[0] and g.numel() == self._early[1]:
+                        self._early_segment = (off, n)
             self.params.pack_grads_()
+            if self.world > 1 and self.in_graph:
+                self._update()
             return loss.detach().reshape(())
         self.params.gflat.zero_()
         loss, loss_for_gradient = self.executor(None, *self.static_in)
@@ -67,7 +119,10 @@ class Stepper(object):
     def _update(self):
         p = self.params
         if self.world > 1:
-            dist.all_reduce(p.gflat, op=dist.ReduceOp.SUM)
+            if self.fused:
+                self._reduce_rest()
+            else:
+                dist.all_reduce(p.gflat, op=dist.ReduceOp.SUM)
         ops.R.adam_step_(p.flat, p.gflat, p.adam_m, p.adam_v, p.adam_t, lr=self.lr, rescale=self.rescale)
 
     def step(self, batch=None):
@@ -99,5 +154,6 @@ class Stepper(object):
         else:
             self.graph.replay()
             self.loss = self._static_loss
-        self._update()
+        if not (self.world > 1 and self.in_graph and self.fused):
+            self._update()
         return self.loss

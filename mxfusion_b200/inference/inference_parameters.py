@@ -147,7 +147,10 @@ class InferenceParameters(object):
     def _allocate(self):
         dt, dev = torch_dtype(self.dtype), self.mxnet_context
         total = 0
-        for p in self._params.values():
+        # large parameters (qU_cov_W: M^2 elements) go to the END of the bucket: a data-parallel step all-reduces them early,
+        # from inside the backward pass, and the remainder is then ONE contiguous prefix (inference/_stepper.py)
+        order = sorted(self._params.values(), key=lambda q: (int(np.prod(q.shape)) if len(q.shape) else 1) >= 65536)
+        for p in order:
             # every view starts on a 128-byte boundary: TMA / vectorised kernels read parameters in place
             total = (total + 31) & ~31
             p.offset = total

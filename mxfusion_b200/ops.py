@@ -451,15 +451,19 @@ class _SVGPLogPdf(torch.autograd.Function):
         R.axpby2d(gsb, v, neg_g, mt, out=F2[:, :, 2 * M:2 * M + P])
         F2 = R.trsm_solve(L, pk, F2, transpose=True)
         dKuu = F2[:, :, :M]
+        # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 (S^-1 from the forward pass); W adjoint 2 Sbar W ; diag adjoint diag(Sbar).
+        # Formed BEFORE the kernel adjoints: qU_cov_W's gradient is 93 % of the gradient bucket (M^2 of M^2 + M D + ...),
+        # and a data-parallel run starts its all-reduce here, under the ~100 us of kernel-adjoint work that follows
+        Sbar = R.axpby2d(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M])
+        dW = R.gemm(Sbar, W, alpha=2.0)
+        if _EARLY_REDUCE[0] is not None and need[8]:
+            _EARLY_REDUCE[0](dW)
+        dd = R.get_diag(Sbar)
         dmu = torch.empty((S, M, P), dtype=dt, device=dev)
         R.copy2d_(dmu, F2[:, :, 2 * M:2 * M + P])
         dZ2, _, dls2, dvar2 = R.kbuild_bwd(ctx.kind, Z, None, ls, kvar, dKuu)
         if side is None:
             dZ1, dX, dls1, dvar1 = kuf_branch()
-        # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 (S^-1 from the forward pass); W adjoint 2 Sbar W ; diag adjoint diag(Sbar)
-        Sbar = R.axpby2d(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M])
-        dW = R.gemm(Sbar, W, alpha=2.0)
-        dd = R.get_diag(Sbar)
         dnoise = dnoise_s.unsqueeze(1)
         dY = R.axpby_dev(neg_gsb, Y, gsb, G1) if need[4] else None          # -g s beta (Y - A^T mt)
         if side is not None:
@@ -522,6 +526,15 @@ def check_factorisations(device, what="a Cholesky factorisation"):
         raise InferenceError("%s failed: the matrix is not positive definite (first non-positive pivot %d). Increase "
                              "`jitter` on the module's log-pdf algorithm (svgp_regression.py:70-72, "
                              "gp_regression.py:58-60) or check the kernel parameters." % (what, bad))
+
+
+# Data-parallel training (inference/_stepper.py) registers a callback here: it is handed the gradient of the largest
+# parameter as soon as it exists and starts its all-reduce on a communication stream.
+_EARLY_REDUCE = [None]
+
+
+def set_early_reduce(fn):
+    _EARLY_REDUCE[0] = fn
 
 
 _SIDE_STREAMS = {}

@@ -183,7 +183,7 @@ def test_two_rank_nccl_step_equals_the_concatenated_batch_step(cuda, tmp_path, m
     script.write_text(_NCCL_WORKER % (ROOT, str(tmp_path)))
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29741')
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr',
-                        '127.0.0.1', '--master-port', '29741', str(script)], env=env, capture_output=True, text=True, timeout=600)
+                        '127.0.0.1', '--master-port', '29741', str(script)], env=env, capture_output=True, text=True, timeout=150)
     assert r.returncode == 0, r.stderr[-3000:]
     f0, f1 = np.load(tmp_path / 'flat_rank0.npy'), np.load(tmp_path / 'flat_rank1.npy')
     np.testing.assert_array_equal(f0, f1)
