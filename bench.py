@@ -41,8 +41,8 @@ WORKLOADS = {'headline': (1000000, 1024, 8, 4096, 'rbf'), 'c2': (100000, 512, 8,
 OTHER_WORKLOADS = ('c1', 'c4', 'c5')      # exact GP N=512 D=2 / mean-field BNN / 2-layer deep GP: see run_other()
 PARITY_STEPS = 25
 JITTER, LR = 1e-6, 1e-2
-KBUILD_NCU_TRAFFIC_BYTES = 4068866256      # committed capture profiles/r1e_kbuild_raw.csv (round-1 commit 5327006; the kernel
-                                           # is unchanged since): 32.06 MB read + 4036.8 MB written per launch
+KBUILD_NCU_TRAFFIC_BYTES = 4069040680      # committed capture profiles/r2_kbuild_raw.csv (ncu --set full, this round):
+                                           # 32.14 MB read + 4036.9 MB written per launch
 METRIC = "svgp_elbo_iters_per_sec"
 UNIT = "minibatch iterations (B=4096 rows: ELBO fwd + grad + Adam) per second, summed over GPUs"
 
@@ -200,7 +200,7 @@ def kernel_rooflines(device, pk):
             'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
             'traffic': KBUILD_NCU_TRAFFIC_BYTES if same else None,
             'traffic_source': ('committed capture (not measured in this run): dram__bytes_read.sum + dram__bytes_write.sum '
-                               'per launch, ncu --set full, profiles/r1e_kbuild_raw.csv (0.032 GB read + 4.037 GB written)')
+                               'per launch, ncu --set full, profiles/r2_kbuild_raw.csv (0.032 GB read + 4.037 GB written)')
             if same else None,
             'ms_per_launch': ms, 'algorithmic_bytes': nbytes,
             'note': 'stand-alone launch at the BASELINE "K(X,Z) HBM GB/s" size; inside the timed step Kuf is 1024 x 4096 and '

@@ -301,216 +301,163 @@ __device__ __forceinline__ void publish(int* flag) {
     if (threadIdx.x == 0) st_release(flag, 1);
 }
 
-// ---- 32-column warp-register Cholesky panel ----------------------------------------------------------------------------
-// Lane i holds row i of the 32 x 32 pivot block in r0[0..31] (entries c <= i meaningful) and, when TWO, row 32 + i of the
-// block below it in r1[0..31].  Column step C: d = pivot (broadcast by the PREVIOUS step, which shuffles it out ahead of its
-// other updates, so that the pivot chain is shuffle -> rsqrt -> fmul -> fma), inv = d^-1/2, l_iC = r_i[C] inv, then
-// r_i[t] -= l_iC l_tC for t > C with l_tC shuffled from lane t; the rows below ride along on the same shuffles (their
-// triangular solve  L21 = A21 L11^-T  costs one extra FMA per shuffle and no extra latency).  Measured on B200
-// (scripts/ubench/chol32.cu): 4.2k cycles for the 32 x 32 block with everything in registers; shared-memory
-// formulations with run-time column loops: 10k-32k; carrying the inverse along (two shuffles per entry): 11k-18k.
+// ---- the 64 x 64 diagonal block: right-looking elimination of [A; I] with 16-column warp-register panels -------------------
+// The block is factored AND inverted by eliminating the augmented 128 x 64 matrix [A; I]: the column operations that turn A
+// into L turn I into L^-T, whose row i is column i of W = L^-1 -- the inverse costs extra ROWS riding on the same column
+// operations, no substitution pass and no second algorithm.  Per 16 columns:
+//   * ONE warp holds the panel in registers (lane = row; up to four row sets: the 16 pivot rows + the A rows below, and the
+//     rows of I that are non-zero in these columns), and runs the 16 column steps: pivot broadcast by shuffle (shuffled out
+//     AHEAD of the step's other updates, so the pivot chain is shuffle -> rsqrt+Newton -> fmul -> fma), column broadcast by
+//     one shuffle per entry, every row set updated by one FMA per shuffle;
+//   * all eight warps apply the rank-16 update to the remaining columns (64 rows x 48 / 32 / 16 columns, 16-byte shared loads).
+// 16 column steps are ~14 KB of straight-line code executed four times per block -- it stays in the instruction caches --
+// where the 32-column version of this kernel (two 32 KB panels + a separate inverse) ran its first panel cold at 9-10k
+// cycles against 5.4k warm (profiles/r2_potrf_dataflow.md).
+// FACTOR = false: A already holds L; only the rows of I are eliminated (mxf_tri_pack).
 __device__ __forceinline__ float rsqrt_newton(float d) {
     const float y = rsqrtf(d);
     return y * fmaf(-0.5f * d * y, y, 1.5f);
 }
 
-// Column steps are template-recursive so that every register index is a compile-time constant: ~40 KB of straight-line
-// code.  Executed COLD (first time on an SM) it runs at ~11 cycles per instruction -- 17k cycles against 3.3k-4.2k warm
-// (scripts/ubench/chol32.cu) -- so (a) there is ONE instantiation, used for both 32-column panels of a diagonal block
-// (the second call is warm by construction), and (b) a diagonal ticket, which has nothing to do until the previous
-// diagonal block is finished, first runs the whole diagonal-block code once on an identity tile to pull it into the
-// instruction caches.  A rotating-register-window loop (4 x 12 KB body) was measured slower than this (31k-35k
-// cycles per diagonal block against 25k-30k, both cold).
-template <int C>
-struct PanelStep {
-    static __device__ __forceinline__ void run(float (&r0)[32], float (&r1)[32], float dcur, int& bad) {
-        if (!(dcur > 0.f) && bad == 0) bad = C + 1;
-        const float inv = rsqrt_newton(dcur);
-        const float l0 = r0[C] * inv;                 // l_iC for lanes >= C (don't-care above the diagonal)
-        const float l1 = r1[C] * inv;
-        r0[C] = l0;
-        r1[C] = l1;
+template <bool FACTOR, int C>
+struct Panel16Step {
+    static __device__ __forceinline__ void run(float (&a0)[16], float (&a1)[16], float (&x0)[16], float (&x1)[16], float dcur,
+                                               int& bad) {
+        float inv;
+        if (FACTOR) {
+            if (!(dcur > 0.f) && bad == 0) bad = C + 1;
+            inv = rsqrt_newton(dcur);
+        } else {
+            inv = 1.0f / dcur;
+        }
+        const float l0 = FACTOR ? a0[C] * inv : a0[C];        // L[row][C] of the A rows (don't-care above the diagonal)
+        const float l1 = FACTOR ? a1[C] * inv : a1[C];
+        const float m0 = x0[C] * inv, m1 = x1[C] * inv;       // (L^-T)[row][C] of the identity rows
+        if (FACTOR) { a0[C] = l0; a1[C] = l1; }
+        x0[C] = m0;
+        x1[C] = m1;
         float dnext = 0.f;
-        // the next pivot first: lane C+1 needs only its OWN l -- no second shuffle on the pivot chain
-        if (C + 1 < 32) dnext = __shfl_sync(0xffffffffu, fmaf(-l0, l0, r0[(C + 1) & 31]), (C + 1) & 31);
-#pragma unroll
-        for (int t = C + 1; t < 32; ++t) {
-            const float ltc = __shfl_sync(0xffffffffu, l0, t);
-            r0[t] = fmaf(-l0, ltc, r0[t]);
-            r1[t] = fmaf(-l1, ltc, r1[t]);
+        if (C + 1 < 16) {
+            // the next pivot first: lane C+1 needs only its OWN l -- no second shuffle on the pivot chain
+            const float cand = FACTOR ? fmaf(-l0, l0, a0[(C + 1) & 15]) : a0[(C + 1) & 15];
+            dnext = __shfl_sync(0xffffffffu, cand, (C + 1) & 15);
         }
-        PanelStep<C + 1>::run(r0, r1, dnext, bad);
+#pragma unroll
+        for (int t = C + 1; t < 16; ++t) {
+            const float ltc = __shfl_sync(0xffffffffu, l0, t);         // L[pivot row t][C]
+            if (FACTOR) {
+                a0[t] = fmaf(-l0, ltc, a0[t]);
+                a1[t] = fmaf(-l1, ltc, a1[t]);
+            }
+            x0[t] = fmaf(-m0, ltc, x0[t]);
+            x1[t] = fmaf(-m1, ltc, x1[t]);
+        }
+        Panel16Step<FACTOR, C + 1>::run(a0, a1, x0, x1, dnext, bad);
     }
 };
-template <>
-struct PanelStep<32> {
-    static __device__ __forceinline__ void run(float (&)[32], float (&)[32], float, int&) {}
-};
-
-// One warp: Cholesky of the 32 x 32 block at D[p0.., p0..] (row stride LDP) with ONE more row set riding along on the
-// same shuffles (one extra FMA per shuffle, no extra latency; measured 4.4k cycles against 3.1k without it and 7.5k with
-// two extra sets, scripts/ubench/chol32.cu):
-//   inverse == false: the 32 rows below the block, D[p0+32.., p0..] <- D[p0+32.., p0..] L^-T (the panel solve); L is
-//                     written back in place (zeros above its diagonal);
-//   inverse == true:  the rows of the IDENTITY: I L^-T = L^-T, so lane i ends up holding column i of W = L^-1, written to
-//                     Wd[p0.., p0 + i] -- the inverse of the block without a substitution pass; L is written back only
-//                     if write_l (two warps may run the two flavours on the same block at the same time: same code,
-//                     one instruction stream through the caches).
-// Returns the 1-based failing pivot (0: none).
-__device__ __noinline__ int warp_chol_panel32(float* D, float* Wd, int p0, int lane, bool inverse, bool write_l, bool pair_sync) {
-    float r0[32], r1[32];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(D + (p0 + lane) * LDP + p0 + 4 * q);
-        r0[4 * q] = v.x; r0[4 * q + 1] = v.y; r0[4 * q + 2] = v.z; r0[4 * q + 3] = v.w;
-        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!inverse) u = *reinterpret_cast<const float4*>(D + (p0 + 32 + lane) * LDP + p0 + 4 * q);
-        r1[4 * q] = u.x; r1[4 * q + 1] = u.y; r1[4 * q + 2] = u.z; r1[4 * q + 3] = u.w;
-    }
-    if (inverse) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) r1[c] = (c == lane) ? 1.f : 0.f;
-    }
-    if (pair_sync) asm volatile("bar.sync 1, 64;" ::: "memory");      // both flavours have read the block
-    int bad = 0;
-    PanelStep<0>::run(r0, r1, __shfl_sync(0xffffffffu, r0[0], 0), bad);
-    if (write_l) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float4 v;
-            v.x = (4 * q <= lane) ? r0[4 * q] : 0.f;
-            v.y = (4 * q + 1 <= lane) ? r0[4 * q + 1] : 0.f;
-            v.z = (4 * q + 2 <= lane) ? r0[4 * q + 2] : 0.f;
-            v.w = (4 * q + 3 <= lane) ? r0[4 * q + 3] : 0.f;
-            *reinterpret_cast<float4*>(D + (p0 + lane) * LDP + p0 + 4 * q) = v;
-        }
-    }
-    if (!inverse) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(D + (p0 + 32 + lane) * LDP + p0 + 4 * q) =
-                make_float4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
-    } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) Wd[(p0 + c) * LDP + p0 + lane] = (c >= lane) ? r1[c] : 0.f;     // W[c][lane]
-    }
-    return bad;
-}
-
-// One warp: W = L^-1 for the 32 x 32 lower-triangular block at D[p0.., p0..] -> Wd[p0.., p0..] (zeros above the diagonal).
-// Lane j owns column j of W; right-looking forward substitution with the 32 running right-hand sides in registers:
-// x_i = acc_i / L_ii, then acc_i' -= L_i'i x_i for i' > i (independent FMAs; L_i'i is a warp-uniform shared-memory load).
-template <int I>
-struct InvStep32 {
-    static __device__ __forceinline__ void run(float (&acc)[32], const float* Dblk, float idg_all) {
-        const float x = acc[I] * __shfl_sync(0xffffffffu, idg_all, I);
-        acc[I] = x;
-#pragma unroll
-        for (int t = I + 1; t < 32; ++t) acc[t] = fmaf(-Dblk[t * LDP + I], x, acc[t]);
-        InvStep32<I + 1>::run(acc, Dblk, idg_all);
-    }
-};
-template <>
-struct InvStep32<32> {
-    static __device__ __forceinline__ void run(float (&)[32], const float*, float) {}
-};
-
-__device__ __noinline__ void warp_inv32(const float* D, float* Wd, int p0, int lane) {
-    const float* Dblk = D + p0 * LDP + p0;
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = (i == lane) ? 1.f : 0.f;
-    const float idg_all = 1.0f / Dblk[lane * LDP + lane];
-    InvStep32<0>::run(acc, Dblk, idg_all);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) Wd[(p0 + i) * LDP + p0 + lane] = acc[i];      // acc[i] = 0 for i < lane
-}
-
-// out[r][c] (32 x 32 at Out, stride LDP) = alpha * sum_t X[r][t] * (NT ? Y[c][t] : Y[t][c]) (+ Out if ACCUM)
-// X, Y, Out: 32 x 32 blocks in plain buffers (row stride LDP, 16-byte aligned rows).  Warps w0 .. w0+nw-1 take part: warp w
-// takes rows w - w0, w - w0 + nw, ...; lane = output column; the lane's Y vector sits in registers, the X rows are
-// warp-uniform 16-byte loads.
-template <bool NT, bool ACCUM>
-__device__ __forceinline__ void small_mm32(float* Out, const float* X, const float* Y, float alpha, int w0 = 0, int nw = 8) {
-    const int warp = (threadIdx.x >> 5) - w0, lane = threadIdx.x & 31;
-    if (warp < 0 || warp >= nw) return;
-    float y[32];
-    if (NT) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(Y + lane * LDP + 4 * q);
-            y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int t = 0; t < 32; ++t) y[t] = Y[t * LDP + lane];
-    }
-    for (int row = warp; row < 32; row += nw) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 x = *reinterpret_cast<const float4*>(X + row * LDP + 4 * q);
-            s0 = fmaf(x.x, y[4 * q], s0);
-            s1 = fmaf(x.y, y[4 * q + 1], s1);
-            s2 = fmaf(x.z, y[4 * q + 2], s2);
-            s3 = fmaf(x.w, y[4 * q + 3], s3);
-        }
-        const float v = alpha * ((s0 + s1) + (s2 + s3));
-        if (ACCUM) Out[row * LDP + lane] += v;
-        else Out[row * LDP + lane] = v;
-    }
-}
-
-// 64 x 64 diagonal block in D (plain, stride LDP; lower part meaningful, padded with identity): factor (FACTOR) and
-// invert.  On exit D = L (zeros above the diagonal), Wd = L^-1 (zeros above).  Tm: 32 x LDP scratch.
-//   warp 0: panel Cholesky of columns 0..31 (L11 and L21), warp 1 the same code on [A11; I] (W11 = L11^-1) -> all:
-//   A22 -= L21 L21^T -> warp 0: Cholesky of [A22; I] (L22, W22) while warps 1..7 form L21 W11 -> all: W21 = -W22 (L21 W11).
 template <bool FACTOR>
-__device__ __forceinline__ int diag_block_64(float* D, float* Wd, float* Tm, long long* st = nullptr) {
+struct Panel16Step<FACTOR, 16> {
+    static __device__ __forceinline__ void run(float (&)[16], float (&)[16], float (&)[16], float (&)[16], float, int&) {}
+};
+
+__device__ __forceinline__ void ld16(float (&v)[16], const float* p, bool valid) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) u = *reinterpret_cast<const float4*>(p + 4 * q);
+        v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+    }
+}
+__device__ __forceinline__ void st16(float* p, const float (&v)[16], bool valid) {
+    if (!valid) return;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+// One warp: the 16 column steps of panel p (columns c0 = 16 p ..) on D = [A; I] (128 rows, row stride LDP).
+// Row sets (lane = row): a0 = A rows c0 + lane (the pivot rows are lanes 0..15), a1 = A rows c0 + 32 + lane, x0 / x1 = rows
+// lane / 32 + lane of the identity part (non-zero in these columns only for rows <= c0 + 15).
+template <bool FACTOR>
+__device__ __noinline__ int warp_panel16(float* D, int p, int lane) {
+    const int c0 = 16 * p;
+    float a0[16], a1[16], x0[16], x1[16];
+    const bool va0 = c0 + lane < B, va1 = c0 + 32 + lane < B, vx0 = lane <= c0 + 15, vx1 = 32 + lane <= c0 + 15;
+    ld16(a0, D + (c0 + lane) * LDP + c0, va0);
+    ld16(a1, D + (c0 + 32 + lane) * LDP + c0, va1);
+    ld16(x0, D + (B + lane) * LDP + c0, vx0);
+    ld16(x1, D + (B + 32 + lane) * LDP + c0, vx1);
+    int bad = 0;
+    Panel16Step<FACTOR, 0>::run(a0, a1, x0, x1, __shfl_sync(0xffffffffu, a0[0], 0), bad);
+    if (FACTOR) {
+        st16(D + (c0 + lane) * LDP + c0, a0, va0);
+        st16(D + (c0 + 32 + lane) * LDP + c0, a1, va1);
+    }
+    st16(D + (B + lane) * LDP + c0, x0, vx0);
+    st16(D + (B + 32 + lane) * LDP + c0, x1, vx1);
+    return bad != 0 ? c0 + bad : 0;
+}
+
+// All warps: rank-16 update of the columns to the right of panel p.  64 rows are live (A rows below the pivot rows and
+// identity rows 0 .. c0+15: 48 - 16 p + 16 p + 16 = 64): thread = (row, group of 4 consecutive columns); the 4 x 16 factor
+// rows are warp-uniform 16-byte loads, the thread's own panel row sits in registers.
+template <bool FACTOR>
+__device__ __forceinline__ void panel16_update(float* D, int p) {
+    const int c0 = 16 * p, cr0 = c0 + 16;
+    const int ncg = (B - cr0) / 16;                       // 16-column groups to the right: 3, 2, 1, 0
+    if (ncg <= 0) return;
+    const int ri = threadIdx.x & 63, cq = threadIdx.x >> 6;                   // row index, column quad within a group
+    const int nA = B - cr0;
+    const int row = ri < nA ? cr0 + ri : B + (ri - nA);                       // A row or identity row
+    if (!FACTOR && ri < nA) return;                        // the given factor is not modified
+    float pr[16];
+    ld16(pr, D + row * LDP + c0, true);
+    for (int g = 0; g < ncg; ++g) {
+        const int c = cr0 + 16 * g + 4 * cq;
+        float4 r4 = *reinterpret_cast<const float4*>(D + row * LDP + c);
+        float acc[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float* Lc = D + (c + b) * LDP + c0;      // factor row c + b, panel columns (same address across the warp)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 l = *reinterpret_cast<const float4*>(Lc + 4 * q);
+                acc[b] = fmaf(-pr[4 * q], l.x, acc[b]);
+                acc[b] = fmaf(-pr[4 * q + 1], l.y, acc[b]);
+                acc[b] = fmaf(-pr[4 * q + 2], l.z, acc[b]);
+                acc[b] = fmaf(-pr[4 * q + 3], l.w, acc[b]);
+            }
+        }
+        *reinterpret_cast<float4*>(D + row * LDP + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+// D: 128 rows x LDP.  Rows 0..63: the block (lower part meaningful, padded with identity), rows 64..127: written here.
+// On exit rows 0..63 hold L in their lower part (the upper part is NOT cleaned: mask on the way out), rows 64..127 hold
+// L^-T (exact zeros below its diagonal): W[r][c] = D[64 + c][r].  Returns the 1-based failing pivot (0: none).
+template <bool FACTOR>
+__device__ __forceinline__ int diag_block_64(float* D, long long* st = nullptr) {
 #define DG_ST(i) do { if (st && threadIdx.x == 0) st[i] = clock64(); } while (0)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ int bad_sh[2];
-    if (threadIdx.x < 2) bad_sh[threadIdx.x] = 0;
-    for (int e = threadIdx.x; e < 32 * 32; e += DG_THREADS) {          // zero the upper-right 32 x 32 blocks
-        const int r = e >> 5, c = 32 + (e & 31);
-        D[r * LDP + c] = 0.f;
-        Wd[r * LDP + c] = 0.f;
+    __shared__ int bad_sh;
+    if (threadIdx.x == 0) bad_sh = 0;
+    for (int e = threadIdx.x; e < B * B; e += DG_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        D[(B + r) * LDP + c] = (r == c) ? 1.f : 0.f;
     }
     __syncthreads();
-    if (FACTOR) {
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
         if (warp == 0) {
-            const int b = warp_chol_panel32(D, Wd, 0, lane, false, true, true);             // L11, L21
-            if (lane == 0) bad_sh[0] = b;
-        } else if (warp == 1) {
-            warp_chol_panel32(D, Wd, 0, lane, true, false, true);                            // W11 (same code, same time)
+            const int b = warp_panel16<FACTOR>(D, p, lane);
+            if (lane == 0 && b != 0 && bad_sh == 0) bad_sh = b;
         }
         __syncthreads();
-        DG_ST(0);
-        small_mm32<true, true>(D + 32 * LDP + 32, D + 32 * LDP, D + 32 * LDP, -1.f);       // A22 -= L21 L21^T
-        __syncthreads();
-        DG_ST(1);
-        if (warp == 0) {
-            const int b = warp_chol_panel32(D, Wd, 32, lane, true, true, false);            // L22, W22
-            if (lane == 0) bad_sh[1] = b;
-        }
-        small_mm32<false, false>(Tm, D + 32 * LDP, Wd, 1.f, 1, 7);                         // Tm = L21 W11 (warps 1..7)
-        __syncthreads();
-        DG_ST(2);
-        DG_ST(3);
-    } else {
-        if (warp == 0) warp_inv32(D, Wd, 0, lane);
-        else if (warp == 1) warp_inv32(D, Wd, 32, lane);
-        __syncthreads();
-        small_mm32<false, false>(Tm, D + 32 * LDP, Wd, 1.f);
+        DG_ST(p);
+        panel16_update<FACTOR>(D, p);
         __syncthreads();
     }
-    small_mm32<false, false>(Wd + 32 * LDP, Wd + 32 * LDP + 32, Tm, -1.f);                  // W21 = -W22 Tm
-    __syncthreads();
     DG_ST(4);
-    int bad = 0;
-    if (bad_sh[0] != 0) bad = bad_sh[0];
-    else if (bad_sh[1] != 0) bad = 32 + bad_sh[1];
-    return bad;
+    return bad_sh;
 #undef DG_ST
 }
 
@@ -522,6 +469,25 @@ __device__ __forceinline__ void plain_to_acc(float (&acc)[4][4], const float* P,
         acc[a][0] = v.x; acc[a][1] = v.y; acc[a][2] = v.z; acc[a][3] = v.w;
     }
 }
+// W[r][c] = X[c][r] with X = L^-T in the plain buffer: this thread's outputs read transposed
+__device__ __forceinline__ void plain_t_to_acc(float (&acc)[4][4], const float* X, const Map& m) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = X[(4 * m.tc + b) * LDP + m.tr + 16 * a];
+}
+// lower triangle of the plain buffer (the part above the diagonal of a factored block is not meaningful)
+__device__ __forceinline__ void plain_lower_to_acc(float (&acc)[4][4], const float* P, const Map& m) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = m.tr + 16 * a;
+        const float4 v = *reinterpret_cast<const float4*>(P + r * LDP + 4 * m.tc);
+        acc[a][0] = (4 * m.tc <= r) ? v.x : 0.f;
+        acc[a][1] = (4 * m.tc + 1 <= r) ? v.y : 0.f;
+        acc[a][2] = (4 * m.tc + 2 <= r) ? v.z : 0.f;
+        acc[a][3] = (4 * m.tc + 3 <= r) ? v.w : 0.f;
+    }
+}
 __device__ __forceinline__ void acc_to_plain(float* P, const float (&acc)[4][4], const Map& m) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -529,11 +495,11 @@ __device__ __forceinline__ void acc_to_plain(float* P, const float (&acc)[4][4],
 }
 
 // Shared memory: bufX | bufY (one swizzled tile each) | bufO (one tile: an accumulator turned operand).  The diagonal
-// ticket overlays its plain D / Wd / Tm buffers on the same space.
+// ticket's plain [A; I] buffer (128 x LDP) follows them.
 // One CTA per SM (the request is padded past half of the SM's shared memory): a diagonal ticket is the critical path of
 // the whole factorisation and a single warp carries most of it -- a co-resident CTA busy with tile products takes half of
 // its issue slots (measured: 20k -> see profiles/r2_potrf_dataflow.md).  The bulk tiles have slack to spare.
-constexpr size_t DG_SMEM_USED = sizeof(float) * (3 * TILE_F + 2 * B * LDP + 32 * LDP) + 64;
+constexpr size_t DG_SMEM_USED = sizeof(float) * (3 * TILE_F + 2 * B * LDP) + 64;
 constexpr size_t DG_SMEM = DG_SMEM_USED > 120 * 1024 ? DG_SMEM_USED : 120 * 1024;
 
 __global__ void __launch_bounds__(DG_THREADS, 1)
@@ -544,7 +510,6 @@ potrf_dag_kernel(const DagParams p) {
     float* bufO = bufY + TILE_F;
     float* Dp = bufO + TILE_F;           // [64][LDP]
     float* Wp = Dp + B * LDP;            // [64][LDP]
-    float* Tm = Wp + B * LDP;            // [32][LDP]
     __shared__ int sh_ticket, sh_flag;
 
     const int s = blockIdx.y;
@@ -593,8 +558,8 @@ potrf_dag_kernel(const DagParams p) {
                 for (int b = 0; b < 4; ++b) acc2[a][b] = (m.tr + 16 * a == 4 * m.tc + b) ? 1.f : 0.f;
             acc_to_plain(Dp, acc2, m);
             __syncthreads();
-            if (factor) diag_block_64<true>(Dp, Wp, Tm);
-            else diag_block_64<false>(Dp, Wp, Tm);
+            if (factor) diag_block_64<true>(Dp);
+            else diag_block_64<false>(Dp);
             __syncthreads();
         }
         load_acc(acc2, A + (int64_t)i0 * lda + i0, lda, re, re, vA, true, m);
@@ -639,11 +604,11 @@ potrf_dag_kernel(const DagParams p) {
         __syncthreads();
         long long* dst = (g_dag_prof && blockIdx.y == 0) ? g_dag_prof + 256 + c * 8 : nullptr;
         if (dst && threadIdx.x == 0) dst[5] = clock64();
-        const int bad = factor ? diag_block_64<true>(Dp, Wp, Tm, dst) : diag_block_64<false>(Dp, Wp, Tm, dst);
+        const int bad = factor ? diag_block_64<true>(Dp, dst) : diag_block_64<false>(Dp, dst);
         DG_STAMP(c, 7);
         if (factor && bad != 0 && bad <= re && threadIdx.x == 0 && p.info) atomicCAS(&p.info[s], 0, p.info_base + i0 + bad);
         float lw[4][4];
-        plain_to_acc(lw, Wp, m);
+        plain_t_to_acc(lw, Wp, m);                               // W = (L^-T)^T
         store_acc(W + (int64_t)i0 * ldw + i0, ldw, lw, re, re, vW, m);
         DG_STAMP(c, 8);
         publish(&sync.Wfin[c * T + c]);
@@ -672,7 +637,7 @@ potrf_dag_kernel(const DagParams p) {
             }
         }
         if (factor) {
-            plain_to_acc(lw, Dp, m);
+            plain_lower_to_acc(lw, Dp, m);
             store_acc(A + (int64_t)i0 * lda + i0, lda, lw, re, re, vA, m);
             if (LT) store_acc_t(LT + (int64_t)i0 * ldlt + i0, ldlt, lw, re, re, m);
         }

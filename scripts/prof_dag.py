@@ -41,7 +41,7 @@ for c in range(T):
     if c == 0:
         d = [0] * 6 + [p[0, 7] - p[0, 0], p[0, 8] - p[0, 7], p[0, 9] - p[0, 8]]
     print('%6d  ' % c + ' '.join('%7d' % x for x in d) + '   %8.1f %8.1f' % ((p[c, 14] - t0) / 1e3, (p[c, 15] - t0) / 1e3))
-print('diag block phases (cycles): panel(two)  syrk22  panel+inv11  inv22|L21W11  W21')
+print('diag block phases (cycles): identity+panel0  upd0+panel1  upd1+panel2  upd2+panel3  upd3')
 for c in range(T):
     q = inner[c]
     print('%6d  %8d %8d %8d %8d %8d' % (c, q[0] - q[5], q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3]))
