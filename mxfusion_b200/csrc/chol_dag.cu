@@ -500,9 +500,9 @@ __device__ __forceinline__ void acc_to_plain(float* P, const float (&acc)[4][4],
 // the whole factorisation and a single warp carries most of it -- a co-resident CTA busy with tile products takes half of
 // its issue slots (measured: 20k -> see profiles/r2_potrf_dataflow.md).  The bulk tiles have slack to spare.
 constexpr size_t DG_SMEM_USED = sizeof(float) * (3 * TILE_F + 2 * B * LDP) + 64;
-constexpr size_t DG_SMEM = DG_SMEM_USED > 120 * 1024 ? DG_SMEM_USED : 120 * 1024;
+constexpr size_t DG_SMEM = DG_SMEM_USED;      // ~83 KB: two CTAs per SM (see the note above)
 
-__global__ void __launch_bounds__(DG_THREADS, 1)
+__global__ void __launch_bounds__(DG_THREADS, 2)
 potrf_dag_kernel(const DagParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* bufX = reinterpret_cast<float*>(smem_raw);
