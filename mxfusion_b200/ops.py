@@ -375,6 +375,15 @@ class _SVGPLogPdf(torch.autograd.Function):
         sldL, sldLs = R.sumlogdiag(L), R.sumlogdiag(Ls)
         RH = R.trsm_solve(L, pk, RH)                            # :85-87  A = L^-1 Kuf, C = L^-1 Ls, mt = L^-1 mu
         A, C, mt = RH[:, :, :B], RH[:, :, B:B + M], RH[:, :, B + M:B + M + P]
+        # T = C C^T only meets Phi in tr(Phi T): its chain runs on the side stream (behind S^-1) beside the Phi chain
+        Tl = torch.empty((S, M, M), dtype=dt, device=dev)
+        T = torch.empty((S, M, M), dtype=dt, device=dev)
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                R.copy_ltu(R.gemm(C, C, transB=True, beta=0.0, C=Tl, tri=1), out=T)
+        else:
+            R.copy_ltu(R.gemm(C, C, transB=True, beta=0.0, C=Tl, tri=1), out=T)
         G = _split_k(M, B) if S == 1 else 1
         if G > 1:
             # Phi = A A^T is M x M x B: 36-72 output tiles on 148 SMs with a 4096-deep K loop each -> split K into G slabs
@@ -387,20 +396,18 @@ class _SVGPLogPdf(torch.autograd.Function):
         else:
             Pl = torch.empty((S, M, M), dtype=dt, device=dev)
             Phi = R.copy_ltu(R.gemm(A, A, transB=True, beta=0.0, C=Pl, tri=1))
-        Tl = torch.empty((S, M, M), dtype=dt, device=dev)
-        T = R.copy_ltu(R.gemm(C, C, transB=True, beta=0.0, C=Tl, tri=1))
         G1 = R.gemm(A, mt, transA=True)                         # :89  (S,B,P)
         sumr2 = R.reduce(R.RED_SUMSQDIFF, Y, G1)
         trPhi = R.reduce(R.RED_SUMSQ, A)
         trT = R.reduce(R.RED_SUMSQ, C)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)                    # join: T (and S^-1, for the adjoint) are ready
         trPhiT = R.reduce(R.RED_DOT, Phi, T)
         mm = R.reduce(R.RED_SUMSQ, mt)
         # :94-108 on the reduced scalars in one launch (`KL_u` of the reference is minus the KL):
         #   Q = -sumr2/2 - P B kv/2 - P (tr(Phi T) - tr Phi)/2,  data = beta Q - B P (log 2pi + log nv)/2,
         #   logL = scale data + P (M/2 + sld(Ls) - sld(L)) - P tr(T)/2 - |mt|^2/2
         logL, beta, Q = R.svgp_bound_fwd(P, B, M, scale, sumr2, trPhi, trT, trPhiT, mm, sldL, sldLs, noise, kvar)
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)                    # join: S^-1 is ready for the adjoint
         ctx.kind, ctx.scale, ctx.dims = kind, scale, (S, B, P, M)
         ctx.save_for_backward(X, Y, Z, ls, kvar, W, L, Sinv, RH, Phi, T, G1, beta, Q, pk)
         ctx.info = info
@@ -419,9 +426,20 @@ class _SVGPLogPdf(torch.autograd.Function):
         sc = ctx.scale
         need = ctx.needs_input_grad      # (kind, jitter, scale, X, Y, Z, noise, mu, W, dvec, ls, kvar)
         coef, gsb, neg_gsb, dnoise_s, dkvar_diag, neg_g, minus1 = R.svgp_coef_bwd(P, B, sc, g.contiguous(), beta, Q)
-        U = R.gemm(Phi, T)
+        side = _side_stream(dev)
+        side2 = _side_stream(dev, 1)
+        cur = torch.cuda.current_stream() if side is not None else None
+        U = torch.empty((S, M, M), dtype=dt, device=dev)
+        if side is not None:                                    # U = Phi T beside v = A (Y - A^T mt)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                R.gemm(Phi, T, C=U)
+        else:
+            R.gemm(Phi, T, C=U)
         v = R.gemm(A, Y)
         R.gemm(Phi, mt, alpha=-1.0, beta=1.0, C=v)              # v = A (Y - A^T mt)
+        if side is not None:
+            cur.wait_stream(side)
         # first solve with L^T: [E | E_S | E_R | mt]  (mt rides along: w = L^-T mt)
         E4 = torch.empty((S, M, 3 * M + PP), dtype=dt, device=dev)
         R.svgp_bwd_assemble(Phi, T, U, mt, v, coef, out=E4)
@@ -432,8 +450,6 @@ class _SVGPLogPdf(torch.autograd.Function):
         w = E4[:, :, 3 * M:3 * M + P]
         wg = R.axpby2d(gsb, w)
         dKuf = torch.empty((S, M, B), dtype=dt, device=dev)
-        side = _side_stream(dev)
-        cur = torch.cuda.current_stream() if side is not None else None
 
         def kuf_branch():
             # Kuf adjoint: (L^-T E_R) A + g s beta (L^-T mt) Y^T, then through the kernel
@@ -454,11 +470,18 @@ class _SVGPLogPdf(torch.autograd.Function):
         # S adjoint: g P/2 S^-1 - L^-T E_S L^-1 (S^-1 from the forward pass); W adjoint 2 Sbar W ; diag adjoint diag(Sbar).
         # Formed BEFORE the kernel adjoints: qU_cov_W's gradient is 93 % of the gradient bucket (M^2 of M^2 + M D + ...),
         # and a data-parallel run starts its all-reduce here, under the ~100 us of kernel-adjoint work that follows
-        Sbar = R.axpby2d(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M])
-        dW = R.gemm(Sbar, W, alpha=2.0)
-        if _EARLY_REDUCE[0] is not None and need[8]:
-            _EARLY_REDUCE[0](dW)
-        dd = R.get_diag(Sbar)
+        def s_adjoint():
+            Sb = R.axpby2d(coef[:, 0], Sinv, minus1, F2[:, :, M:2 * M])
+            dW_ = R.gemm(Sb, W, alpha=2.0)
+            if _EARLY_REDUCE[0] is not None and need[8]:
+                _EARLY_REDUCE[0](dW_)
+            return dW_, R.get_diag(Sb)
+        if side2 is not None:                                   # beside the Kuu kernel adjoint (third stream)
+            side2.wait_stream(cur)
+            with torch.cuda.stream(side2):
+                dW, dd = s_adjoint()
+        else:
+            dW, dd = s_adjoint()
         dmu = torch.empty((S, M, P), dtype=dt, device=dev)
         R.copy2d_(dmu, F2[:, :, 2 * M:2 * M + P])
         dZ2, _, dls2, dvar2 = R.kbuild_bwd(ctx.kind, Z, None, ls, kvar, dKuu)
@@ -468,6 +491,7 @@ class _SVGPLogPdf(torch.autograd.Function):
         dY = R.axpby_dev(neg_gsb, Y, gsb, G1) if need[4] else None          # -g s beta (Y - A^T mt)
         if side is not None:
             cur.wait_stream(side)                                            # join the Kuf branch
+            cur.wait_stream(side2)                                           # and the S adjoint
         dZ = R.axpby2d(None, dZ1, None, dZ2)
         dls = R.axpby2d(None, dls1.unsqueeze(0), None, dls2.unsqueeze(0)).squeeze(0)
         dkvar = R.axpby2d(None, dvar1.unsqueeze(0), None, dvar2.unsqueeze(0)).squeeze(0)
@@ -540,11 +564,11 @@ def set_early_reduce(fn):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    """A second stream per device for independent kernel chains (capturable fork/join)."""
+def _side_stream(device, idx=0):
+    """Extra streams per device for independent kernel chains (capturable fork/join)."""
     if device.type != 'cuda':
         return None
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    key = (device.index if device.index is not None else torch.cuda.current_device(), idx)
     s = _SIDE_STREAMS.get(key)
     if s is None:
         s = torch.cuda.Stream(device=device)
