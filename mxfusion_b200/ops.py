@@ -331,12 +331,12 @@ class _SVGPLogPdf(torch.autograd.Function):
         S, B, P, M = X.shape[0], X.shape[1], Y.shape[2], Z.shape[1]
         dt, dev = X.dtype, X.device
         PP = (P + 3) & ~3                                       # keep every row stride a multiple of 4 elements
-        Kuu = R.kbuild_fwd(kind, Z, None, ls, kvar, diag_const=jitter)
         # all right-hand sides of the solves with L ride in ONE buffer [Kuf | Ls | mu]: one GEMM, not three.  S = W W^T +
         # diag is formed and factored IN PLACE inside that buffer (the factorisation takes any row stride), so Ls never
         # has to be copied into it.  Padding columns stay uninitialised: a GEMM column only depends on its own column.
         RH = torch.empty((S, M, B + M + PP), dtype=dt, device=dev)
         Sm = RH[:, :, B:B + M]
+        Kuu = torch.empty((S, M, M), dtype=dt, device=dev)
         pk, pks = R.new_pack(Kuu), R.new_pack(Sm)
         info = torch.empty((2, S), dtype=torch.int32, device=dev)
         Sinv_l = torch.empty((S, M, M), dtype=dt, device=dev)
@@ -355,24 +355,33 @@ class _SVGPLogPdf(torch.autograd.Function):
             join_ls = torch.cuda.Event()
             with torch.cuda.stream(side):
                 s_branch()
+                sldLs = R.sumlogdiag(Sm)
                 if R.pack_inverse(pks, Sm) is not None:
                     join_ls.record()                            # S^-1 only reads the pack: the solves need not wait for it
                     _sinv_chain(Sm, pks, Sinv_l, Sinv)
                 else:
                     _sinv_chain(Sm, pks, Sinv_l, Sinv)          # reads Ls, which an in-place solve below overwrites
                     join_ls.record()
-            R.kbuild_fwd(kind, Z, X, ls, kvar, out=RH[:, :, :B])    # Kuf (:73)
-            R.copy2d_(RH[:, :, B + M:B + M + P], mu)
+            side_k = _side_stream(dev, 1)
+            side_k.wait_stream(cur)
+            with torch.cuda.stream(side_k):                     # Kuf (:73) and mu: third stream, beside the factorisations
+                R.kbuild_fwd(kind, Z, X, ls, kvar, out=RH[:, :, :B])
+                R.copy2d_(RH[:, :, B + M:B + M + P], mu)
+            R.kbuild_fwd(kind, Z, None, ls, kvar, diag_const=jitter, out=Kuu)    # :69-72
             R.potrf_packed_(Kuu, info[0], pk)                   # :83
             cur.wait_event(join_ls)
+            cur.wait_stream(side_k)
         else:
+            R.kbuild_fwd(kind, Z, None, ls, kvar, diag_const=jitter, out=Kuu)
             R.kbuild_fwd(kind, Z, X, ls, kvar, out=RH[:, :, :B])
             R.copy2d_(RH[:, :, B + M:B + M + P], mu)
             R.potrf_packed_(Kuu, info[0], pk)
             s_branch()
             _sinv_chain(Sm, pks, Sinv_l, Sinv)
         L, Ls = Kuu, Sm
-        sldL, sldLs = R.sumlogdiag(L), R.sumlogdiag(Ls)
+        sldL = R.sumlogdiag(L)
+        if side is None:
+            sldLs = R.sumlogdiag(Ls)
         RH = R.trsm_solve(L, pk, RH)                            # :85-87  A = L^-1 Kuf, C = L^-1 Ls, mt = L^-1 mu
         A, C, mt = RH[:, :, :B], RH[:, :, B:B + M], RH[:, :, B + M:B + M + P]
         # T = C C^T only meets Phi in tr(Phi T): its chain runs on the side stream (behind S^-1) beside the Phi chain
@@ -384,6 +393,18 @@ class _SVGPLogPdf(torch.autograd.Function):
                 R.copy_ltu(R.gemm(C, C, transB=True, beta=0.0, C=Tl, tri=1), out=T)
         else:
             R.copy_ltu(R.gemm(C, C, transB=True, beta=0.0, C=Tl, tri=1), out=T)
+        # the data-fit residual (A^T mt and its reduction) is independent of Phi: third stream
+        side2 = _side_stream(dev, 1)
+        if side2 is not None:
+            side2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side2):
+                G1 = R.gemm(A, mt, transA=True)                 # :89  (S,B,P)
+                sumr2 = R.reduce(R.RED_SUMSQDIFF, Y, G1)
+                mm = R.reduce(R.RED_SUMSQ, mt)
+        else:
+            G1 = R.gemm(A, mt, transA=True)
+            sumr2 = R.reduce(R.RED_SUMSQDIFF, Y, G1)
+            mm = R.reduce(R.RED_SUMSQ, mt)
         G = _split_k(M, B) if S == 1 else 1
         if G > 1:
             # Phi = A A^T is M x M x B: 36-72 output tiles on 148 SMs with a 4096-deep K loop each -> split K into G slabs
@@ -396,14 +417,12 @@ class _SVGPLogPdf(torch.autograd.Function):
         else:
             Pl = torch.empty((S, M, M), dtype=dt, device=dev)
             Phi = R.copy_ltu(R.gemm(A, A, transB=True, beta=0.0, C=Pl, tri=1))
-        G1 = R.gemm(A, mt, transA=True)                         # :89  (S,B,P)
-        sumr2 = R.reduce(R.RED_SUMSQDIFF, Y, G1)
         trPhi = R.reduce(R.RED_SUMSQ, A)
         trT = R.reduce(R.RED_SUMSQ, C)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)                    # join: T (and S^-1, for the adjoint) are ready
+            torch.cuda.current_stream().wait_stream(side2)                   # and the residual
         trPhiT = R.reduce(R.RED_DOT, Phi, T)
-        mm = R.reduce(R.RED_SUMSQ, mt)
         # :94-108 on the reduced scalars in one launch (`KL_u` of the reference is minus the KL):
         #   Q = -sumr2/2 - P B kv/2 - P (tr(Phi T) - tr Phi)/2,  data = beta Q - B P (log 2pi + log nv)/2,
         #   logL = scale data + P (M/2 + sld(Ls) - sld(L)) - P tr(T)/2 - |mt|^2/2
