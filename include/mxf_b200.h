@@ -71,6 +71,11 @@ int mxf_kbuild_fwd(int kind, int dtype,
                    int64_t sX, int64_t sX2, int64_t sLs, int64_t sVar, int64_t sDiag, int64_t sOut,
                    void* stream);
 
+/* Tuning knob of mxf_kbuild_fwd: f32 cross-covariances (X2 != NULL, D <= 16, N2 >= 128) with at least `min_elems`
+ * output elements take the tcgen05 + TMA-store kernel (csrc/kbuild_tc.cuh: the gemm2 of stationary.py:102 on the tensor
+ * pipe), smaller ones the streaming FMA kernel.  Returns the previous value; a negative argument only queries. */
+long long mxf_kbuild_tc_threshold(long long min_elems);
+
 /* Adjoint of mxf_kbuild_fwd (replaces MXNet autograd through the same ops).
  *   G (S,N,N2) with row stride ldg -> dX (S,N,D) or NULL, dX2 (S,N2,D) or NULL,
  *   dls (S,ls_len), dvar (S,1); every output is OVERWRITTEN (write, not add).

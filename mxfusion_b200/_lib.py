@@ -6,7 +6,7 @@ current stream.
 """
 import ctypes
 import os
-from ctypes import c_int, c_int64, c_uint64, c_double, c_void_p, c_size_t
+from ctypes import c_int, c_int64, c_longlong, c_uint64, c_double, c_void_p, c_size_t
 
 import torch
 
@@ -29,6 +29,7 @@ def _declare(lib):
         'mxf_version': (c_int, []),
         'mxf_launch_count': (u, []),
         'mxf_kbuild_fwd': (i, [i, i, p, p, p, i, p, p, d, p, l, i, i, i, i, l, l, l, l, l, l, p]),
+        'mxf_kbuild_tc_threshold': (c_longlong, [c_longlong]),
         'mxf_kbuild_bwd_workspace_bytes': (z, [i, i, i, i, i]),
         'mxf_kbuild_bwd': (i, [i, i, p, p, p, i, p, p, l, p, p, p, p, i, i, i, i, l, l, l, l, l, p, z, p]),
         'mxf_gemm': (i, [i, i, i, i, i, i, d, p, l, l, p, l, l, d, p, l, l, i, i, p]),

@@ -44,6 +44,12 @@ def kbuild_fwd(kind, X, X2, ls, var, diag_add=None, diag_const=0.0, out=None):
     return out
 
 
+def kbuild_tc_threshold(min_elems=-1):
+    """Output size (elements) from which f32 cross-covariances with D <= 16 take the tcgen05 + TMA-store kernel; returns
+    the previous value (negative argument: query only)."""
+    return int(lib().mxf_kbuild_tc_threshold(int(min_elems)))
+
+
 def kbuild_bwd(kind, X, X2, ls, var, G, need_dX=True, need_dX2=True):
     """Adjoint of kbuild_fwd.  Returns (dX, dX2, dls, dvar), each with S leading."""
     require_cuda(X, X2, ls, var, G)

@@ -86,8 +86,8 @@ __device__ __forceinline__ T kern_dr2(T r2, T var, T* k_over_var) {
 template <int KIND>
 __device__ __forceinline__ float matern_value_l2(float r2, float l2v) {
     const float r2c = r2 > 1e-14f ? r2 : 1e-14f;
-    const float R = r2c * rsqrt_pos<float>(r2c);
-    float y;
+    float R, y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(R) : "f"(r2c));       // one MUFU.SQRT (r2c >= 1e-14: never denormal)
     if (KIND == MXF_KERN_MATERN52) {
         const float poly = fmaf(2.2360679774997896f, R, fmaf(5.0f / 3.0f, r2, 1.0f));
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(-2.2360679774997896f * 1.4426950408889634f, R, l2v)));
@@ -590,6 +590,10 @@ static int launch_fwd_mma(const float* X, const float* X2, const float* ls, int 
     return after_launch();
 }
 
+}  // namespace mxf
+#include "kbuild_tc.cuh"
+namespace mxf {
+
 template <typename T, int KIND, int DP>
 static int dispatch_fwd_stream_wc(const T* X, const T* X2, const T* ls, int ls_len, const T* var, const T* diag_add,
                                   double diag_const, T* out, int64_t ldo, int S, int N, int N2, int D, int64_t sX,
@@ -619,6 +623,13 @@ static int dispatch_fwd_dc(const T* X, const T* X2, const T* ls, int ls_len, con
     constexpr int RM = sizeof(T) == 4 ? 16 : 8;
     if (N2 >= 32) {
 #define MXF_KS_ARGS X, X2, ls, ls_len, var, diag_add, diag_const, out, ldo, S, N, N2, D, sX, sX2, sLs, sVar, sDiag, sOut, st
+        if constexpr (sizeof(T) == 4) {
+            // large cross-covariances: the dot products on tcgen05, the output through TMA stores (kbuild_tc.cuh)
+            if (X2 != nullptr && D <= 16 && N2 >= 128 && (int64_t)S * N * N2 >= g_kbuild_tc_min_elems.load(std::memory_order_relaxed)) {
+                const int rc = launch_fwd_tc<KIND>(X, X2, ls, ls_len, var, out, ldo, S, N, N2, D, sX, sX2, sLs, sVar, sOut, st);
+                if (rc != MXF_ENOTIMPL) return rc;
+            }
+        }
         if (D <= 4) return dispatch_fwd_stream_wc<T, KIND, 4>(MXF_KS_ARGS);
         if (D <= 8) return dispatch_fwd_stream_wc<T, KIND, 8>(MXF_KS_ARGS);
         if constexpr (sizeof(T) == 4) {
@@ -1089,6 +1100,12 @@ extern "C" int mxf_kbuild_fwd(int kind, int dtype, const void* X, const void* X2
                                                      (const T*)var, (const T*)diag_add, diag_add_const, (T*)out,
                                                      ldo, S, N, N2, D, sX, sX2, sLs, sVar, sDiag, sOut,
                                                      (cudaStream_t)stream));
+}
+
+extern "C" long long mxf_kbuild_tc_threshold(long long min_elems) {
+    const long long old = mxf::g_kbuild_tc_min_elems.load();
+    if (min_elems >= 0) mxf::g_kbuild_tc_min_elems.store(min_elems);
+    return old;
 }
 
 extern "C" size_t mxf_kbuild_bwd_workspace_bytes(int dtype, int S, int N, int N2, int D) {

@@ -37,6 +37,46 @@ def test_kbuild_cross(cuda, prec, kind, shape):
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=rtol, atol=atol * 10 if prec == 'f32' else atol)
 
 
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('shape', [(1, 300, 512, 16, True), (2, 129, 600, 16, False), (1, 1000, 1100, 8, True),
+                                   (1, 128, 128, 5, False), (3, 77, 260, 12, True), (1, 4096, 1024, 16, False),
+                                   (1, 50, 130, 16, True)])
+def test_kbuild_cross_tensor_core_path(cuda, kind, shape):
+    """The tcgen05 + TMA-store K-build (csrc/kbuild_tc.cuh; stationary.py:102's gemm2 on the tensor pipe, 3xTF32) against the
+    f64 oracle at the f32 tolerance of the streaming kernel, and against the streaming FMA kernel itself; ragged row tiles,
+    ragged / multiple 512-column groups, D <= 8 (one K slice) and 8 < D <= 16 (two), sample axis, and a width TMA cannot
+    store without touching the neighbours (N2 = 130, not a multiple of 4: must fall back to the streaming kernel, not fail)."""
+    from mxfusion_b200 import _raw
+    S, N, N2, D, ard = shape
+    tdt, ndt, rtol, atol = DT['f32']
+    rng = np.random.RandomState(11)
+    X = rng.uniform(-2, 2, (S, N, D)).astype(ndt)
+    X2 = rng.uniform(-2, 2, (S, N2, D)).astype(ndt)
+    ls = rng.uniform(0.5, 2.0, (S, D if ard else 1)).astype(ndt)
+    var = rng.uniform(0.5, 2.0, (S, 1)).astype(ndt)
+    want = ok.K(kind, X.astype(np.float64), ls.astype(np.float64), var.astype(np.float64), X2.astype(np.float64))
+    args = (kind, T(X, cuda, tdt), T(X2, cuda, tdt), T(ls, cuda, tdt), T(var, cuda, tdt))
+    old = _raw.kbuild_tc_threshold(1 << 62)
+    try:
+        fma = _raw.kbuild_fwd(*args).cpu().numpy()
+        _raw.kbuild_tc_threshold(0)
+        before = _raw.launch_count()
+        got = _raw.kbuild_fwd(*args)
+        # sentinel-filled strided output: the TMA stores must clip at the edges of the (N, N2) view
+        big = torch.full((S, N + 3, N2 + 4 - N2 % 4 + 8), -7.0, dtype=tdt, device=cuda)
+        view = big[:, :N, :N2]
+        _raw.kbuild_fwd(*args, out=view)
+        assert _raw.launch_count() - before == 2
+    finally:
+        _raw.kbuild_tc_threshold(old)
+    got = got.cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol * 10)
+    np.testing.assert_allclose(got, fma, rtol=2e-5, atol=2e-6)
+    big = big.cpu().numpy()
+    np.testing.assert_array_equal(big[:, :N, :N2], got)
+    assert (big[:, N:, :] == -7.0).all() and (big[:, :, N2:] == -7.0).all()
+
+
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
 @pytest.mark.parametrize('kind', KINDS)
 def test_kbuild_symmetric_with_diag(cuda, prec, kind):
