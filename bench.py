@@ -10,7 +10,8 @@ driven through the public API (Model / SVGPRegression.define_variable / GradBase
 MinibatchInferenceLoop).  `value` has the data set resident in HBM (a 256 MiB L2 flush between iterations inside the
 timed region; `value_no_flush` is the same loop without it); `e2e` streams every minibatch from pinned host memory and
 streams the loss back (non-blocking D2H into pinned memory every step).  Data-parallel runs give every rank a 1/G shard
-of the rows and the same per-rank batch (weak scaling), with one NCCL all-reduce of the flat gradient bucket per step;
+of the rows and the same per-rank batch (weak scaling), with the flat gradient bucket averaged once per step (one peer-memory
+all-reduce kernel captured in the step's graph; NCCL if the GPUs cannot map each other's memory);
 value = G * steps / time, in minibatch iterations per second; `strong_scaling` repeats the run with the GLOBAL batch
 fixed at B (B/G rows per rank).
 
@@ -521,7 +522,8 @@ def main():
                           'jitter 1e-6, Adam lr 1e-2, rv_scaling=N/B)' % (N_ROWS, M_IND, D_IN, KERNEL, BATCH, args.workload),
               'N': N_ROWS, 'M': M_IND, 'D': D_IN,
               'batch_per_gpu': BATCH, 'parallelism': 'dp%d' % world,
-              'sharding': 'rows split across ranks, one NCCL all-reduce of the flat gradient per step'}
+              'sharding': 'rows split across ranks; the flat gradient is averaged once per step by one two-shot all-reduce '
+                          'kernel over NVLink peer memory inside the captured step (NCCL all-reduce if peer mapping fails)'}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -621,6 +623,7 @@ def main():
             'gpu_launches': int(launches_per_step * args.steps),
             'launches_per_step': int(launches_per_step), 'final_loss': loss, 'final_loss_e2e': loss2,
             'peaks': pk_kind}
+    line['config']['gradient_exchange'] = getattr(st, 'exchange', 'single')
     if strong is not None:
         line['strong_scaling'] = strong
     if world == 1:

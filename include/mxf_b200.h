@@ -325,6 +325,18 @@ int mxf_mlp_tanh_bwd(int dtype, int n_layers, const int* widths, const void* x, 
                      const void* const* W, const int64_t* sW, const void* const* b, const int64_t* sb,
                      const void* gout, void* const* dW, void* const* db, int S, int B, void* stream);
 
+/* ---- data-parallel exchange --------------------------------------------------------------
+ * The reference is single-device (its multi-device story would be the MXNet KVStore behind gluon.Trainer.step,
+ * inference/grad_based_inference.py:67, batch_loop.py:58); here the averaged gradient of the ranks is ONE kernel over
+ * NVLink peer memory (csrc/allreduce_p2p.cu) that is captured in the step's CUDA graph.
+ *   bufs[0..world-1]: device pointers (valid in this process) of the ranks' symmetric buffers, laid out as
+ *   [ n elements | padding to 16 bytes | mxf_allreduce_p2p_flag_bytes() bytes of flags, zeroed once ]; flags start at
+ *   flag_byte_off.  In place: every buffer ends up holding scale * sum over ranks.  *err (device int) is set to 1 when
+ *   a peer did not arrive within timeout_s (<= 0: 10 s). */
+size_t mxf_allreduce_p2p_flag_bytes(void);
+int mxf_allreduce_p2p(int dtype, void* const* bufs, int rank, int world, int64_t n, double scale,
+                      size_t flag_byte_off, double timeout_s, int* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

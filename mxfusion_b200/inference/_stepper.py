@@ -53,12 +53,22 @@ class Stepper(object):
         import os
         self.comm = torch.cuda.Stream(device=self.static_in[0].device) if (self.world > 1 and self.static_in and
                                                                              self.static_in[0].is_cuda) else None
-        self.in_graph = bool(self.use_graph) and self.world > 1 and os.environ.get('MXF_DP_INGRAPH', '0') == '1'
-        # OFF by default: with torch 2.11 / NCCL 2.28 a dist.all_reduce issued from inside the captured backward pass hung
+        # Gradient exchange: ONE kernel over NVLink peer memory (inference/_p2p.py, csrc/allreduce_p2p.cu) when every rank
+        # could map its peers' buckets -- a plain launch, captured in the step's graph together with the Adam update, so the
+        # data-parallel step is a single graph replay; NCCL (outside the graph) otherwise.
+        self.p2p = None
+        if self.world > 1 and self.fused and self.comm is not None:
+            from ._p2p import try_peer_bucket
+            self.p2p = try_peer_bucket(params.gflat.numel(), params.gflat.dtype, params.gflat.device)
+        self.exchange = 'single' if self.world == 1 else ('p2p-kernel' if self.p2p is not None else 'nccl')
+        self.in_graph = bool(self.use_graph) and self.world > 1 and (
+            self.p2p is not None or os.environ.get('MXF_DP_INGRAPH', '0') == '1')
+        # NCCL inside the graph is OFF by default: with torch 2.11 / NCCL 2.28 a dist.all_reduce issued from inside the captured backward pass hung
         # both ranks on a 2 x B200 box (capture or first replay), so the default data-parallel step
         # keeps the collective OUTSIDE the graph: replay -> all-reduce of the bucket -> fused Adam.  MXF_DP_EARLY=1 enables
         # the early reduce for eager (use_cuda_graph=False) steps.
-        self.early_reduce_enabled = os.environ.get('MXF_DP_EARLY', '0') == '1' and (self.in_graph or not self.use_graph)
+        self.early_reduce_enabled = os.environ.get('MXF_DP_EARLY', '0') == '1' and self.p2p is None and \
+            (self.in_graph or not self.use_graph)
         self._early, self._early_segment = None, None
         self.n_calls = 0
         self.launches_per_step = None    # library kernels launched by one forward+backward (counted on an eager step)
@@ -107,7 +117,7 @@ class Stepper(object):
                     g = (p.tleaf if k == 1 else p.tensor).grad
                     if g is not None and g.data_ptr() == self._early[0] and g.numel() == self._early[1]:
                         self._early_segment = (off, n)
-            self.params.pack_grads_()
+            self.params.pack_grads_(out=None if self.p2p is None else self.p2p.grad)
             if self.world > 1 and self.in_graph:
                 self._update()
             return loss.detach().reshape(())
@@ -118,12 +128,21 @@ class Stepper(object):
 
     def _update(self):
         p = self.params
+        if self.p2p is not None:
+            g = self.p2p.all_reduce_()
+            ops.R.adam_step_(p.flat, g, p.adam_m, p.adam_v, p.adam_t, lr=self.lr, rescale=self.rescale)
+            return
         if self.world > 1:
             if self.fused:
                 self._reduce_rest()
             else:
                 dist.all_reduce(p.gflat, op=dist.ReduceOp.SUM)
         ops.R.adam_step_(p.flat, p.gflat, p.adam_m, p.adam_v, p.adam_t, lr=self.lr, rescale=self.rescale)
+
+    def check_exchange(self):
+        """Raises InferenceError when the peer-memory all-reduce gave up waiting for a rank (one D2H read)."""
+        if self.p2p is not None:
+            self.p2p.check()
 
     def step(self, batch=None):
         """Runs one step on `batch` (copied into the static inputs) and returns the device loss scalar."""

@@ -25,6 +25,7 @@ class BatchInferenceLoop(GradLoop):
             if dev is not None and ((i + 1) % check_every == 0 or i == max_iter - 1):
                 # non-PD factorisations are recorded on the device; read back every few steps (no per-step sync)
                 ops.check_factorisations(dev, "a Cholesky factorisation at iteration %d" % (i + 1))
+                stepper.check_exchange()
             if verbose:
                 print('\rIteration {} loss: {}\t\t\t\t'.format(i + 1, float(loss)), end='')
                 if ((i + 1) % iter_step == 0 and i > 0) or i == max_iter - 1:

@@ -220,11 +220,12 @@ class InferenceParameters(object):
             if p.tleaf is not None:
                 p.tleaf.grad = None
 
-    def pack_grads_(self):
+    def pack_grads_(self, out=None):
+        """`out`: a bucket other than `gflat` (the data-parallel step packs straight into peer-mapped memory)."""
         from .. import ops
         seg = self._segments
         grads = [(p.tleaf if k == 1 else p.tensor).grad for _, p, _, _, k, _ in seg]
-        ops.R.params_pack_grads(self.flat, self.gflat, grads, [s[2] for s in seg], [s[3] for s in seg],
+        ops.R.params_pack_grads(self.flat, self.gflat if out is None else out, grads, [s[2] for s in seg], [s[3] for s in seg],
                                 [s[4] for s in seg])
 
     def fix_all(self):

@@ -119,6 +119,7 @@ class MinibatchInferenceLoop(GradLoop):
             # a non-positive-definite factorisation is recorded on the device by the bounds; surfaced once per epoch
             # (the reference gets an MXNetError at its per-step asscalar(), minibatch_loop.py:92)
             ops.check_factorisations(dev, "a Cholesky factorisation during epoch %d" % (e + 1))
+            stepper.check_exchange()
             if max_steps is not None and steps_done >= max_steps:
                 break
         self.last_stepper = stepper

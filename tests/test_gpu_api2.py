@@ -165,6 +165,7 @@ infr.params[m.Y.factor._extra_graphs[0].qU_cov_W] = np.eye(M) * 0.1
 infr.run(X=Xs, Y=Ys, max_iter=1, learning_rate=0.05, max_steps=3)
 flat = infr.params.flat.detach().cpu().numpy()
 np.save(os.path.join(%r, 'flat_rank%%d.npy' %% rank), flat)
+open(os.path.join(%r, 'exchange_rank%%d.txt' %% rank), 'w').write(infr._grad_loop.last_stepper.exchange)
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -180,13 +181,16 @@ def test_two_rank_nccl_step_equals_the_concatenated_batch_step(cuda, tmp_path, m
     from mxfusion_b200.inference.minibatch_loop import RolloverBatchSampler
     from oracle import torch_ref
     script = tmp_path / 'worker.py'
-    script.write_text(_NCCL_WORKER % (ROOT, str(tmp_path)))
+    script.write_text(_NCCL_WORKER % (ROOT, str(tmp_path), str(tmp_path)))
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29741')
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr',
                         '127.0.0.1', '--master-port', '29741', str(script)], env=env, capture_output=True, text=True, timeout=150)
     assert r.returncode == 0, r.stderr[-3000:]
     f0, f1 = np.load(tmp_path / 'flat_rank0.npy'), np.load(tmp_path / 'flat_rank1.npy')
     np.testing.assert_array_equal(f0, f1)
+    exch = [(tmp_path / ('exchange_rank%d.txt' % r)).read_text() for r in range(2)]
+    print('gradient exchange used by the ranks:', exch)
+    assert exch[0] == exch[1] and exch[0] in ('p2p-kernel', 'nccl')
     # single process on the concatenated batches
     monkeypatch.setattr(mf.config, 'DEFAULT_DTYPE', 'float64')
     np.random.seed(0)
@@ -220,3 +224,71 @@ def test_two_rank_nccl_step_equals_the_concatenated_batch_step(cuda, tmp_path, m
     # float64; the two formulations sum the batch in a different order (all-reduce of two B-row gradients vs one 2B-row
     # launch with atomics), and Adam's first steps turn a relative gradient difference d into a relative update difference ~d
     np.testing.assert_allclose(f0, want, rtol=1e-8, atol=1e-10)      # measured max |diff| 2.4e-11
+
+
+_P2P_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from mxfusion_b200.inference._p2p import PeerBucket
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+torch.cuda.set_device(rank)
+dev = torch.device('cuda', rank)
+dist.init_process_group('nccl', device_id=dev)
+out = {}
+for dt, name in ((torch.float32, 'f32'), (torch.float64, 'f64')):
+    for n in (1, 7, 4096, 1085447):
+        b = PeerBucket(n, dt, dev)
+        g = torch.Generator(device='cpu').manual_seed(100 * rank + n %% 97)
+        for rep in range(3):                       # repeated calls: the flags reset themselves
+            mine = torch.randn(n, generator=g, dtype=dt).to(dev)
+            b.grad.copy_(mine)
+            got = b.all_reduce_(scale=0.5).clone()
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            want = parts[0].clone()
+            for q in parts[1:]:
+                want += q                           # rank order, like the kernel
+            want *= 0.5
+            assert torch.equal(got, want), (name, n, rep, float((got - want).abs().max()))
+        b.check()
+        out['%%s_%%d' %% (name, n)] = got.cpu().numpy()
+# the launch is capturable: 5 replays of [fill -> all-reduce] inside one CUDA graph each
+b = PeerBucket(4099, torch.float32, dev)
+src = torch.full((4099,), float(rank + 1), device=dev)
+s = torch.cuda.Stream(device=dev)
+s.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s):
+    b.grad.copy_(src); b.all_reduce_()
+torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g, stream=s):
+    b.grad.copy_(src)
+    b.all_reduce_()
+for rep in range(5):
+    src.fill_(float(rank + 1 + rep))
+    g.replay()
+    torch.cuda.synchronize()
+    want = float(sum(r + 1 + rep for r in range(world)))
+    assert bool((b.grad == want).all()), (rep, float(b.grad[0]), want)
+b.check()
+np.savez(os.path.join(%r, 'p2p_rank%%d.npz' %% rank), **out)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_peer_memory_allreduce_kernel(tmp_path):
+    """csrc/allreduce_p2p.cu on two B200s: in-place scale * sum over the ranks, bit-identical to the rank-ordered sum and
+    identical on both ranks, f32 / f64, sizes that are not multiples of 16 bytes or of the rank count, repeated calls
+    (self-resetting flags), and replayed from a CUDA graph."""
+    script = tmp_path / 'p2p_worker.py'
+    script.write_text(_P2P_WORKER % (ROOT, str(tmp_path)))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29743', MXF_P2P_TIMEOUT_S='10')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr',
+                        '127.0.0.1', '--master-port', '29743', str(script)], env=env, capture_output=True, text=True, timeout=150)
+    assert r.returncode == 0, r.stderr[-3000:]
+    a, b = np.load(tmp_path / 'p2p_rank0.npz'), np.load(tmp_path / 'p2p_rank1.npz')
+    for k in a.files:
+        np.testing.assert_array_equal(a[k], b[k])
