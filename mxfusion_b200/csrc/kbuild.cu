@@ -625,8 +625,9 @@ static int dispatch_fwd_dc(const T* X, const T* X2, const T* ls, int ls_len, con
 #define MXF_KS_ARGS X, X2, ls, ls_len, var, diag_add, diag_const, out, ldo, S, N, N2, D, sX, sX2, sLs, sVar, sDiag, sOut, st
         if constexpr (sizeof(T) == 4) {
             // large cross-covariances: the dot products on tcgen05, the output through TMA stores (kbuild_tc.cuh)
-            if (X2 != nullptr && D <= 16 && N2 >= 128 && (int64_t)S * N * N2 >= g_kbuild_tc_min_elems.load(std::memory_order_relaxed)) {
-                const int rc = launch_fwd_tc<KIND>(X, X2, ls, ls_len, var, out, ldo, S, N, N2, D, sX, sX2, sLs, sVar, sOut, st);
+            if (D <= 16 && N2 >= 128 && (int64_t)S * N * N2 >= g_kbuild_tc_min_elems.load(std::memory_order_relaxed)) {
+                const int rc = launch_fwd_tc<KIND>(X, X2, ls, ls_len, var, diag_add, diag_const, out, ldo, S, N, N2, D, sX, sX2,
+                                                   sLs, sVar, sDiag, sOut, st);
                 if (rc != MXF_ENOTIMPL) return rc;
             }
         }

@@ -116,11 +116,12 @@ __device__ __forceinline__ void kt_load_row(const float* __restrict__ base, int6
     }
 }
 
-template <int KIND, int KS>
+template <int KIND, int KS, bool SYM>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 kbuild_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ X, const float* __restrict__ X2,
-                     const float* __restrict__ ls, int ls_len, const float* __restrict__ var, int N, int N2, int D,
-                     int row_tiles, int64_t sX, int64_t sX2, int64_t sLs, int64_t sVar, int vecX, int vecX2, int evict_first) {
+                     const float* __restrict__ ls, int ls_len, const float* __restrict__ var, const float* __restrict__ diag_add,
+                     float diag_const, int N, int N2, int D, int row_tiles, int group_cols, int64_t sX, int64_t sX2, int64_t sLs,
+                     int64_t sVar, int64_t sDiag, int vecX, int vecX2, int evict_first) {
     constexpr bool RBF_FOLD = (KIND == MXF_KERN_RBF);
     extern __shared__ __align__(16) uint8_t kt_smem_raw[];
     const uint32_t base = (smem_u32(kt_smem_raw) + 1023u) & ~1023u;
@@ -138,8 +139,8 @@ kbuild_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const float* __r
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.z;
-    const int colbase = blockIdx.y * KT_GROUP;
-    const int cols_here = min(KT_GROUP, N2 - colbase);
+    const int colbase = blockIdx.y * group_cols;          // group_cols: 512, or 256 when 512-wide groups would leave SMs idle
+    const int cols_here = min(group_cols, N2 - colbase);
     const int nblk = (cols_here + KT_BN - 1) / KT_BN;
     const float* Xs = X + (int64_t)s * sX;
     const float* X2s = X2 + (int64_t)s * sX2;
@@ -165,7 +166,7 @@ kbuild_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const float* __r
     if (threadIdx.x < 16) sc_s[threadIdx.x] = (int)threadIdx.x < D ? csq / lss[ls_len == 1 ? 0 : threadIdx.x] : 0.f;
     __syncthreads();
     // resident B operand: the CTA's 512 scaled column vectors + their norms (with the RBF constant folded in)
-    for (int c = threadIdx.x; c < KT_GROUP; c += KT_THREADS) {
+    for (int c = threadIdx.x; c < nblk * KT_BN; c += KT_THREADS) {
         const int j = colbase + c;
         float x[16];
         kt_load_row(X2s, j, D, j < N2, vecX2 != 0, x);
@@ -242,6 +243,8 @@ kbuild_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const float* __r
         const uint32_t stage0 = base + KT_OFF_STAGE + warp * 2 * KT_STAGE_BYTES;
         uint8_t* stage0_ptr = bp + KT_OFF_STAGE + warp * 2 * KT_STAGE_BYTES;
         const int sw = lane & 7;
+        float dadd = 0.f;
+        if (SYM) dadd = diag_const + (diag_add ? diag_add[(int64_t)s * sDiag] : 0.f);
         int i = 0;
         uint32_t u = 0, sb = 0;
         for (int t = blockIdx.x; t < row_tiles; t += gridDim.x, ++i) {
@@ -288,6 +291,17 @@ kbuild_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const float* __r
                         if (RBF_FOLD) o[e] = ex2_approx(-r2);
                         else o[e] = matern_value_l2<KIND>(r2, l2v);
                     }
+                    if (SYM) {
+                        // K(X, X): on the diagonal r2 is exactly 0 (the expanded form only leaves cancellation noise there,
+                        // which the Matern square root would amplify), and the `+ eye * (noise + jitter)` is folded in
+                        const int dcol = row0 + lane - (colbase + col0);        // this lane's diagonal column within the block
+                        if (dcol >= 0 && dcol < 32) {
+                            const float kd = RBF_FOLD ? ex2_approx(l2v) : matern_value_l2<KIND>(0.f, l2v);
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (e == dcol) o[e] = kd + dadd;
+                        }
+                    }
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         *reinterpret_cast<float4*>(st + ((c ^ sw) << 4)) = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
@@ -314,24 +328,30 @@ kbuild_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const float* __r
 
 // Output elements from which mxf_kbuild_fwd takes this path (smaller outputs: the per-CTA prologue -- 512 column vectors
 // staged, TMEM allocated -- is not amortised and the streaming FMA kernel wins).  mxf_kbuild_tc_threshold() changes it.
-static std::atomic<long long> g_kbuild_tc_min_elems{1ll << 24};
+static std::atomic<long long> g_kbuild_tc_min_elems{1ll << 20};
 
 template <int KIND>
-static int launch_fwd_tc(const float* X, const float* X2, const float* ls, int ls_len, const float* var, float* out, int64_t ldo,
-                         int S, int N, int N2, int D, int64_t sX, int64_t sX2, int64_t sLs, int64_t sVar, int64_t sOut,
-                         cudaStream_t st) {
+static int launch_fwd_tc(const float* X, const float* X2, const float* ls, int ls_len, const float* var, const float* diag_add,
+                         double diag_const, float* out, int64_t ldo, int S, int N, int N2, int D, int64_t sX, int64_t sX2,
+                         int64_t sLs, int64_t sVar, int64_t sDiag, int64_t sOut, cudaStream_t st) {
     if (D > 16 || N2 < 32 || N < 1 || S > 65535) return MXF_ENOTIMPL;
     // TMA: 16-byte aligned base and strides; and the unit clips a box at 16-byte granularity along the row (measured: with
     // N2 % 4 != 0 the elements up to the next multiple of 4 are overwritten), so N2 must be a multiple of 4 as well
     if ((ldo & 3) || (N2 & 3) || (S > 1 && (sOut & 3)) || (reinterpret_cast<uintptr_t>(out) & 15)) return MXF_ENOTIMPL;
     CUtensorMap tm;
     if (!make_map(&tm, out, N, N2, ldo, sOut, S, 32, 32)) return MXF_ENOTIMPL;
-    const int row_tiles = cdiv(N, KT_BM), groups = cdiv(N2, KT_GROUP);
+    const bool sym = (X2 == nullptr);
+    const float* X2e = sym ? X : X2;
+    const int64_t sX2e = sym ? sX : sX2;
+    const int row_tiles = cdiv(N, KT_BM);
+    // 512-column groups amortise the row-tile staging over two accumulators; 256-column groups when that would leave SMs idle
+    const int group_cols = ((int64_t)cdiv(N2, KT_GROUP) * row_tiles * S >= kNumSMs) ? KT_GROUP : KT_BN;
+    const int groups = cdiv(N2, group_cols);
     if (groups > 65535) return MXF_ENOTIMPL;
     int per_group = std::max(1, kNumSMs / (groups * S));
     per_group = std::min(per_group, row_tiles);
     const int vecX = (D == 16) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((sX & 3) == 0);
-    const int vecX2 = (D == 16) && ((reinterpret_cast<uintptr_t>(X2) & 15) == 0) && ((sX2 & 3) == 0);
+    const int vecX2 = (D == 16) && ((reinterpret_cast<uintptr_t>(X2e) & 15) == 0) && ((sX2e & 3) == 0);
     const int evict_first = ((int64_t)S * N * N2 * 4 > (64ll << 20)) ? 1 : 0;     // larger than what L2 can keep for a consumer
     dim3 grid(per_group, groups, S);
     auto launch = [&](auto kern, bool& attr_set) -> int {
@@ -340,13 +360,13 @@ static int launch_fwd_tc(const float* X, const float* X2, const float* ls, int l
                 return (int)cudaGetLastError();
             attr_set = true;
         }
-        kern<<<grid, KT_THREADS, KT_SMEM, st>>>(tm, X, X2, ls, ls_len, var, N, N2, D, row_tiles, sX, sX2, sLs, sVar, vecX, vecX2,
-                                                evict_first);
+        kern<<<grid, KT_THREADS, KT_SMEM, st>>>(tm, X, X2e, ls, ls_len, var, diag_add, (float)diag_const, N, N2, D, row_tiles,
+                                                group_cols, sX, sX2e, sLs, sVar, sDiag, vecX, vecX2, evict_first);
         return after_launch();
     };
-    static bool set1 = false, set2 = false;       // per KIND instantiation, one flag per kernel
-    if (D <= 8) return launch(kbuild_fwd_tc_kernel<KIND, 1>, set1);
-    return launch(kbuild_fwd_tc_kernel<KIND, 2>, set2);
+    static bool set[4] = {false, false, false, false};       // per KIND instantiation, one flag per kernel
+    if (D <= 8) return sym ? launch(kbuild_fwd_tc_kernel<KIND, 1, true>, set[0]) : launch(kbuild_fwd_tc_kernel<KIND, 1, false>, set[1]);
+    return sym ? launch(kbuild_fwd_tc_kernel<KIND, 2, true>, set[2]) : launch(kbuild_fwd_tc_kernel<KIND, 2, false>, set[3]);
 }
 
 }  // namespace mxf

@@ -77,6 +77,35 @@ def test_kbuild_cross_tensor_core_path(cuda, kind, shape):
     assert (big[:, N:, :] == -7.0).all() and (big[:, :, N2:] == -7.0).all()
 
 
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('shape', [(2, 300, 16), (1, 1024, 8), (1, 132, 5), (1, 640, 12)])
+def test_kbuild_symmetric_tensor_core_path(cuda, kind, shape):
+    """K(X, X) + eye * (noise + jitter) on the tcgen05 kernel: exact kernel value on the diagonal, the diagonal term folded
+    into the store, 256- and 512-column groups; against the f64 oracle and the streaming kernel."""
+    from mxfusion_b200 import _raw
+    S, N, D = shape
+    tdt, ndt, rtol, atol = DT['f32']
+    rng = np.random.RandomState(12)
+    X = rng.uniform(-2, 2, (S, N, D)).astype(ndt)
+    ls = rng.uniform(0.5, 2.0, (S, D)).astype(ndt)
+    var = rng.uniform(0.5, 2.0, (S, 1)).astype(ndt)
+    noise = rng.uniform(0.1, 0.2, (S, 1)).astype(ndt)
+    want = ok.K(kind, X.astype(np.float64), ls.astype(np.float64), var.astype(np.float64)) + \
+        np.eye(N)[None] * (noise.astype(np.float64)[..., None] + 1e-3)
+    args = (kind, T(X, cuda, tdt), None, T(ls, cuda, tdt), T(var, cuda, tdt))
+    old = _raw.kbuild_tc_threshold(1 << 62)
+    try:
+        fma = _raw.kbuild_fwd(*args, diag_add=T(noise, cuda, tdt), diag_const=1e-3).cpu().numpy()
+        _raw.kbuild_tc_threshold(0)
+        got = _raw.kbuild_fwd(*args, diag_add=T(noise, cuda, tdt), diag_const=1e-3).cpu().numpy()
+    finally:
+        _raw.kbuild_tc_threshold(old)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol * 10)
+    np.testing.assert_allclose(got, fma, rtol=2e-5, atol=2e-6)
+    d = np.arange(N)
+    np.testing.assert_array_equal(got[:, d, d], fma[:, d, d])
+
+
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
 @pytest.mark.parametrize('kind', KINDS)
 def test_kbuild_symmetric_with_diag(cuda, prec, kind):
