@@ -42,8 +42,8 @@ WORKLOADS = {'headline': (1000000, 1024, 8, 4096, 'rbf'), 'c2': (100000, 512, 8,
 OTHER_WORKLOADS = ('c1', 'c4', 'c5')      # exact GP N=512 D=2 / mean-field BNN / 2-layer deep GP: see run_other()
 PARITY_STEPS = 25
 JITTER, LR = 1e-6, 1e-2
-KBUILD_NCU_TRAFFIC_BYTES = 4069040680      # committed capture profiles/r2_kbuild_raw.csv (ncu --set full, this round):
-                                           # 32.14 MB read + 4036.9 MB written per launch
+KBUILD_NCU_TRAFFIC_BYTES = 4068219664      # committed capture profiles/r2b_kbuild_tc_rbf8_raw.csv (ncu --set full, this round,
+                                           # kbuild_fwd_tc_kernel<rbf, 1 K-slice>): 32.08 MB read + 4036.1 MB written per launch
 METRIC = "svgp_elbo_iters_per_sec"
 UNIT = "minibatch iterations (B=4096 rows: ELBO fwd + grad + Adam) per second, summed over GPUs"
 
@@ -196,16 +196,17 @@ def kernel_rooflines(device, pk):
     ach = nbytes / ms / 1e6
     del out
     same = (KERNEL, N_ROWS, M_IND, D_IN) == ('rbf', 1000000, 1024, 8)
-    return {'bound': 'hbm', 'kernel': 'kbuild_fwd_stream_kernel<float,%s> K(X,Z) N=%d M=%d D=%d' % (KERNEL, N_ROWS, M_IND, D_IN),
+    return {'bound': 'hbm', 'kernel': 'kbuild_fwd_tc_kernel<%s> (tcgen05 cross term + TMA stores) K(X,Z) N=%d M=%d D=%d' % (
+                KERNEL, N_ROWS, M_IND, D_IN),
             'achieved': ach,
             'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
             'traffic': KBUILD_NCU_TRAFFIC_BYTES if same else None,
             'traffic_source': ('committed capture (not measured in this run): dram__bytes_read.sum + dram__bytes_write.sum '
-                               'per launch, ncu --set full, profiles/r2_kbuild_raw.csv (0.032 GB read + 4.037 GB written)')
+                               'per launch, ncu --set full, profiles/r2b_kbuild_tc_rbf8_raw.csv (0.032 GB read + 4.036 GB written)')
             if same else None,
             'ms_per_launch': ms, 'algorithmic_bytes': nbytes,
-            'note': 'stand-alone launch at the BASELINE "K(X,Z) HBM GB/s" size; inside the timed step Kuf is 1024 x 4096 and '
-                    'L2-resident'}
+            'note': 'stand-alone launch at the BASELINE "K(X,Z) HBM GB/s" size; inside the timed step the same kernel builds '
+                    'Kuu (1024 x 1024) and Kuf (1024 x 4096), L2-resident'}
 
 
 def measure_tf32_peak(device, n=8192):
@@ -480,6 +481,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='headline', choices=sorted(WORKLOADS) + list(OTHER_WORKLOADS))
     ap.add_argument('--out', default=None, help='also write the JSON line to this file')
+    ap.add_argument('--step-only', action='store_true',
+                    help='profiling aid (ncu launch lists): only the data-resident timed loop, none of the other arms')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -577,6 +580,14 @@ def main():
     clocks = sampler.finish() if sampler else None
     secs = max_over_ranks(secs)
     st = loop.last_stepper
+
+    if args.step_only:
+        if rank == 0:
+            emit({'metric': METRIC, 'value': world * args.steps / secs, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                  'warmup': warmup, 'ms_per_step': 1e3 * secs / args.steps, 'note': '--step-only: profiling aid, not a bench line'})
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- the same without the L2 flush (steady-state training: the 21 MB working set stays in L2) --------
     infr1, loop1 = build_inference(Xs, Ys, Z, N_ROWS, world, data_resident=True, device=device)

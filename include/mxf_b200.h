@@ -292,6 +292,11 @@ int mxf_adam_step(int dtype, void* w, const void* g, void* m, void* v, int64_t n
                   double lr, double beta1, double beta2, double eps, double rescale,
                   int* step_count, void* stream);
 
+/* mx.gluon.Trainer('sgd') (grad_based_inference.py:67 accepts any optimiser name): w -= lr * rescale * g, or with
+ * momentum != 0 (mom: state bucket) mom = momentum * mom - lr * rescale * g; w += mom.  Bumps step_count like Adam. */
+int mxf_sgd_step(int dtype, void* w, const void* g, void* mom, int64_t n, double lr, double momentum, double rescale,
+                 int* step_count, void* stream);
+
 /* ---- flat parameter bucket: multi-tensor transform and gradient gather (inference_alg.py:79-80 applies
  *      `var_trans[k].transform` per constrained parameter on every forward; gluon Trainer / autograd accumulate one
  *      gradient per parameter) ----

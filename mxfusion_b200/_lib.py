@@ -72,6 +72,7 @@ def _declare(lib):
         'mxf_normal_reparam_multi_bwd': (i, [i, i, p, p, p, p, p, p, p, p, p, p]),
         'mxf_normal_reparam_bwd': (i, [i, p, p, p, l, l, i, l, p, p, p]),
         'mxf_adam_step': (i, [i, p, p, p, p, l, d, d, d, d, d, p, p]),
+        'mxf_sgd_step': (i, [i, p, p, p, l, d, d, d, p, p]),
         'mxf_gather_rows': (i, [i, p, l, p, p, l, p, p]),
         'mxf_params_transform': (i, [i, i, p, p, p, p, p, p, p]),
         'mxf_params_pack_grads': (i, [i, i, p, p, p, p, p, p, p]),

@@ -392,6 +392,13 @@ def adam_step_(w, g, m, v, step_count, lr, beta1=0.9, beta2=0.999, eps=1e-8, res
           'mxf_adam_step')
 
 
+def sgd_step_(w, g, mom, step_count, lr, momentum=0.0, rescale=1.0):
+    """mx.optimizer.SGD on the flat bucket (mom: state bucket, only read when momentum != 0)."""
+    require_cuda(w, g, mom, step_count)
+    check(lib().mxf_sgd_step(dtype_code(w), ptr(w), ptr(g), ptr(mom), w.numel(), float(lr), float(momentum), float(rescale),
+                             ptr(step_count), stream_ptr()), 'mxf_sgd_step')
+
+
 def gather_rows(src, idx, off, rows, out=None):
     require_cuda(src, idx, off)
     src = _c(src)

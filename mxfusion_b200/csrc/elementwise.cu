@@ -365,6 +365,24 @@ adam_kernel(T* __restrict__ w, const T* __restrict__ g, T* __restrict__ m, T* __
     }
 }
 
+// mx.optimizer.SGD (the Trainer('sgd') of grad_based_inference.py:67): w -= lr * rescale * g, or with momentum
+// mom = momentum * mom - lr * rescale * g; w += mom  (weight decay 0, as the reference never sets it)
+template <typename T>
+__global__ void __launch_bounds__(256)
+sgd_kernel(T* __restrict__ w, const T* __restrict__ g, T* __restrict__ mom, int64_t n, double lr, double momentum, double rescale) {
+    const T L = (T)(lr * rescale), MU = (T)momentum;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (mom) {
+            const T mi = MU * mom[i] - L * g[i];
+            mom[i] = mi;
+            w[i] += mi;
+        } else {
+            w[i] -= L * g[i];
+        }
+    }
+}
+
 __global__ void incr_kernel(int* c) { c[0] += 1; }
 
 template <typename T>
@@ -778,6 +796,16 @@ extern "C" int mxf_adam_step(int dtype, void* w, const void* g, void* m, void* v
         MXF_DISPATCH_DTYPE(dtype, adam_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
                                       (T*)w, (const T*)g, (T*)m, (T*)v, n, lr, beta1, beta2, eps, rescale,
                                       step_count));
+    incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_count);
+    return after_launch(2);
+}
+
+extern "C" int mxf_sgd_step(int dtype, void* w, const void* g, void* mom, int64_t n, double lr, double momentum,
+                            double rescale, int* step_count, void* stream) {
+    if (!w || !g || !step_count || n < 0 || (momentum != 0.0 && !mom)) return MXF_EINVAL;
+    if (n > 0)
+        MXF_DISPATCH_DTYPE(dtype, sgd_kernel<T><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
+                                      (T*)w, (const T*)g, momentum != 0.0 ? (T*)mom : (T*)nullptr, n, lr, momentum, rescale));
     incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_count);
     return after_launch(2);
 }

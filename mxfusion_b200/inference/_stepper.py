@@ -15,9 +15,10 @@ from ..common.exceptions import InferenceError
 class Stepper(object):
     def __init__(self, infr_executor, params, optimizer, learning_rate, rescale_grad, example_batch,
                  use_cuda_graph=True, warmup_steps=2):
-        if optimizer != 'adam':
-            raise InferenceError("only optimizer='adam' (the reference's default, grad_based_inference.py:67) is "
+        if optimizer not in ('adam', 'sgd'):
+            raise InferenceError("optimizer='adam' (the reference's default, grad_based_inference.py:67) and 'sgd' are "
                                  "implemented on the fused update path; got %r" % (optimizer,))
+        self.optimizer = optimizer
         self.executor, self.params = infr_executor, params
         self.lr = float(learning_rate)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -129,15 +130,22 @@ class Stepper(object):
     def _update(self):
         p = self.params
         if self.p2p is not None:
-            g = self.p2p.all_reduce_()
-            ops.R.adam_step_(p.flat, g, p.adam_m, p.adam_v, p.adam_t, lr=self.lr, rescale=self.rescale)
+            self._apply(self.p2p.all_reduce_())
             return
         if self.world > 1:
             if self.fused:
                 self._reduce_rest()
             else:
                 dist.all_reduce(p.gflat, op=dist.ReduceOp.SUM)
-        ops.R.adam_step_(p.flat, p.gflat, p.adam_m, p.adam_v, p.adam_t, lr=self.lr, rescale=self.rescale)
+        self._apply(p.gflat)
+
+    def _apply(self, g):
+        """One fused update of the flat parameter bucket (mx.gluon.Trainer(optimizer).step, minibatch_loop.py:91)."""
+        p = self.params
+        if self.optimizer == 'sgd':
+            ops.R.sgd_step_(p.flat, g, None, p.adam_t, lr=self.lr, momentum=0.0, rescale=self.rescale)
+        else:
+            ops.R.adam_step_(p.flat, g, p.adam_m, p.adam_v, p.adam_t, lr=self.lr, rescale=self.rescale)
 
     def check_exchange(self):
         """Raises InferenceError when the peer-memory all-reduce gave up waiting for a rank (one D2H read)."""

@@ -22,15 +22,32 @@ def variables_to_UUID(variables):
 class ObjectiveBlock(object):
     def __init__(self, infr_method, constants, data_def, var_trans, var_ties, excluded, params=None):
         self._infr_method = infr_method
-        # constants given as arrays live next to the parameters (same device / dtype); shape constants stay ints
-        dev, dt = params.mxnet_context, params.flat.dtype if params.flat is not None else None
-        self._constants = {k: (v.to(device=dev, dtype=dt if v.is_floating_point() and dt is not None else v.dtype)
-                               if isinstance(v, torch.Tensor) else v) for k, v in constants.items()}
+        # The LIVE dictionary of the parameters (inference_alg.py:41 of the reference keeps it too): the minibatch loop
+        # updates the shape constants (m.N = batch size) after the executor exists.  Constants given as arrays are moved
+        # next to the parameters (same device / dtype) on first use and cached; shape constants stay ints.
+        self._constants_live = constants
+        self._constants_cache = {}
         self._data_def = data_def
         self._var_trans = var_trans
         self._var_ties = var_ties
         self._infr_params = params
         self._excluded = excluded
+
+    @property
+    def _constants(self):
+        params = self._infr_params
+        dev, dt = params.mxnet_context, params.flat.dtype if params.flat is not None else None
+        out = {}
+        for k, v in self._constants_live.items():
+            if isinstance(v, torch.Tensor):
+                hit = self._constants_cache.get(k)
+                if hit is None or hit[0] is not v:
+                    hit = (v, v.to(device=dev, dtype=dt if v.is_floating_point() and dt is not None else v.dtype))
+                    self._constants_cache[k] = hit
+                out[k] = hit[1]
+            else:
+                out[k] = v
+        return out
 
     def __call__(self, x, *args):
         """`x` is the reference's dummy first argument (``mx.nd.zeros(1)``); ignored."""

@@ -188,6 +188,15 @@ def adam_step_(w, g, m, v, step_count, lr, beta1=0.9, beta2=0.999, eps=1e-8, res
     step_count += 1
 
 
+def sgd_step_(w, g, mom, step_count, lr, momentum=0.0, rescale=1.0):
+    if momentum != 0.0:
+        mom.mul_(momentum).sub_(g, alpha=lr * rescale)
+        w.add_(mom)
+    else:
+        w.sub_(g, alpha=lr * rescale)
+    step_count += 1
+
+
 def gather_rows(src, idx, off, rows, out=None):
     o = int(off.item()) if off is not None else 0
     r = src[idx[o:o + rows]]

@@ -344,6 +344,28 @@ def test_adam_matches_mxnet_update_rule(cuda, prec):
     np.testing.assert_allclose(wt.cpu().numpy(), w, rtol=rtol, atol=atol)
 
 
+@pytest.mark.parametrize('prec', ['f64', 'f32'])
+@pytest.mark.parametrize('momentum', [0.0, 0.9])
+def test_sgd_matches_mxnet_update_rule(cuda, prec, momentum):
+    """mx.optimizer.SGD.update (python/mxnet/optimizer/optimizer.py, the Trainer('sgd') of grad_based_inference.py:67):
+    mom = momentum * mom - lr * rescale * g; w += mom   (plain w -= lr * rescale * g without momentum)."""
+    from mxfusion_b200 import _raw
+    tdt, ndt, rtol, atol = DT[prec]
+    rng = np.random.RandomState(15)
+    n = 1000
+    w = rng.randn(n)
+    mom = np.zeros(n)
+    wt, mt = T(w, cuda, tdt), T(mom, cuda, tdt)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=cuda)
+    for t in range(1, 6):
+        g = rng.randn(n)
+        mom = momentum * mom - 0.01 * (g / 16)
+        w = w + mom
+        _raw.sgd_step_(wt, T(g, cuda, tdt), mt if momentum else None, cnt, lr=0.01, momentum=momentum, rescale=1. / 16)
+    assert int(cnt.item()) == 5
+    np.testing.assert_allclose(wt.cpu().numpy(), w, rtol=rtol, atol=atol)
+
+
 def test_gather_rows_bit_exact(cuda):
     from mxfusion_b200 import _raw
     rng = np.random.RandomState(14)

@@ -337,3 +337,46 @@ def test_gp_modules_draw_samples_by_default(mf):
         with torch.no_grad():
             y = infr.run(X=X)[0]
         assert tuple(y.shape) == (ns, N, 1) and bool(torch.isfinite(y).all())
+
+
+def test_executor_sees_shape_constants_updated_after_its_creation(mf):
+    """The minibatch loop calls update_shape_constants(batch) AFTER the executor exists (grad_based_inference.py:80-86 of
+    the reference): the executor must read the live constants (m.N = batch size), not a snapshot taken at creation."""
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    m, X, Y = gp_notebook_model(mf)
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]))
+    infr.initialize(X=X.shape, Y=Y.shape)
+    ex = infr.inference_algorithm.create_executor(data_def=infr.observed_variable_UUIDs, params=infr.params,
+                                                  var_ties=infr.params.var_ties)
+    assert ex._constants[m.N.uuid] == 20
+    infr.params.update_constants({m.N: 7})
+    assert ex._constants[m.N.uuid] == 7
+    t = torch.arange(3.)
+    infr.params.update_constants({'some_array': t})
+    assert ex._constants['some_array'].dtype == torch.float64 and ex._constants['some_array'] is ex._constants['some_array']
+
+
+def test_sgd_optimizer_takes_plain_gradient_steps(mf):
+    """run(optimizer='sgd') (grad_based_inference.py:67 hands any optimiser name to gluon.Trainer): one step is
+    w -= lr * grad on the unconstrained parameters; other names raise InferenceError."""
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    from mxfusion_b200.common.exceptions import InferenceError
+    m, X, Y = gp_notebook_model(mf)
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]))
+    infr.initialize(X=X.shape, Y=Y.shape)
+    def hyper(i, mm):           # unconstrained values of the three trained hyper-parameters
+        return np.concatenate([i.params._params[v.uuid].tensor.detach().numpy().ravel()
+                               for v in (mm.noise_var, mm.kernel.lengthscale, mm.kernel.variance)])
+    w0 = hyper(infr, m)
+    infr.run(X=X, Y=Y, optimizer='sgd', learning_rate=1e-4, max_iter=1)
+    step = (w0 - hyper(infr, m)) / 1e-4                       # = the gradient of the first step
+    assert np.abs(step).min() > 0
+    m2, _, _ = gp_notebook_model(mf)
+    infr2 = GradBasedInference(inference_algorithm=MAP(model=m2, observed=[m2.X, m2.Y]))
+    infr2.initialize(X=X.shape, Y=Y.shape)
+    np.testing.assert_array_equal(hyper(infr2, m2), w0)
+    infr2.run(X=X, Y=Y, optimizer='sgd', learning_rate=2e-4, max_iter=1)
+    step2 = (w0 - hyper(infr2, m2)) / 2e-4
+    np.testing.assert_allclose(step, step2, rtol=1e-6)        # same gradient, twice the step
+    with pytest.raises(InferenceError, match='sgd'):
+        infr2.run(X=X, Y=Y, optimizer='rmsprop', learning_rate=1e-3, max_iter=1)
