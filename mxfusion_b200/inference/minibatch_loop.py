@@ -57,13 +57,21 @@ class MinibatchInferenceLoop(GradLoop):
         cols = [int(np.prod(d.shape[1:])) for d in data]
         if self.data_resident:
             src = [d.to(dev).reshape(n, c).contiguous() for d, c in zip(data, cols)]
-            idx_dev = torch.empty((n + B,), dtype=torch.int64, device=dev)
+            # two index buffers (+ pinned staging): the next epoch's permutation is shuffled on the host and uploaded while
+            # the device still works through the steps queued for the current epoch
+            idx_devs = [torch.empty((n + B,), dtype=torch.int64, device=dev) for _ in range(2)]
+            idx_pin = [torch.empty((n + B,), dtype=torch.int64) for _ in range(2)]
+            if dev.type == 'cuda':
+                idx_pin = [t.pin_memory() for t in idx_pin]
             off = torch.zeros((1,), dtype=torch.int64, device=dev)
         else:
             src = [d.detach().cpu().reshape(n, c).contiguous() for d, c in zip(data, cols)]
             # ring of pinned staging buffers: a slot is refilled by the host only after the H2D copy that read it
-            # has completed (event), so the host can run ahead of the device by RING-1 steps
-            RING = 4
+            # has completed (event), so the host can run ahead of the device by RING-1 steps -- far enough (up to 64 steps,
+            # at most 64 MB of pinned memory) that the host-side shuffle of the next epoch's permutation (tens of ms at
+            # N = 1e6) is covered by steps already queued
+            step_bytes = sum(B * c * d.element_size() for d, c in zip(src, cols))
+            RING = int(max(4, min(64, (64 << 20) // max(step_bytes, 1))))
             pinned = [[torch.empty((B, c), dtype=d.dtype).pin_memory() if dev.type == 'cuda'
                        else torch.empty((B, c), dtype=d.dtype) for d, c in zip(src, cols)] for _ in range(RING)]
             copied = [torch.cuda.Event() if dev.type == 'cuda' else None for _ in range(RING)]
@@ -80,12 +88,23 @@ class MinibatchInferenceLoop(GradLoop):
             loss_host = loss_host.pin_memory()
         self.d2h_bytes_per_step = loss_host.element_size()
         epoch_losses, steps_done = [], 0
-        for e in range(max_iter):
-            idx, nfull = sampler.epoch_indices()
+
+        def stage(e, idx):
+            """Epoch e's indices -> the device (resident data) or a host tensor; stream-ordered, no host wait."""
             if self.data_resident:
-                idx_dev[:idx.shape[0]].copy_(torch.from_numpy(idx), non_blocking=True)
+                k = idx.shape[0]
+                idx_pin[e & 1][:k].copy_(torch.from_numpy(idx))
+                idx_devs[e & 1][:k].copy_(idx_pin[e & 1][:k], non_blocking=True)
+                return idx_devs[e & 1]
+            return torch.from_numpy(idx)
+
+        idx, nfull = sampler.epoch_indices()
+        staged = stage(0, idx)
+        for e in range(max_iter):
+            if self.data_resident:
+                idx_dev = staged
             else:
-                idx_t = torch.from_numpy(idx)
+                idx_t = staged
             loss_acc.zero_()
             for i in range(nfull):
                 if self.data_resident:
@@ -113,9 +132,16 @@ class MinibatchInferenceLoop(GradLoop):
                     print('\repoch {} Iteration {} loss: {}\t\t\t'.format(e + 1, i + 1, float(loss)), end='')
                 if max_steps is not None and steps_done >= max_steps:
                     break
+            nfull_done = nfull
+            last = (e + 1 >= max_iter) or (max_steps is not None and steps_done >= max_steps)
+            if not last:
+                # the reference shuffles at the start of the next epoch (DataLoader, minibatch_loop.py:68-70); same draws in
+                # the same order here, only earlier on the host's clock: the device is still busy with this epoch's steps
+                idx, nfull = sampler.epoch_indices()
+                staged = stage(e + 1, idx)
             if verbose:
-                print('epoch-loss: {} '.format(float(loss_acc) / max(nfull, 1)))
-            epoch_losses.append(loss_acc / max(nfull, 1))
+                print('epoch-loss: {} '.format(float(loss_acc) / max(nfull_done, 1)))
+            epoch_losses.append(loss_acc / max(nfull_done, 1))
             # a non-positive-definite factorisation is recorded on the device by the bounds; surfaced once per epoch
             # (the reference gets an MXNetError at its per-step asscalar(), minibatch_loop.py:92)
             ops.check_factorisations(dev, "a Cholesky factorisation during epoch %d" % (e + 1))
