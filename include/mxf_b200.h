@@ -330,6 +330,11 @@ int mxf_mlp_tanh_bwd(int dtype, int n_layers, const int* widths, const void* x, 
                      const void* const* W, const int64_t* sW, const void* const* b, const int64_t* sb,
                      const void* gout, void* const* dW, void* const* db, int S, int B, void* stream);
 
+/* Tuning knob of the single-launch dataflow potrf (f32, n <= 1024): CTAs per matrix of the persistent kernel (default 148 =
+ * one per SM, so that two factorisations issued on two streams are both fully resident).  Returns the previous value;
+ * ctas <= 0 only queries. */
+int mxf_potrf_dag_ctas(int ctas);
+
 /* ---- data-parallel exchange --------------------------------------------------------------
  * The reference is single-device (its multi-device story would be the MXNet KVStore behind gluon.Trainer.step,
  * inference/grad_based_inference.py:67, batch_loop.py:58); here the averaged gradient of the ranks is ONE kernel over

@@ -526,6 +526,11 @@ potrf_dag_kernel(const DagParams p) {
     const int64_t lda = p.lda, ldw = p.ldw, ldlt = p.ldlt;
     const bool factor = p.mode != 0;
 
+    // Persistent: a CTA takes ticket after ticket.  A ticket only waits on tickets with smaller numbers, each of which is
+    // finished or held by a CTA that is running -- so the schedule is deadlock-free for ANY grid size; the grid is sized to
+    // the machine (dag_launch), not to the ticket count, so that two concurrent factorisations are both fully resident.
+    for (;;) {
+    __syncthreads();                                    // the previous ticket's shared memory (and sh_ticket) is free
     if (threadIdx.x == 0) sh_ticket = atomicAdd(sync.ticket, 1);
     __syncthreads();
     int t = sh_ticket;
@@ -655,7 +660,7 @@ potrf_dag_kernel(const DagParams p) {
             }
         }
         if (g_dag_prof && threadIdx.x == 0 && blockIdx.y == 0) g_dag_prof[c * 16 + 15] = (long long)globaltimer_ns();
-        return;
+        continue;
     }
 
     if (t - 1 < nA) {
@@ -687,7 +692,7 @@ potrf_dag_kernel(const DagParams p) {
             store_acc_t(LT + (int64_t)j0 * ldlt + i0, ldlt, l, re, B, m);
             zero_tile(LT + (int64_t)i0 * ldlt + j0, ldlt, re, B, false, m);
         }
-        return;
+        continue;
     }
 
     {
@@ -733,11 +738,14 @@ potrf_dag_kernel(const DagParams p) {
             zero_tile(dvT + (int64_t)B * 128, 128, B, B, true, m);
         }
     }
+    }   // ticket loop
 }
 
 }  // namespace
 
 int dag_set_prof(long long* dev_ptr) { return (int)cudaMemcpyToSymbol(g_dag_prof, &dev_ptr, sizeof(dev_ptr)); }
+
+std::atomic<int> g_dag_ctas{kNumSMs};
 
 int dag_tickets(int T, int mode) {
     int tot = 0;
@@ -773,7 +781,10 @@ int dag_launch(int mode, float* A, int64_t lda, int64_t sA, int n, float* pack, 
     if (S == 1) e = cudaMemsetAsync(pack + oSync, 0, (size_t)DG_SYNC_INTS * sizeof(int), st);
     else e = cudaMemset2DAsync(pack + oSync, (size_t)sP * sizeof(float), 0, (size_t)DG_SYNC_INTS * sizeof(int), (size_t)S, st);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid(dag_tickets(p.T, mode), S);
+    // CTAs per matrix: one per SM (two factorisations that run concurrently -- Kuu and S in the SVGP step -- then fill the two
+    // CTA slots of every SM between them instead of the second one waiting for slots); mxf_potrf_dag_ctas() overrides
+    const int ctas = std::max(1, std::min(dag_tickets(p.T, mode), g_dag_ctas.load(std::memory_order_relaxed)));
+    dim3 grid(ctas, S);
     potrf_dag_kernel<<<grid, DG_THREADS, DG_SMEM, st>>>(p);
     return after_launch();
 }

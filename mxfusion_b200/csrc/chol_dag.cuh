@@ -1,5 +1,6 @@
 // Interface of the single-launch tile-dataflow Cholesky + inverse (chol_dag.cu), used by chol_packed.cu.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -20,6 +21,7 @@ int dag_launch(int mode, float* A, int64_t lda, int64_t sA, int n, float* pack, 
                int64_t oLT, int64_t oDinv, int64_t oDinvT, int64_t oSync, int ldw, int ldlt, int* info, int info_base, int S,
                cudaStream_t st);
 int dag_tickets(int T, int mode);
+extern std::atomic<int> g_dag_ctas;        // CTAs per matrix of the persistent dataflow kernel (default: one per SM)
 int dag_set_prof(long long* dev_ptr);      // debug: 16 stamps per diagonal ticket (clock64; [14], [15] globaltimer ns)
 
 }  // namespace mxf

@@ -874,6 +874,12 @@ extern "C" int mxf_debug_set_prof(void* dev_ptr) {
 
 extern "C" int mxf_debug_set_dag_prof(void* dev_ptr) { return dag_set_prof((long long*)dev_ptr); }
 
+extern "C" int mxf_potrf_dag_ctas(int ctas) {
+    const int old = mxf::g_dag_ctas.load();
+    if (ctas > 0) mxf::g_dag_ctas.store(ctas);
+    return old;
+}
+
 extern "C" int mxf_tri_block(int dtype) { return dtype == MXF_F64 ? TriBlock<double>::NB : TriBlock<float>::NB; }
 
 extern "C" size_t mxf_tri_pack_elems(int dtype, int n) {

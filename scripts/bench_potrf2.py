@@ -27,7 +27,9 @@ def one():
     _raw.potrf_packed_(B0, i0, p0)
 
 
-for name, fn in (('one', one), ('two concurrent', both)):
+ctas_list = [int(a) for a in sys.argv[2:]] or [_raw.lib().mxf_potrf_dag_ctas(0)]
+for ctas, (name, fn) in [(c, nf) for c in ctas_list for nf in (('one', one), ('two concurrent', both))]:
+    _raw.lib().mxf_potrf_dag_ctas(ctas)          # CTAs per matrix of the persistent dataflow kernel (captured with the graph)
     main.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(main):
         fn()
@@ -44,4 +46,5 @@ for name, fn in (('one', one), ('two concurrent', both)):
         gr.replay()
     b.record()
     torch.cuda.synchronize()
-    print('%s: %.1f us per replay (in place on an already factored matrix: timing only)' % (name, 1e3 * a.elapsed_time(b) / 50))
+    print('ctas/matrix %d  %s: %.1f us per replay (in place on an already factored matrix: timing only)' % (
+        ctas, name, 1e3 * a.elapsed_time(b) / 50))
