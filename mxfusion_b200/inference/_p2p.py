@@ -25,13 +25,17 @@ class PeerBucket(object):
         data_bytes = ((n * esz + 15) // 16) * 16
         flag_bytes = int(_lib.lib().mxf_allreduce_p2p_flag_bytes())
         self.n, self.dtype, self.flag_off = int(n), dtype, data_bytes
-        self.buf = symm.empty((data_bytes + flag_bytes) // esz, dtype=dtype, device=device)
+        self.flag_bytes, self.esz = flag_bytes, esz
+        # two flag regions: the early exchange of one segment may still be in flight when the exchange of the rest starts
+        self.buf = symm.empty((data_bytes + 2 * flag_bytes) // esz, dtype=dtype, device=device)
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, group)
         ptrs = list(self.handle.buffer_ptrs)
         if len(ptrs) != self.world or int(ptrs[self.rank]) != self.buf.data_ptr():
             raise InferenceError("symmetric memory: unexpected peer pointer table")
-        self._ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in ptrs])
+        self._base = [int(p) for p in ptrs]
+        self._ptrs = (ctypes.c_void_p * self.world)(*self._base)
+        self._range_ptrs = {}
         self.grad = self.buf[:n]
         self.err = torch.zeros((1,), dtype=torch.int32, device=device)
         self.timeout_s = float(os.environ.get('MXF_P2P_TIMEOUT_S', '20'))
@@ -46,6 +50,20 @@ class PeerBucket(object):
                                                 float(scale), self.flag_off, self.timeout_s, _lib.ptr(self.err),
                                                 _lib.stream_ptr()), 'mxf_allreduce_p2p')
         return self.grad
+
+    def all_reduce_range_(self, off, n, slot=0, scale=1.0):
+        """The same on elements [off, off + n) only (off * element size a multiple of 16); `slot` selects the flag region, so
+        that two exchanges of disjoint ranges may overlap in time.  Every rank must issue the same sequence of calls."""
+        if (off * self.esz) % 16 != 0 or off < 0 or n < 0 or off + n > self.n or slot not in (0, 1):
+            raise InferenceError("all_reduce_range_: bad range (%d, %d)" % (off, n))
+        ptrs = self._range_ptrs.get(off)
+        if ptrs is None:
+            ptrs = (ctypes.c_void_p * self.world)(*[b + off * self.esz for b in self._base])
+            self._range_ptrs[off] = ptrs
+        flag_rel = self.flag_off + slot * self.flag_bytes - off * self.esz
+        _lib.check(_lib.lib().mxf_allreduce_p2p(_lib.dtype_code(self.buf), ptrs, self.rank, self.world, int(n), float(scale),
+                                                flag_rel, self.timeout_s, _lib.ptr(self.err), _lib.stream_ptr()),
+                   'mxf_allreduce_p2p')
 
     def check(self):
         if int(self.err.item()) != 0:

@@ -71,6 +71,18 @@ class Stepper(object):
         self.early_reduce_enabled = os.environ.get('MXF_DP_EARLY', '0') == '1' and self.p2p is None and \
             (self.in_graph or not self.use_graph)
         self._early, self._early_segment = None, None
+        # Peer-memory exchange: the gradient of the LAST segment of the bucket (the largest parameters are laid out last:
+        # qU_cov_W is 93 % of the SVGP bucket) is copied into the bucket and exchanged on `comm` as soon as the backward pass
+        # has formed it; the kernel adjoints that follow hide its transfer AND the wait for the slowest rank.  Only the small
+        # remainder is exchanged at the end of the step.  MXF_DP_EARLY=0 disables.
+        self._peer_early_seg, self._peer_early_ok, self._peer_early_probe = None, False, None
+        if self.p2p is not None and os.environ.get('MXF_DP_EARLY', '1') != '0':
+            segs = [sg for sg in params._segments]
+            total = params.gflat.numel()
+            last = max(segs, key=lambda sg: sg[2]) if segs else None
+            if last is not None and last[4] == 0 and 2 * last[3] >= total and \
+                    sum(1 for sg in segs if sg[3] == last[3]) == 1 and (last[2] * params.gflat.element_size()) % 16 == 0:
+                self._peer_early_seg, self._peer_early_ok = (last[2], last[3]), True
         self.n_calls = 0
         self.launches_per_step = None    # library kernels launched by one forward+backward (counted on an eager step)
 
@@ -83,6 +95,20 @@ class Stepper(object):
         self.comm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        self._early = (t.data_ptr(), t.numel())
+
+    def _peer_early(self, t):
+        """The peer-memory twin of _early_reduce: copy the freshly formed gradient into its bucket segment and start the
+        exchange of that segment on `comm` (forked from the stream the gradient was formed on)."""
+        if self._early is not None or not self._peer_early_ok or t.numel() != self._peer_early_seg[1]:
+            return
+        off, n = self._peer_early_seg
+        self.p2p.buf[off:off + n].copy_(t.reshape(-1))
+        if self._peer_early_probe is None and not torch.cuda.is_current_stream_capturing():
+            self._peer_early_probe = t.detach().clone()       # first eager step: checked against the leaf gradient below
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            self.p2p.all_reduce_range_(off, n, slot=1)
         self._early = (t.data_ptr(), t.numel())
 
     def _reduce_rest(self):
@@ -107,11 +133,16 @@ class Stepper(object):
             self._early, self._early_segment = None, None
             if self.world > 1 and self.comm is not None and self.early_reduce_enabled:
                 ops.set_early_reduce(self._early_reduce)
+            elif self.p2p is not None and self._peer_early_ok:
+                ops.set_early_reduce(self._peer_early)
             try:
                 loss, loss_for_gradient = self.executor(None, *self.static_in)
                 loss_for_gradient.backward()
             finally:
                 ops.set_early_reduce(None)
+            if self.p2p is not None:
+                self._pack_and_exchange_peer()
+                return loss.detach().reshape(())
             if self._early is not None:
                 torch.cuda.current_stream().wait_stream(self.comm)          # the reduced values are packed below
                 for _, p, off, n, k, _ in self.params._segments:
@@ -127,11 +158,36 @@ class Stepper(object):
         loss_for_gradient.backward()
         return loss.detach().reshape(())
 
+    def _pack_and_exchange_peer(self):
+        """End of a data-parallel step on the peer-memory path: pack the gradients into the symmetric bucket, exchange what
+        has not been exchanged yet, update.  Inside the captured graph when there is one."""
+        p, cur = self.params, torch.cuda.current_stream()
+        early = self._early is not None
+        if early and isinstance(self._peer_early_probe, torch.Tensor):
+            # one-time check (first eager step): the tensor handed to the hook IS the parameter's whole gradient (a parameter
+            # used by a second factor would receive further contributions after the hook ran)
+            off, n = self._peer_early_seg
+            leaf = [(q.tleaf if k == 1 else q.tensor).grad for _, q, o, _, k, _ in p._segments if o == off][0]
+            self._peer_early_ok = leaf is not None and torch.equal(leaf.reshape(-1), self._peer_early_probe.reshape(-1))
+            self._peer_early_probe = False
+            if not self._peer_early_ok:
+                cur.wait_stream(self.comm)                    # the early exchange must be over before the segment is rewritten
+                early = False
+        if early:
+            off, n = self._peer_early_seg
+            p.pack_grads_(out=self.p2p.grad, skip_offset=off)
+            if off > 0:
+                self.p2p.all_reduce_range_(0, off, slot=0)
+            cur.wait_stream(self.comm)
+        else:
+            p.pack_grads_(out=self.p2p.grad)
+            self.p2p.all_reduce_()
+        self._apply(self.p2p.grad)
+
     def _update(self):
         p = self.params
         if self.p2p is not None:
-            self._apply(self.p2p.all_reduce_())
-            return
+            return                                            # done inside _fwd_bwd (_pack_and_exchange_peer)
         if self.world > 1:
             if self.fused:
                 self._reduce_rest()

@@ -220,10 +220,11 @@ class InferenceParameters(object):
             if p.tleaf is not None:
                 p.tleaf.grad = None
 
-    def pack_grads_(self, out=None):
-        """`out`: a bucket other than `gflat` (the data-parallel step packs straight into peer-mapped memory)."""
+    def pack_grads_(self, out=None, skip_offset=None):
+        """`out`: a bucket other than `gflat` (the data-parallel step packs straight into peer-mapped memory);
+        `skip_offset`: the segment starting there is left alone (its gradient was written -- and exchanged -- earlier)."""
         from .. import ops
-        seg = self._segments
+        seg = [s for s in self._segments if skip_offset is None or s[2] != skip_offset]
         grads = [(p.tleaf if k == 1 else p.tensor).grad for _, p, _, _, k, _ in seg]
         ops.R.params_pack_grads(self.flat, self.gflat if out is None else out, grads, [s[2] for s in seg], [s[3] for s in seg],
                                 [s[4] for s in seg])
