@@ -380,3 +380,33 @@ def test_sgd_optimizer_takes_plain_gradient_steps(mf):
     np.testing.assert_allclose(step, step2, rtol=1e-6)        # same gradient, twice the step
     with pytest.raises(InferenceError, match='sgd'):
         infr2.run(X=X, Y=Y, optimizer='rmsprop', learning_rate=1e-3, max_iter=1)
+
+
+def test_pack_grads_can_leave_one_segment_alone(mf):
+    """The data-parallel step exchanges the gradient of the last bucket segment early (inference/_stepper.py): the final
+    gradient gather must then skip that segment and still write every other one."""
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    m, X, Y = gp_notebook_model(mf)
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]))
+    infr.initialize(X=X.shape, Y=Y.shape)
+    ex = infr.inference_algorithm.create_executor(data_def=infr.observed_variable_UUIDs, params=infr.params,
+                                                  var_ties=infr.params.var_ties)
+    p = infr.params
+    p.refresh_leaves()
+    p.setup_fused_transforms(ex._var_trans)
+    ex.pretransformed = p._fused_uuids
+    p.transform_all_()
+    p.clear_leaf_grads()
+    loss, lg = ex(None, torch.tensor(X), torch.tensor(Y))
+    lg.backward()
+    full = torch.full_like(p.gflat, 7.0)
+    p.pack_grads_(out=full)
+    segs = [s for s in p._segments if (s[1].tleaf if s[4] == 1 else s[1].tensor).grad is not None]
+    assert len(segs) >= 2
+    skip = segs[-1]
+    part = torch.full_like(p.gflat, 7.0)
+    p.pack_grads_(out=part, skip_offset=skip[2])
+    assert bool((part[skip[2]:skip[2] + skip[3]] == 7.0).all())
+    keep = torch.ones_like(part, dtype=torch.bool)
+    keep[skip[2]:skip[2] + skip[3]] = False
+    np.testing.assert_array_equal(part[keep].numpy(), full[keep].numpy())
