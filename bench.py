@@ -635,6 +635,10 @@ def main():
             'launches_per_step': int(launches_per_step), 'final_loss': loss, 'final_loss_e2e': loss2,
             'peaks': pk_kind}
     line['config']['gradient_exchange'] = getattr(st, 'exchange', 'single')
+    # the same throughput as data rows per second and as seconds per pass over the N rows
+    line['rows_per_s'] = value * BATCH
+    line['seconds_per_pass_over_N'] = N_ROWS / (value * BATCH)
+    line['e2e']['rows_per_s'] = e2e * BATCH
     if strong is not None:
         line['strong_scaling'] = strong
     if world == 1:
