@@ -9,7 +9,8 @@
 // a quarter of a 16-byte shared store: the kernel is back on the HBM roofline.
 //
 // Structure (persistent, one CTA per SM, 10 warps):
-//   * a CTA owns one (sample, 512-column group) and walks row tiles of 128 rows t = blockIdx.x, + gridDim.x, ...
+//   * a CTA owns one (sample, 512-column group) -- 256-column groups when 512-wide ones would leave SMs idle -- and walks row
+//     tiles of 128 rows t = blockIdx.x, + gridDim.x, ...
 //   * the scaled column vectors b' = c x2 / l of its 512 columns sit in shared memory for the CTA's lifetime as TWO K-major
 //     128B-swizzled operand tiles of 256 rows; a row is [hi (8 KS floats) | lo (8 KS floats)]: the tf32 head and the
 //     remainder of the 3xTF32 split share one 128-byte swizzle row (KS = 1 for D <= 8, 2 for D <= 16);
@@ -22,6 +23,8 @@
 //     kernel does, writes the 32 x 32 block into a 128B-swizzled staging buffer (conflict-free 16-byte shared stores) and
 //     one lane issues the TMA store (cp.async.bulk.tensor, bulk-group completion, two staging buffers per warp).
 //     Ragged edges (N % 128, N2 % 32) are clipped by the TMA unit (N2 % 4 == 0 required: it clips 16-byte chunks).
+//   * SYM (X2 == X): the diagonal gets the exact kernel value at r2 = 0 plus `diag_add + diag_const` (the `+ eye * noise`,
+//     `+ eye * jitter` of gp_regression.py:55-60 / svgp_regression.py:70-72), exactly as the streaming kernel does.
 #pragma once
 #include "tc_common.cuh"
 
