@@ -113,3 +113,35 @@ def test_full_size_step_is_finite_and_decreases(cuda):
     assert np.mean(ls[-5:]) < np.mean(ls[:5])
     import mxfusion_b200 as mf
     mf.config.DEFAULT_DTYPE = 'float32'
+
+
+def test_inference_save_load_round_trip_on_gpu(cuda, mf64, tmp_path):
+    """Inference.save / load (inference.py:179-310) with the parameters living on the device: a freshly built inference of
+    the same topology gets the trained values back (on the device) and reproduces the loss through the real kernels."""
+    from tests.test_host_api import gp_notebook_model
+    from mxfusion_b200.inference import GradBasedInference, MAP
+    m, X, Y = gp_notebook_model(mf64)
+    infr = GradBasedInference(inference_algorithm=MAP(model=m, observed=[m.X, m.Y]))
+    infr.initialize(X=X.shape, Y=Y.shape)
+    infr.run(X=X, Y=Y, max_iter=15, learning_rate=0.05)
+    Xt, Yt = torch.tensor(X, device=cuda), torch.tensor(Y, device=cuda)
+    loss, _ = infr.create_executor()(None, Xt, Yt)
+    path = str(tmp_path / 'inference.zip')
+    infr.save(path)
+    m2, _, _ = gp_notebook_model(mf64)
+    infr2 = GradBasedInference(inference_algorithm=MAP(model=m2, observed=[m2.X, m2.Y]))
+    infr2.initialize(X=X.shape, Y=Y.shape)
+    before, _ = infr2.create_executor()(None, Xt, Yt)
+    assert abs(float(before) - float(loss)) > 1e-3
+    infr2.load(path)
+    after, _ = infr2.create_executor()(None, Xt, Yt)
+    np.testing.assert_allclose(float(after), float(loss), rtol=1e-10)
+    for a, b in ((m.kernel.variance, m2.kernel.variance), (m.kernel.lengthscale, m2.kernel.lengthscale),
+                 (m.noise_var, m2.noise_var)):
+        got, want = infr2.params[b], infr.params[a]
+        assert got.is_cuda
+        np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().cpu().numpy(), rtol=1e-12)
+    # training continues from the loaded state on the device
+    infr2.run(X=X, Y=Y, max_iter=5, learning_rate=0.05)
+    later, _ = infr2.create_executor()(None, Xt, Yt)
+    assert float(later) < float(after)
