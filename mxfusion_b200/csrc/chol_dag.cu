@@ -496,9 +496,10 @@ __device__ __forceinline__ void acc_to_plain(float* P, const float (&acc)[4][4],
 
 // Shared memory: bufX | bufY (one swizzled tile each) | bufO (one tile: an accumulator turned operand).  The diagonal
 // ticket's plain [A; I] buffer (128 x LDP) follows them.
-// One CTA per SM (the request is padded past half of the SM's shared memory): a diagonal ticket is the critical path of
-// the whole factorisation and a single warp carries most of it -- a co-resident CTA busy with tile products takes half of
-// its issue slots (measured: 20k -> see profiles/r2_potrf_dataflow.md).  The bulk tiles have slack to spare.
+// A diagonal ticket is the critical path of the whole factorisation and a single warp carries most of it -- a co-resident
+// CTA busy with tile products takes issue slots from it (diagonal block ~20k cycles against ~17k alone, see
+// profiles/r2_potrf_dataflow.md).  The kernel is therefore launched with ONE CTA per SM per matrix (dag_launch), but built
+// for two per SM (83 KB, 128 registers) so that two factorisations on two streams overlap.
 constexpr size_t DG_SMEM_USED = sizeof(float) * (3 * TILE_F + 2 * B * LDP) + 64;
 constexpr size_t DG_SMEM = DG_SMEM_USED;      // ~83 KB: two CTAs per SM (see the note above)
 
