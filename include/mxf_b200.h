@@ -330,6 +330,11 @@ int mxf_mlp_tanh_bwd(int dtype, int n_layers, const int* widths, const void* x, 
                      const void* const* W, const int64_t* sW, const void* const* b, const int64_t* sb,
                      const void* gout, void* const* dW, void* const* db, int S, int B, void* stream);
 
+/* Debug hooks (scripts/prof_dag.py, scripts/prof_diag.py): a device buffer of int64 that the potrf kernels fill with
+ * clock64 / globaltimer stamps per phase; NULL switches the stamps off (the default).  Not part of the drop-in surface. */
+int mxf_debug_set_prof(void* dev_ptr);
+int mxf_debug_set_dag_prof(void* dev_ptr);
+
 /* Tuning knob of the single-launch dataflow potrf (f32, n <= 1024): CTAs per matrix of the persistent kernel (default 148 =
  * one per SM, so that two factorisations issued on two streams are both fully resident).  Returns the previous value;
  * ctas <= 0 only queries. */
