@@ -32,6 +32,8 @@ def _declare(lib):
         'mxf_kbuild_tc_threshold': (c_longlong, [c_longlong]),
         'mxf_kbuild_bwd_workspace_bytes': (z, [i, i, i, i, i]),
         'mxf_potrf_dag_ctas': (i, [i]),
+        'mxf_debug_set_prof': (i, [p]),
+        'mxf_debug_set_dag_prof': (i, [p]),
         'mxf_allreduce_p2p_flag_bytes': (z, []),
         'mxf_allreduce_p2p': (i, [i, p, i, i, l, d, z, d, p, p]),
         'mxf_kbuild_bwd': (i, [i, i, p, p, p, i, p, p, l, p, p, p, p, i, i, i, i, l, l, l, l, l, p, z, p]),
